@@ -1,0 +1,148 @@
+/*
+ * ni_b200 — C-ABI of the B200-native neural-imaging hot path (libni_b200.so).
+ *
+ * The reference (pkorus/neural-imaging) has NO FFI on this path: every operator below is a chain of TensorFlow ops
+ * issued from Python (models/*.py, helpers/tf_helpers.py, workflows/manipulation_classification.py). Each entry point
+ * therefore cites the reference Python code it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NI_ERR_* code otherwise; ni_last_error() has the message;
+ *   - all tensor pointers are DEVICE pointers to float32 NHWC data owned by the caller; no hidden allocation;
+ *   - `stream` is a cudaStream_t (passed as void* so that this header needs no CUDA include);
+ *   - functions are asynchronous w.r.t. the host (ordered on `stream`), except where stated;
+ *   - build target: sm_100a only. There is no CPU fallback.
+ */
+#ifndef NI_B200_H
+#define NI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ni_stream_t;
+
+#define NI_OK 0
+#define NI_ERR_ARG (-1)
+#define NI_ERR_CUDA (-2)
+#define NI_ERR_UNSUPPORTED (-3)
+
+const char* ni_last_error(void);
+int ni_version(void);
+int ni_device_arch(void);                    /* compute capability major*10+minor of the current device */
+unsigned long long ni_launch_count(void);    /* kernels launched by this library since the last reset */
+void ni_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ differentiable JPEG
+ * Replaces DifferentiableJPEG.call (models/jpeg.py:91-159) incl. Quantization (models/layers.py:118-136) in ONE kernel.
+ * x, y: (n,h,w,3) in [0,1]; h, w multiples of 8. q_luma/q_chroma: HOST pointers to 64 floats (jpeg_qtable,
+ * compression/jpeg_helpers.py:264-305), row-major [k][l]. mode: 0 'soft', 1 'sin', 2 'harmonic'.
+ * x_deq (optional, may be NULL): de-quantised coefficients (3*n*(h/8)*(w/8), 8, 8) in the reference block order
+ * ((n*3+c)*nb + by*(w/8)+bx)  — the second return value of DifferentiableJPEG.call (models/jpeg.py:159).
+ * Algorithmic HBM bytes: 24 B/pixel forward, 36 B/pixel backward (X/Q recomputed from x, nothing saved). */
+int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h, int w, const float* q_luma, const float* q_chroma,
+                 int mode, ni_stream_t stream);
+int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, int h, int w, const float* q_luma,
+                 const float* q_chroma, int mode, ni_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ manipulations
+ * helpers/tf_helpers.py:68-184. All on (n,h,w,3). */
+/* manipulation_sharpen (tf_helpers.py:156-184): filt9 = HOST 3x3 filter applied to H and V; S takes tap [2,2]. */
+int ni_manip_sharpen_fwd(const float* x, float* y, int n, int h, int w, const float* filt9, ni_stream_t stream);
+/* manipulation_gaussian (tf_helpers.py:113-125): REFLECT pad k/2, depth-wise k x k filter (HOST, k*k floats), clip.
+ * mask (optional, n*h*w bytes): bit c set where channel c of the un-clipped output lies in [0,1] (clip_by_value grad). */
+int ni_manip_gaussian_fwd(const float* x, float* y, unsigned char* mask, int n, int h, int w, const float* filt, int k,
+                          int clip, ni_stream_t stream);
+int ni_manip_gaussian_bwd(const float* dy, const unsigned char* mask, float* dx, int n, int h, int w, const float* filt, int k,
+                          float scale, int accumulate, ni_stream_t stream);
+/* tf.image.resize(method='bilinear') (TF2 half-pixel centres, no antialias) used by manipulation_resample
+ * (tf_helpers.py:68-76) and run_downsampling 'bilinear' (workflows/manipulation_classification.py:238). */
+int ni_resize_bilinear_fwd(const float* x, float* y, int n, int ih, int iw, int oh, int ow, int clip, ni_stream_t stream);
+int ni_resize_bilinear_bwd(const float* dy, float* dx_zeroed, int n, int ih, int iw, int oh, int ow, float scale, ni_stream_t stream);
+/* manipulation_awgn (tf_helpers.py:79-82). noise: optional injected N(0,1) tensor; NULL = on-device Philox4x32-10(seed). */
+int ni_manip_awgn_fwd(const float* x, const float* noise, float* y, int n, int h, int w, float strength,
+                      unsigned long long seed, ni_stream_t stream);
+int ni_manip_awgn_bwd(const float* x, const float* noise, const float* dy, float* dx, int n, int h, int w, float strength,
+                      unsigned long long seed, int accumulate, ni_stream_t stream);
+/* manipulation_gamma (tf_helpers.py:85-88) */
+int ni_manip_gamma_fwd(const float* x, float* y, int n, int h, int w, float strength, ni_stream_t stream);
+int ni_manip_gamma_bwd(const float* x, const float* dy, float* dx, int n, int h, int w, float strength, int accumulate,
+                       ni_stream_t stream);
+/* manipulation_median (tf_helpers.py:91-110), k odd */
+int ni_manip_median_fwd(const float* x, float* y, int n, int h, int w, int k, ni_stream_t stream);
+int ni_manip_median_bwd(const float* x, const float* dy, float* dx_accum, int n, int h, int w, int k, ni_stream_t stream);
+/* tf.nn.avg_pool k x k stride k SAME (workflows/manipulation_classification.py:235) */
+int ni_avgpool_fwd(const float* x, float* y, int n, int h, int w, int k, ni_stream_t stream);
+int ni_avgpool_bwd(const float* dy, float* dx, int n, int h, int w, int k, ni_stream_t stream);
+int ni_axpy(float* y, const float* x, float a, long long n, ni_stream_t stream);   /* y += a*x */
+
+/* ------------------------------------------------------------------------------------------------ convolutions
+ * Keras Conv2D / Conv2DTranspose / Dense of the reference models (models/pipelines.py:190-218,
+ * models/forensics.py:65-90, models/compression.py:219-266). NHWC activations, HWIO weights (kh,kw,cin,cout). */
+enum { NI_ACT_NONE = 0, NI_ACT_LEAKY_RELU = 1, NI_ACT_RELU = 2, NI_ACT_TANH = 3, NI_ACT_SIGMOID = 4, NI_ACT_CLIP01 = 5 };
+enum { NI_MODE_PLAIN = 0, NI_MODE_BLOCK2 = 1 };
+enum { NI_PAD_ZERO = 0, NI_PAD_SYMMETRIC = 1, NI_PAD_REFLECT = 2 };
+
+typedef struct ni_conv_desc {
+    int n, h, w;             /* logical input: batch, height, width */
+    int cin, cout;
+    int kh, kw;
+    int stride;              /* 1 or 2 */
+    int pad_t, pad_l;        /* zero padding before (TF SAME rule computed by the caller) */
+    int oh, ow;              /* logical output size */
+    int in_pitch, in_coff;   /* physical channel pitch and first channel of the input buffer (concat-free skips) */
+    int out_pitch, out_coff;
+    int in_mode;             /* NI_MODE_BLOCK2: input read through tf.nn.space_to_depth(2) of a (n,2h,2w,cin/4) buffer */
+    int out_mode;            /* NI_MODE_BLOCK2: output written through tf.nn.depth_to_space(2) into (n,2oh,2ow,cout/4) */
+    int act;                 /* fused after bias (fprop) */
+    float act_alpha;
+    int accumulate;          /* out += result */
+    int bias_mod;            /* > 0: bias index = co % bias_mod (Conv2DTranspose as 1x1 conv + depth_to_space) */
+    int pad_mode;            /* NI_PAD_* index mapping of out-of-range taps (fprop, wgrad) */
+} ni_conv_desc;
+
+/* Dispatchers: tcgen05 implicit GEMM where the layer is a dense contraction, FP32 SIMT otherwise. */
+int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
+int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w_t /* (kh,kw,cout,cin) */, float* dx, ni_stream_t stream);
+int ni_conv2d_wgrad(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+/* The SIMT implementations, callable directly (tests compare the two paths on the device). */
+int ni_conv2d_fprop_simt(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
+int ni_conv2d_dgrad_simt(const ni_conv_desc* d, const float* dy, const float* w_t, float* dx, ni_stream_t stream);
+int ni_conv2d_wgrad_simt(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+int ni_weight_transpose_io(const float* w, float* w_t, int taps, int cin, int cout, ni_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ other layers */
+/* MaxPool2D 2x2 (SAME in UNet models/pipelines.py:197, VALID in FAN models/forensics.py:70) */
+int ni_maxpool2_fwd(const float* x, float* y, int n, int h, int w, int c, int same, int x_pitch, int x_coff, int y_pitch,
+                    int y_coff, ni_stream_t stream);
+int ni_maxpool2_bwd(const float* x, const float* dy, const float* add_or_null, float* dx, int n, int h, int w, int c, int same,
+                    int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff, int dx_pitch, int dx_coff,
+                    ni_stream_t stream);
+/* dy <- dy * act'(y) in place and dbias = column sums (Keras layer activation + bias gradients) */
+int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, int h, int w, int c, int y_pitch, int y_coff, int y_mode,
+                    int dy_pitch, int dy_coff, int dy_mode, int act, float alpha, int bias_mod, ni_stream_t stream);
+/* GlobalAveragePooling2D (models/forensics.py:79) */
+int ni_gap_fwd(const float* x, float* y, int n, int hw, int c, ni_stream_t stream);
+int ni_gap_bwd(const float* dy, float* dx, int n, int hw, int c, ni_stream_t stream);
+/* softmax + SparseCategoricalCrossentropy on probabilities, Keras eager semantics (models/forensics.py:90,94) */
+int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* loss_sum, float* dlogits, int m, int c,
+                  float gscale, ni_stream_t stream);
+/* tf_helpers.mse / mae (helpers/tf_helpers.py:31-36): kind 0 = L2, 1 = L1 */
+int ni_image_loss(const float* a, const float* b, float* acc, long long n, int kind, ni_stream_t stream);
+int ni_image_loss_grad(const float* a, const float* b, float* da, long long n, int kind, float scale, int accumulate,
+                       ni_stream_t stream);
+/* ConstrainedConv2D filter normalisation (models/layers.py:45-53) and its backward */
+int ni_constrained_filter_fwd(const float* k, float* nf, int ksize, int channels, float strength, ni_stream_t stream);
+int ni_constrained_filter_bwd(const float* k, const float* dnf, float* dk, int ksize, int channels, float strength, ni_stream_t stream);
+/* gradient of tf.pad(SYMMETRIC|REFLECT): fold the padded-domain gradient back (models/layers.py:56) */
+int ni_pad_fold(const float* dpad, float* dx, int n, int h, int w, int c, int pad, int mode, int accumulate, ni_stream_t stream);
+/* tf.keras.optimizers.Adam.apply_gradients on a flat buffer (workflows/manipulation_classification.py:156,279-283);
+ * also replaces the host-side NaN scan (:281): *nonfinite_flag |= 1 if any gradient is NaN/Inf. */
+int ni_adam_keras(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  long long step, float gscale, int* nonfinite_flag, ni_stream_t stream);
+int ni_fill(float* p, float value, long long n, ni_stream_t stream);
+int ni_affine(const float* x, float* y, float a, float b, int clip, long long n, ni_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NI_B200_H */

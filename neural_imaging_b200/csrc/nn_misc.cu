@@ -1,0 +1,467 @@
+// Non-convolution layer kernels of the training path: max-pool, activation backward + bias gradient, global
+// average pooling, softmax + sparse categorical cross-entropy (Keras semantics), image losses, the constrained
+// residual filter normalisation (models/layers.py:45-53), mirrored-pad gradient folding, fused Keras-Adam.
+#include "conv_desc.h"
+#include "ni_common.cuh"
+#include "views.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+inline int grid_for(long long n) { return ni_cdiv(n, kT); }
+
+// ------------------------------------------------------------------ max pooling 2x2 stride 2 (SAME or VALID)
+// x: (n,h,w,c) with pitch/coff; y: (n,oh,ow,c) with pitch/coff. Channel-vectorised by 4 when possible.
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int h, int w, int c, int oh,
+                                   int ow, int xp, int xo, int yp, int yo) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    const long long total = (long long)n * oh * ow * c;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    long long t = i / c;
+    const int ox = (int)(t % ow); t /= ow;
+    const int oy = (int)(t % oh);
+    const int nn = (int)(t / oh);
+    float m = -INFINITY;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int sy = 2 * oy + a, sx = 2 * ox + b;
+            if (sy < h && sx < w) m = fmaxf(m, x[(((long long)nn * h + sy) * w + sx) * xp + xo + ch]);
+        }
+    y[(((long long)nn * oh + oy) * ow + ox) * yp + yo + ch] = m;
+}
+
+// dx[pixel] = (pixel is the first maximum of its window ? dy[window] : 0) + (add ? add[pixel] : 0)
+__global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ add,
+                                   float* __restrict__ dx, int n, int h, int w, int c, int oh, int ow, int xp, int xo,
+                                   int dyp, int dyo, int addp, int addo, int dxp, int dxo) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    const long long total = (long long)n * h * w * c;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    long long t = i / c;
+    const int px = (int)(t % w); t /= w;
+    const int py = (int)(t % h);
+    const int nn = (int)(t / h);
+    const int oy = py >> 1, ox = px >> 1;
+    float g = 0.f;
+    if (oy < oh && ox < ow) {
+        float m = -INFINITY; int arg = -1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int sy = 2 * oy + a, sx = 2 * ox + b;
+                if (sy < h && sx < w) {
+                    const float v = x[(((long long)nn * h + sy) * w + sx) * xp + xo + ch];
+                    if (v > m) { m = v; arg = a * 2 + b; }
+                }
+            }
+        if (arg == (py & 1) * 2 + (px & 1)) g = dy[(((long long)nn * oh + oy) * ow + ox) * dyp + dyo + ch];
+    }
+    const long long pix = ((long long)nn * h + py) * w + px;
+    if (add) g += add[pix * addp + addo + ch];
+    dx[pix * dxp + dxo + ch] = g;
+}
+
+// ------------------------------------------------------------------ activation backward (+ bias gradient)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float alpha) {
+    switch (act) {
+        case NI_ACT_LEAKY_RELU: return y > 0.f ? 1.f : alpha;
+        case NI_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case NI_ACT_TANH: return 1.f - y * y;
+        case NI_ACT_SIGMOID: return y * (1.f - y);
+        default: return 1.f;  // none; clip01 is straight-through in the ISPs / DCN (models/pipelines.py:223)
+    }
+}
+
+// dy <- dy * act'(y) (in place, skipped for ACT_NONE) and dbias[c] += sum_pixels dy, on LOGICAL (n,H,W,C) views.
+// blockDim = (32, 8): x over channels (coalesced), y over pixels; grid.x over channel groups, grid.y over pixel chunks.
+__global__ void act_bwd_bias_kernel(const float* __restrict__ y, float* __restrict__ dy, float* __restrict__ dbias,
+                                    long long npix, TensorView yv, TensorView dv, int act, float alpha,
+                                    int pix_per_block, int bias_mod) {
+    __shared__ float red[8][33];
+    const int c = dv.C;
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    const long long p0 = (long long)blockIdx.y * pix_per_block;
+    const long long p1 = min(p0 + (long long)pix_per_block, npix);
+    float s = 0.f;
+    if (ch < c) {
+        for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+            const int px = (int)(p % dv.W);
+            const long long t = p / dv.W;
+            const int py = (int)(t % dv.H), pn = (int)(t / dv.H);
+            const long long ad = view_addr(dv, pn, py, px, ch);
+            float g = dy[ad];
+            if (act != NI_ACT_NONE && act != NI_ACT_CLIP01) {
+                g *= act_grad_from_out(y[view_addr(yv, pn, py, px, ch)], act, alpha);
+                dy[ad] = g;
+            }
+            s += g;
+        }
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c && dbias) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tsum += red[k][threadIdx.x];
+        atomicAdd(dbias + (bias_mod > 0 ? ch % bias_mod : ch), tsum);
+    }
+}
+
+// ------------------------------------------------------------------ global average pooling (n,h,w,c) <-> (n,c)
+__global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c) {
+    const int n = blockIdx.x;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < hw; ++p) s += x[((long long)n * hw + p) * c + ch];
+        y[(long long)n * c + ch] = s / (float)hw;
+    }
+}
+__global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long total, int hw, int c) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    const long long n = i / ((long long)hw * c);
+    dx[i] = dy[n * c + ch] / (float)hw;
+}
+
+// ------------------------------------------------------------------ softmax + Keras SparseCategoricalCrossentropy
+// Forward: probs = softmax(logits); loss_i = -log(q_l / sum_k q_k), q = clip(p, 1e-7, 1-1e-7)  (models/forensics.py:94,
+// Keras backend.sparse_categorical_crossentropy with from_logits=False in eager mode). loss_sum accumulates sum_i loss_i.
+// Backward (fused, optional): dlogits = d(mean loss)/dlogits * gscale.
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* __restrict__ labels, float* __restrict__ probs,
+                                  float* __restrict__ loss_sum, float* __restrict__ dlogits, int m, int c, float gscale) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    float li = 0.f;
+    if (i < m) {
+        const float* z = logits + (long long)i * c;
+        float mx = -INFINITY;
+        for (int k = 0; k < c; ++k) mx = fmaxf(mx, z[k]);
+        float se = 0.f;
+        for (int k = 0; k < c; ++k) se += expf(z[k] - mx);
+        const float eps = 1e-7f;
+        float sq = 0.f;
+        for (int k = 0; k < c; ++k) {
+            const float pk = expf(z[k] - mx) / se;
+            if (probs) probs[(long long)i * c + k] = pk;
+            sq += fminf(fmaxf(pk, eps), 1.f - eps);
+        }
+        if (labels) {
+            const int l = labels[i];
+            const float pl = expf(z[l] - mx) / se;
+            const float ql = fminf(fmaxf(pl, eps), 1.f - eps);
+            li = -logf(ql / sq);
+            if (dlogits) {
+                // g_k = dL/dp_k = (q_k/sq - 1[k==l]) / p_k inside the clip range, else 0
+                float dot = 0.f;
+                for (int k = 0; k < c; ++k) {
+                    const float pk = expf(z[k] - mx) / se;
+                    const float qk = fminf(fmaxf(pk, eps), 1.f - eps);
+                    const float gk = (pk >= eps && pk <= 1.f - eps) ? (qk / sq - (k == l ? 1.f : 0.f)) / pk : 0.f;
+                    dot += gk * pk;
+                }
+                for (int k = 0; k < c; ++k) {
+                    const float pk = expf(z[k] - mx) / se;
+                    const float qk = fminf(fmaxf(pk, eps), 1.f - eps);
+                    const float gk = (pk >= eps && pk <= 1.f - eps) ? (qk / sq - (k == l ? 1.f : 0.f)) / pk : 0.f;
+                    dlogits[(long long)i * c + k] = pk * (gk - dot) * gscale;
+                }
+            }
+        }
+    }
+    if (loss_sum) {
+        // block reduce
+        __shared__ float red[kT / 32];
+        float v = li;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int k = 0; k < kT / 32; ++k) s += red[k];
+            atomicAdd(loss_sum, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ image losses (helpers/tf_helpers.py:31-36)
+// kind 0: L2 = mean((255a-255b)^2); kind 1: L1 = mean(|255a-255b|). acc[0] += sum of per-element terms.
+__global__ void image_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ acc,
+                                  long long n, int kind) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+        const float d = 255.f * a[i] - 255.f * b[i];
+        s += kind == 0 ? d * d : fabsf(d);
+    }
+    __shared__ float red[kT / 32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < kT / 32; ++k) t += red[k];
+        atomicAdd(acc, t);
+    }
+}
+// da (+)= scale * d loss / d a
+__global__ void image_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ da,
+                                       long long n, int kind, float scale, int accumulate) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= n) return;
+    const float d = 255.f * a[i] - 255.f * b[i];
+    const float g = (kind == 0 ? 2.f * 255.f * d : (d > 0.f ? 255.f : (d < 0.f ? -255.f : 0.f))) * scale / (float)n;
+    da[i] = accumulate ? da[i] + g : g;
+}
+
+// ------------------------------------------------------------------ constrained residual filter (models/layers.py:45-53)
+// k: trainable (5,5,3,3) HWIO. nf = s*k*(1-ind)/sum_{a,b,ci}(k*(1-ind))[co] - s*ind, ind = centre tap on the channel diagonal.
+__global__ void constrained_filter_fwd_kernel(const float* __restrict__ k, float* __restrict__ nf, int ks, int ch, float strength) {
+    __shared__ float df[16];
+    const int total = ks * ks * ch * ch;
+    if (threadIdx.x < ch) {
+        float s = 0.f;
+        for (int i = 0; i < ks * ks * ch; ++i) {
+            const int ci = i % ch, tap = i / ch;
+            const bool centre = (tap == (ks / 2) * ks + ks / 2) && ci == (int)threadIdx.x;
+            if (!centre) s += k[i * ch + threadIdx.x];
+        }
+        df[threadIdx.x] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int co = i % ch, ci = (i / ch) % ch, tap = i / (ch * ch);
+        const bool centre = (tap == (ks / 2) * ks + ks / 2) && ci == co;
+        nf[i] = centre ? -strength : strength * k[i] / df[co];
+    }
+}
+// dk_j = m_j * s * (g_j / D - (sum_i g_i k_i m_i) / D^2), per output channel
+__global__ void constrained_filter_bwd_kernel(const float* __restrict__ k, const float* __restrict__ dnf, float* __restrict__ dk,
+                                              int ks, int ch, float strength) {
+    __shared__ float df[16], dot[16];
+    const int total = ks * ks * ch * ch;
+    if (threadIdx.x < ch) {
+        float s = 0.f, d = 0.f;
+        for (int i = 0; i < ks * ks * ch; ++i) {
+            const int ci = i % ch, tap = i / ch;
+            const bool centre = (tap == (ks / 2) * ks + ks / 2) && ci == (int)threadIdx.x;
+            if (!centre) { s += k[i * ch + threadIdx.x]; d += k[i * ch + threadIdx.x] * dnf[i * ch + threadIdx.x]; }
+        }
+        df[threadIdx.x] = s; dot[threadIdx.x] = d;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int co = i % ch, ci = (i / ch) % ch, tap = i / (ch * ch);
+        const bool centre = (tap == (ks / 2) * ks + ks / 2) && ci == co;
+        dk[i] = centre ? 0.f : strength * (dnf[i] / df[co] - dot[co] / (df[co] * df[co]));
+    }
+}
+
+// ------------------------------------------------------------------ mirrored-pad gradient folding
+// dpad: (n, h+2p, w+2p, c) gradient w.r.t. the padded tensor; dx[pixel] = sum of dpad over all padded aliases.
+__global__ void pad_fold_kernel(const float* __restrict__ dpad, float* __restrict__ dx, int n, int h, int w, int c, int pad,
+                                int mode, int accumulate) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    const long long total = (long long)n * h * w * c;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    long long t = i / c;
+    const int px = (int)(t % w); t /= w;
+    const int py = (int)(t % h);
+    const int nn = (int)(t / h);
+    int uy[3], ux[3], ny = 0, nx = 0;
+    uy[ny++] = py; ux[nx++] = px;
+    if (mode == NI_PAD_SYMMETRIC) {
+        if (py <= pad - 1) uy[ny++] = -py - 1;
+        if (py >= h - pad) uy[ny++] = 2 * h - 1 - py;
+        if (px <= pad - 1) ux[nx++] = -px - 1;
+        if (px >= w - pad) ux[nx++] = 2 * w - 1 - px;
+    } else {
+        if (py >= 1 && py <= pad) uy[ny++] = -py;
+        if (py <= h - 2 && 2 * (h - 1) - py <= h - 1 + pad) uy[ny++] = 2 * (h - 1) - py;
+        if (px >= 1 && px <= pad) ux[nx++] = -px;
+        if (px <= w - 2 && 2 * (w - 1) - px <= w - 1 + pad) ux[nx++] = 2 * (w - 1) - px;
+    }
+    const int ph = h + 2 * pad, pw = w + 2 * pad;
+    float s = 0.f;
+    for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) s += dpad[(((long long)nn * ph + uy[a] + pad) * pw + ux[b] + pad) * c + ch];
+    dx[i] = accumulate ? dx[i] + s : s;
+}
+
+// ------------------------------------------------------------------ fused Keras Adam on a flat parameter buffer
+// m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= lr_t * m / (sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) (host-computed).
+// gscale multiplies the gradient first (1/world_size after the sum all-reduce). Non-finite gradients raise *flag and
+// leave the parameter untouched (the reference raises on NaN gradients, workflows/manipulation_classification.py:281).
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr_t, float b1, float b2, float eps, float gscale, int* __restrict__ flag) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * gscale;
+    if (!isfinite(gi)) { if (flag) atomicOr(flag, 1); return; }
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.f - b2);
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// y = a*x + b (elementwise), optional clip to [0,1]
+__global__ void affine_kernel(const float* __restrict__ x, float* __restrict__ y, float a, float b, int clip, long long n) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i < n) { const float v = fmaf(a, x[i], b); y[i] = clip ? ni_clamp01(v) : v; }
+}
+
+}  // namespace
+
+extern "C" int ni_maxpool2_fwd(const float* x, float* y, int n, int h, int w, int c, int same, int x_pitch, int x_coff,
+                               int y_pitch, int y_coff, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0 && h > 0 && w > 0 && c > 0, "ni_maxpool2_fwd: invalid arguments");
+    const int oh = same ? (h + 1) / 2 : h / 2, ow = same ? (w + 1) / 2 : w / 2;
+    NI_REQUIRE(oh > 0 && ow > 0, "ni_maxpool2_fwd: input smaller than the pooling window");
+    if (n == 0) return NI_OK;
+    maxpool_fwd_kernel<<<grid_for((long long)n * oh * ow * c), kT, 0, st>>>(x, y, n, h, w, c, oh, ow, x_pitch, x_coff, y_pitch, y_coff);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_maxpool2_bwd(const float* x, const float* dy, const float* add, float* dx, int n, int h, int w, int c,
+                               int same, int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff,
+                               int dx_pitch, int dx_coff, cudaStream_t st) {
+    NI_REQUIRE(x && dy && dx && n >= 0 && h > 0 && w > 0 && c > 0, "ni_maxpool2_bwd: invalid arguments");
+    const int oh = same ? (h + 1) / 2 : h / 2, ow = same ? (w + 1) / 2 : w / 2;
+    if (n == 0) return NI_OK;
+    maxpool_bwd_kernel<<<grid_for((long long)n * h * w * c), kT, 0, st>>>(x, dy, add, dx, n, h, w, c, oh, ow, x_pitch, x_coff,
+                                                                       dy_pitch, dy_coff, add_pitch, add_coff, dx_pitch, dx_coff);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// Logical (n,h,w,c) views of the layer output y and its gradient dy (pitch/coff/mode as in ni_conv_desc):
+// dy <- dy * act'(y) in place; dbias[c] (or dbias[c % bias_mod] when bias_mod > 0) = sum over pixels. dbias may be null.
+extern "C" int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, int h, int w, int c, int y_pitch, int y_coff,
+                               int y_mode, int dy_pitch, int dy_coff, int dy_mode, int act, float alpha, int bias_mod,
+                               cudaStream_t st) {
+    NI_REQUIRE(dy && n >= 0 && h > 0 && w > 0 && c > 0, "ni_act_bwd_bias: invalid arguments");
+    NI_REQUIRE(y || act == NI_ACT_NONE || act == NI_ACT_CLIP01, "ni_act_bwd_bias: activation backward needs the layer output");
+    const int nb = bias_mod > 0 ? bias_mod : c;
+    if (dbias) NI_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * nb, st));
+    const long long npix = (long long)n * h * w;
+    if (npix == 0) return NI_OK;
+    if (!dbias && (act == NI_ACT_NONE || act == NI_ACT_CLIP01)) return NI_OK;
+    const int cgroups = ni_cdiv(c, 32);
+    long long chunks = (4LL * ni_num_sms() + cgroups - 1) / cgroups;
+    if (chunks > (npix + 63) / 64) chunks = (npix + 63) / 64;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    const int ppb = (int)((npix + chunks - 1) / chunks);
+    dim3 grid(cgroups, ni_cdiv(npix, ppb));
+    TensorView yv{h, w, c, y_pitch, y_coff, y_mode}, dv{h, w, c, dy_pitch, dy_coff, dy_mode};
+    act_bwd_bias_kernel<<<grid, dim3(32, 8), 0, st>>>(y, dy, dbias, npix, yv, dv, act, alpha, ppb, bias_mod);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_gap_fwd(const float* x, float* y, int n, int hw, int c, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0 && hw > 0 && c > 0, "ni_gap_fwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    gap_fwd_kernel<<<n, 256, 0, st>>>(x, y, hw, c);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+extern "C" int ni_gap_bwd(const float* dy, float* dx, int n, int hw, int c, cudaStream_t st) {
+    NI_REQUIRE(dy && dx && n >= 0 && hw > 0 && c > 0, "ni_gap_bwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    const long long total = (long long)n * hw * c;
+    gap_bwd_kernel<<<grid_for(total), kT, 0, st>>>(dy, dx, total, hw, c);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// probs / loss_sum / dlogits / labels may each be null. *loss_sum accumulates the SUM of per-sample losses
+// (caller zeroes it and divides by m); dlogits = gscale * d(mean loss)/dlogits requires gscale to include 1/m.
+extern "C" int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* loss_sum, float* dlogits, int m,
+                             int c, float gscale, cudaStream_t st) {
+    NI_REQUIRE(logits && m >= 0 && c > 0, "ni_softmax_ce: invalid arguments");
+    NI_REQUIRE(labels || (!loss_sum && !dlogits), "ni_softmax_ce: loss / gradient need labels");
+    if (m == 0) return NI_OK;
+    softmax_ce_kernel<<<ni_cdiv(m, kT), kT, 0, st>>>(logits, labels, probs, loss_sum, dlogits, m, c, gscale);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// *acc += sum_i term_i (caller zeroes and divides by n). kind: 0 = L2 (mse of 255-scaled images), 1 = L1.
+extern "C" int ni_image_loss(const float* a, const float* b, float* acc, long long n, int kind, cudaStream_t st) {
+    NI_REQUIRE(a && b && acc && n >= 0 && (kind == 0 || kind == 1), "ni_image_loss: invalid arguments");
+    if (n == 0) return NI_OK;
+    int grid = ni_cdiv(n, kT * 8);
+    if (grid > 8 * ni_num_sms()) grid = 8 * ni_num_sms();
+    image_loss_kernel<<<grid, kT, 0, st>>>(a, b, acc, n, kind);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+extern "C" int ni_image_loss_grad(const float* a, const float* b, float* da, long long n, int kind, float scale, int accumulate,
+                                  cudaStream_t st) {
+    NI_REQUIRE(a && b && da && n >= 0 && (kind == 0 || kind == 1), "ni_image_loss_grad: invalid arguments");
+    if (n == 0) return NI_OK;
+    image_loss_grad_kernel<<<grid_for(n), kT, 0, st>>>(a, b, da, n, kind, scale, accumulate);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_constrained_filter_fwd(const float* k, float* nf, int ksize, int channels, float strength, cudaStream_t st) {
+    NI_REQUIRE(k && nf && ksize > 0 && (ksize & 1) && channels > 0 && channels <= 16, "ni_constrained_filter_fwd: invalid arguments");
+    constrained_filter_fwd_kernel<<<1, 256, 0, st>>>(k, nf, ksize, channels, strength);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+extern "C" int ni_constrained_filter_bwd(const float* k, const float* dnf, float* dk, int ksize, int channels, float strength,
+                                         cudaStream_t st) {
+    NI_REQUIRE(k && dnf && dk && ksize > 0 && (ksize & 1) && channels > 0 && channels <= 16, "ni_constrained_filter_bwd: invalid arguments");
+    constrained_filter_bwd_kernel<<<1, 256, 0, st>>>(k, dnf, dk, ksize, channels, strength);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_pad_fold(const float* dpad, float* dx, int n, int h, int w, int c, int pad, int mode, int accumulate,
+                           cudaStream_t st) {
+    NI_REQUIRE(dpad && dx && n >= 0 && h > 0 && w > 0 && c > 0 && pad >= 0, "ni_pad_fold: invalid arguments");
+    NI_REQUIRE(mode == NI_PAD_SYMMETRIC || mode == NI_PAD_REFLECT, "ni_pad_fold: mode must be symmetric (1) or reflect (2)");
+    NI_REQUIRE(pad <= (mode == NI_PAD_SYMMETRIC ? h : h - 1) && pad <= (mode == NI_PAD_SYMMETRIC ? w : w - 1), "ni_pad_fold: pad too large");
+    if (n == 0) return NI_OK;
+    pad_fold_kernel<<<grid_for((long long)n * h * w * c), kT, 0, st>>>(dpad, dx, n, h, w, c, pad, mode, accumulate);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_adam_keras(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                             float eps, long long step, float gscale, int* nonfinite_flag, cudaStream_t st) {
+    NI_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "ni_adam_keras: invalid arguments");
+    if (n == 0) return NI_OK;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+    adam_kernel<<<grid_for(n), kT, 0, st>>>(p, g, m, v, n, (float)lr_t, beta1, beta2, eps, gscale, nonfinite_flag);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_fill(float* p, float value, long long n, cudaStream_t st) {
+    NI_REQUIRE(p && n >= 0, "ni_fill: invalid arguments");
+    if (n == 0) return NI_OK;
+    fill_kernel<<<grid_for(n), kT, 0, st>>>(p, value, n);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_affine(const float* x, float* y, float a, float b, int clip, long long n, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0, "ni_affine: invalid arguments");
+    if (n == 0) return NI_OK;
+    affine_kernel<<<grid_for(n), kT, 0, st>>>(x, y, a, b, clip, n);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}

@@ -1,0 +1,163 @@
+"""JPEG compression models on the B200 path.
+
+`DifferentiableJPEG` : the differentiable codec (reference models/jpeg.py:45-159) as one fused CUDA kernel forward
+                       and one backward (csrc/djpeg.cu) instead of ~40 TensorFlow ops.
+`JPEG`               : the toolbox-facing wrapper (reference models/jpeg.py:162-285): quality randomisation, codec
+                       selection, `process(batch_x, quality=None, return_entropy=False)`.
+`differentiable_jpeg`: lazily-created shared instance (reference models/jpeg.py:38-42).
+"""
+import numpy as np
+
+from .. import ops
+from ..compression.jpeg_helpers import jpeg_qf_estimation, jpeg_qtable
+from ..helpers.utils import is_number
+from ..tensor import as_device, wrap
+from .tfmodel import TFModel
+
+_common_codec = None
+
+
+def is_valid_quality(quality):
+    if is_number(quality) and 1 <= quality <= 100:
+        return True
+    if hasattr(quality, '__getitem__') and len(quality) > 1 and all((1 <= x <= 100) for x in quality):
+        return True
+    return False
+
+
+def differentiable_jpeg(x, quality):
+    global _common_codec
+    if _common_codec is None:
+        _common_codec = JPEG(None, 'soft')
+    return _common_codec.process(x, quality)
+
+
+class DifferentiableJPEG(object):
+    """Callable model: ``y, X = model(x)`` with x (N,H,W,3) in [0,1]; X = de-quantised DCT coefficients
+    (3*N*H/8*W/8, 8, 8) in the reference block order."""
+
+    def __init__(self, quality=None, rounding_approximation='sin', rounding_approximation_steps=5, trainable=False):
+        if quality is not None and not is_valid_quality(quality):
+            raise ValueError('Invalid JPEG quality: requires int in [1,100] or an iterable with least 2 such numbers')
+        if rounding_approximation is not None and rounding_approximation not in ['sin', 'harmonic', 'soft']:
+            raise ValueError('Unsupported rounding approximation: {}'.format(rounding_approximation))
+        if rounding_approximation is None:
+            # the reference fails inside Quantization(None, ...) (models/layers.py:99-100)
+            raise ValueError('Unsupported quantization: {}'.format(rounding_approximation))
+        if trainable:
+            raise NotImplementedError('trainable quantisation tables are "under development" in the reference '
+                                      '(models/jpeg.py:58-62) and not part of the B200 path yet')
+        if is_number(quality):
+            self._q_mtx_luma, self._q_mtx_chroma = jpeg_qtable(quality, 0), jpeg_qtable(quality, 1)
+        else:
+            self._q_mtx_luma = np.ones((8, 8), dtype=np.float32)
+            self._q_mtx_chroma = np.ones((8, 8), dtype=np.float32)
+        self.quality = quality
+        self.trainable = trainable
+        self.rounding_approximation = rounding_approximation
+        self.rounding_approximation_steps = rounding_approximation_steps
+
+    def __call__(self, inputs, want_coeffs=True):
+        x = as_device(inputs)
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        out = ops.djpeg_fwd(x, self._q_mtx_luma, self._q_mtx_chroma, self.rounding_approximation, want_coeffs=want_coeffs)
+        if want_coeffs:
+            return wrap(out[0]), wrap(out[1])
+        return wrap(out)
+
+    call = __call__
+
+    def forward_into(self, x, y):
+        """x, y: device tensors (no conversion); used by the workflow's training step."""
+        return ops.djpeg_fwd(x, self._q_mtx_luma, self._q_mtx_chroma, self.rounding_approximation, out=y)
+
+    def backward(self, x, dy, dx=None):
+        return ops.djpeg_bwd(x, dy, self._q_mtx_luma, self._q_mtx_chroma, self.rounding_approximation, out=dx)
+
+
+class JPEG(TFModel):
+
+    def __init__(self, quality=None, codec='soft', trainable=False):
+        super().__init__()
+        if codec is not None and codec not in ['libjpeg', 'soft', 'sin', 'harmonic']:
+            raise ValueError('Unsupported codec version: {}'.format(codec))
+        self._model = None if codec == 'libjpeg' else DifferentiableJPEG(quality, codec, trainable=trainable)
+        self.codec = codec
+        self.quality = quality
+
+    @staticmethod
+    def loss(target, compressed, sample_weight=None):
+        """tf.keras.losses.MeanSquaredError()(a, b, sample_weight). The workflow passes the (NaN) entropy as the third
+        positional argument, which Keras interprets as sample_weight => NaN; reproduced."""
+        a, b = as_device(target), as_device(compressed)
+        if sample_weight is not None and is_number(sample_weight) and np.isnan(sample_weight):
+            return float('nan')
+        v = ops.image_loss(a, b, 'L2') / (255.0 * 255.0)
+        return wrap(v.reshape(())) if sample_weight is None else wrap(v.reshape(()) * float(sample_weight))
+
+    def reset_performance_stats(self):
+        self.performance = self._reset_performance(['entropy', 'ssim', 'psnr'])
+
+    @property
+    def parameters(self):
+        return []
+
+    def count_parameters(self):
+        return 0
+
+    def _draw_quality(self, quality):
+        quality = self.quality if quality is None else quality
+        if not is_valid_quality(quality):
+            raise ValueError('Invalid or unspecified JPEG quality!')
+        if hasattr(quality, '__getitem__') and len(quality) > 2:
+            return int(np.random.choice(quality))
+        if hasattr(quality, '__getitem__') and len(quality) == 2:
+            return int(np.random.randint(quality[0], quality[1]))
+        if is_number(quality) and 1 <= quality <= 100:
+            return int(quality)
+        raise ValueError('Invalid quality! {}'.format(quality))
+
+    def process(self, batch_x, quality=None, return_entropy=False):
+        quality = self._draw_quality(quality)
+        if self._model is None:
+            raise NotImplementedError("codec='libjpeg' (host-side PIL/imageio validation codec, reference "
+                                      "models/jpeg.py:227-233) is outside the B200 hot path")
+        y = self._with_quality(quality, lambda: self._model(batch_x, want_coeffs=False))
+        return (y, np.nan) if return_entropy else y
+
+    def _with_quality(self, quality, fn):
+        """Temporarily swap the tables like the reference (models/jpeg.py:235-243; not re-entrant)."""
+        m = self._model
+        if quality != self.quality:
+            old = m._q_mtx_luma, m._q_mtx_chroma
+            m._q_mtx_luma, m._q_mtx_chroma = jpeg_qtable(quality, 0), jpeg_qtable(quality, 1)
+            try:
+                return fn()
+            finally:
+                m._q_mtx_luma, m._q_mtx_chroma = old
+        return fn()
+
+    def __repr__(self):
+        if self._model is not None:
+            return 'JPEG(quality={},codec="{}",trainable={})'.format(self.quality, self.codec, self._model.trainable)
+        return 'JPEG(quality={},codec="{}")'.format(self.quality, self.codec)
+
+    def summary(self, quality=None):
+        return 'JPEG ({}) {}'.format(self.codec, self._quality_mode(quality))
+
+    def summary_compact(self, quality=None):
+        return 'JPEG ({}) {}'.format(self.codec, self._quality_mode(quality))
+
+    def estimate_qf(self, channel=0):
+        return jpeg_qf_estimation(self._model._q_mtx_luma, channel)
+
+    def _quality_mode(self, quality=None):
+        quality = quality or self.quality
+        if is_number(quality):
+            return 'QF={}'.format(quality)
+        if hasattr(quality, '__getitem__') and len(quality) == 2:
+            return 'QF~[{},{}]'.format(*quality)
+        if hasattr(quality, '__getitem__') and len(quality) > 2:
+            return 'QF~{{{}}}'.format(','.join(str(x) for x in quality))
+        return 'QF=?'

@@ -1,0 +1,224 @@
+"""Layer engine for the B200 path: flat parameter storage, convolution layers with explicit forward / backward
+(no autograd tape: the reference's tf.GradientTape chain is replaced by hand-ordered kernel launches), Keras-Adam.
+
+Layout conventions (TensorFlow's): activations NHWC, Conv2D kernels HWIO (kh, kw, cin, cout), Dense kernels
+(in, out) stored as (1, 1, in, out). Conv2DTranspose(2x2, stride 2) is stored as the equivalent 1x1 convolution
+(1, 1, cin, 4*cout) whose output goes through depth_to_space(2): W1x1[ci, (a*2+b)*cout + f] = K_keras[a, b, f, ci].
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_CLIP01, ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, MODE_BLOCK2, MODE_PLAIN, PAD_REFLECT,
+                   PAD_SYMMETRIC, PAD_ZERO, ConvDesc)
+from .tensor import device, empty, ptr, stream, zeros
+
+ACTIVATIONS = {None: ACT_NONE, 'none': ACT_NONE, 'leaky_relu': ACT_LEAKY_RELU, 'relu': ACT_RELU, 'tanh': ACT_TANH,
+               'sigmoid': ACT_SIGMOID, 'clip01': ACT_CLIP01}
+
+
+def same_padding(size, k, stride):
+    """TF SAME rule: (out, pad_before)."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return out, total // 2
+
+
+def glorot_uniform(rng, shape):
+    """Keras default kernel initializer; fans follow keras.initializers._compute_fans."""
+    receptive = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    fan_in, fan_out = shape[-2] * receptive, shape[-1] * receptive
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+class Param:
+    __slots__ = ('name', 'shape', 'init', 'trainable', 'offset', 'size', 'value', 'grad')
+
+    def __init__(self, name, shape, init, trainable):
+        self.name, self.shape, self.trainable = name, tuple(int(s) for s in shape), trainable
+        self.init = np.ascontiguousarray(np.broadcast_to(np.asarray(init, dtype=np.float32), self.shape))
+        self.size = int(np.prod(self.shape)) if self.shape else 1
+        self.offset, self.value, self.grad = None, None, None
+
+
+class ParamStore:
+    """All parameters of a model in ONE flat device buffer (+ one flat gradient buffer): Adam and the data-parallel
+    all-reduce are each a single launch over the flat buffers. Offsets are padded to 4 floats (16-byte alignment)."""
+
+    def __init__(self):
+        self.params = []
+        self.flat = self.gflat = self.frozen = None
+
+    def add(self, name, shape, init, trainable=True):
+        p = Param(name, shape, init, trainable)
+        self.params.append(p)
+        return p
+
+    def finalize(self):
+        for trainable in (True, False):
+            ps = [p for p in self.params if p.trainable == trainable]
+            off = 0
+            for p in ps:
+                p.offset = off
+                off += (p.size + 3) // 4 * 4
+            host = np.zeros((max(off, 4),), np.float32)
+            for p in ps:
+                host[p.offset:p.offset + p.size] = p.init.reshape(-1)
+            buf = torch.from_numpy(host).to(device())
+            if trainable:
+                self.flat, self.gflat = buf, torch.zeros_like(buf)
+            else:
+                self.frozen = buf
+            for p in ps:
+                p.value = buf[p.offset:p.offset + p.size].view(p.shape if p.shape else ())
+                p.grad = self.gflat[p.offset:p.offset + p.size].view(p.shape if p.shape else ()) if trainable else None
+        return self
+
+    @property
+    def trainable(self):
+        return [p for p in self.params if p.trainable]
+
+    def count(self):
+        return int(sum(p.size for p in self.trainable))
+
+    def state_dict(self):
+        return {p.name: p.value.detach().cpu().numpy().copy() for p in self.params}
+
+    def load_state_dict(self, state, strict=True):
+        for p in self.params:
+            if p.name not in state:
+                if strict:
+                    raise KeyError('missing parameter {}'.format(p.name))
+                continue
+            a = np.asarray(state[p.name], dtype=np.float32)
+            if tuple(a.shape) != p.shape:
+                raise ValueError('shape mismatch for {}: {} vs {}'.format(p.name, a.shape, p.shape))
+            p.value.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+
+
+class Conv2D:
+    """Keras Conv2D / Dense / Conv2DTranspose(2,2) with explicit fprop / bprop through libni_b200.so."""
+
+    def __init__(self, store, name, k, cin, cout, stride=1, padding='SAME', activation=None, use_bias=True, rng=None,
+                 kernel_init=None, bias_init=None, trainable=True, pad_mode=PAD_ZERO, alpha=0.2, bias_mod=0, explicit_pad=None):
+        self.name, self.k, self.cin, self.cout, self.stride = name, int(k), int(cin), int(cout), int(stride)
+        self.padding, self.act, self.alpha = padding, ACTIVATIONS[activation], float(alpha)
+        self.pad_mode, self.bias_mod, self.explicit_pad = pad_mode, int(bias_mod), explicit_pad
+        shape = (self.k, self.k, self.cin, self.cout)
+        if kernel_init is None:
+            kernel_init = glorot_uniform(rng, shape)
+        self.w = store.add(name + '/kernel', shape, kernel_init, trainable)
+        nb = self.bias_mod if self.bias_mod else self.cout
+        self.b = store.add(name + '/bias', (nb,), np.zeros((nb,), np.float32) if bias_init is None else bias_init,
+                           trainable) if use_bias else None
+        self._wt = None          # (kh,kw,cout,cin) copy for dgrad
+        self._bexp = None        # bias tiled to cout when bias_mod (transposed conv)
+
+    # ---- geometry
+    def out_hw(self, h, w):
+        if self.explicit_pad is not None:        # mirrored pad p then VALID conv: same spatial size for p = k//2
+            p = self.explicit_pad
+            return (h + 2 * p - self.k) // self.stride + 1, (w + 2 * p - self.k) // self.stride + 1
+        if self.padding == 'SAME':
+            return same_padding(h, self.k, self.stride)[0], same_padding(w, self.k, self.stride)[0]
+        return (h - self.k) // self.stride + 1, (w - self.k) // self.stride + 1
+
+    def desc(self, n, h, w, in_pitch=None, in_coff=0, out_pitch=None, out_coff=0, in_mode=MODE_PLAIN, out_mode=MODE_PLAIN,
+             accumulate=False, act=None):
+        oh, ow = self.out_hw(h, w)
+        if self.explicit_pad is not None:
+            pt = pl = self.explicit_pad
+        elif self.padding == 'SAME':
+            pt, pl = same_padding(h, self.k, self.stride)[1], same_padding(w, self.k, self.stride)[1]
+        else:
+            pt = pl = 0
+        cin_phys = self.cin // 4 if in_mode == MODE_BLOCK2 else self.cin
+        cout_phys = self.cout // 4 if out_mode == MODE_BLOCK2 else self.cout
+        d = ConvDesc()
+        d.n, d.h, d.w, d.cin, d.cout, d.kh, d.kw, d.stride = n, h, w, self.cin, self.cout, self.k, self.k, self.stride
+        d.pad_t, d.pad_l, d.oh, d.ow = pt, pl, oh, ow
+        d.in_pitch, d.in_coff = (cin_phys if in_pitch is None else in_pitch), in_coff
+        d.out_pitch, d.out_coff = (cout_phys if out_pitch is None else out_pitch), out_coff
+        d.in_mode, d.out_mode = in_mode, out_mode
+        d.act, d.act_alpha = (self.act if act is None else act), self.alpha
+        d.accumulate, d.pad_mode, d.bias_mod = int(accumulate), self.pad_mode, self.bias_mod
+        return d
+
+    def _bias_ptr(self):
+        return None if self.b is None else ptr(self.b.value)
+
+    # ---- compute
+    def fprop(self, x, y, d, weight=None):
+        L = _lib.lib()
+        L.ni_conv2d_fprop(ctypes.byref(d), ptr(x), ptr(self.w.value if weight is None else weight), self._bias_ptr(), ptr(y), stream())
+        return y
+
+    def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
+              dx_accumulate=False):
+        """Backward of fprop(x -> y) described by the forward descriptor `d`.
+
+        dy is modified in place (multiplied by the activation derivative). dW / db go to the flat gradient buffer
+        (or `dweight`). dy_addr / dx_addr = (pitch, coff, mode) of the gradient buffers when they are laid out
+        differently from y / x (default: same addressing as the forward tensors)."""
+        L = _lib.lib()
+        st = stream()
+        dyp, dyo, dym = dy_addr if dy_addr is not None else (d.out_pitch, d.out_coff, d.out_mode)
+        db = ptr(self.b.grad) if (self.b is not None and self.b.trainable) else None
+        if db is not None or d.act not in (ACT_NONE, ACT_CLIP01):
+            L.ni_act_bwd_bias(ptr(y), ptr(dy), db, d.n, d.oh, d.ow, d.cout, d.out_pitch, d.out_coff, d.out_mode,
+                              dyp, dyo, dym, d.act, d.act_alpha, self.bias_mod, st)
+        dd = ConvDesc()
+        ctypes.memmove(ctypes.byref(dd), ctypes.byref(d), ctypes.sizeof(ConvDesc))
+        dd.out_pitch, dd.out_coff, dd.out_mode = dyp, dyo, dym
+        dd.accumulate = 0
+        if self.w.trainable or dweight is not None:
+            L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(self.w.grad if dweight is None else dweight), st)
+        if need_dx:
+            if dx_addr is not None:
+                dd.in_pitch, dd.in_coff, dd.in_mode = dx_addr
+            dd.accumulate = int(dx_accumulate)
+            dd.pad_mode = PAD_ZERO
+            wv = self.w.value if weight is None else weight
+            if self._wt is None:
+                self._wt = empty((self.k, self.k, self.cout, self.cin))
+            L.ni_weight_transpose_io(ptr(wv), ptr(self._wt), self.k * self.k, self.cin, self.cout, st)
+            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(self._wt), ptr(dx), st)
+        return dx
+
+
+class AdamKeras:
+    """tf.keras.optimizers.Adam semantics (eps=1e-7 outside the bias correction) over flat parameter buffers
+    (reference workflows/manipulation_classification.py:156,279-283)."""
+
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), beta1, beta2, eps
+        self.iterations = 0
+        self._state = {}
+        self._flag = None
+
+    def apply(self, stores, gscale=1.0, check_finite=True):
+        L = _lib.lib()
+        self.iterations += 1
+        if self._flag is None:
+            self._flag = zeros((1,), torch.int32)
+        for s in stores:
+            key = s.flat.data_ptr()
+            if key not in self._state:
+                self._state[key] = (torch.zeros_like(s.flat), torch.zeros_like(s.flat))
+            m, v = self._state[key]
+            L.ni_adam_keras(ptr(s.flat), ptr(s.gflat), ptr(m), ptr(v), s.flat.numel(), self.lr, self.beta1, self.beta2, self.eps,
+                            self.iterations, gscale, ptr(self._flag), stream())
+        return self._flag
+
+    def nonfinite(self):
+        """Device->host read of the NaN/Inf flag raised by the fused Adam kernel (lazy check)."""
+        if self._flag is None:
+            return False
+        bad = bool(self._flag.item())
+        if bad:
+            self._flag.zero_()
+        return bad

@@ -1,0 +1,329 @@
+"""End-to-end acquisition / distribution workflow with manipulation classification on the B200 path:
+
+    raw -> (nip) -> rgb -> (N manipulations) -> [(downsample) ->] (compression) -> (forensics) -> class probabilities
+
+API mirror of reference workflows/manipulation_classification.py:14-328. The training step (reference :260-285,
+tf.GradientTape + Keras Adam) is an explicit forward / backward kernel sequence + one fused Adam launch per model;
+with torch.distributed initialised the batch is sharded by rank and the flat gradient buffers are all-reduced.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import _lib, nn, ops
+from ..models import forensics, jpeg, pipelines
+from ..tensor import Workspace, as_device, empty, ptr, stream, wrap, zeros
+
+
+class ManipulationClassification(object):
+
+    def __init__(self, nip_model, manipulations=None, distribution=None, fan_args=None, trainable=None,
+                 raw_patch_size=128, loss_metric='L2', seed=None):
+        if raw_patch_size < 16 or raw_patch_size > 512:
+            raise ValueError('The patch size ({}) looks incorrect, typical values should be >= 16 and <= 512'.format(raw_patch_size))
+        self._trainable = set() if trainable is None else set(trainable)
+        self._trainable.add('fan')
+        fan_args = dict(fan_args or {})        # the reference crashes on None (SURVEY 8b "footguns"); we accept it
+
+        if distribution is None:
+            self._distribution = {'downsampling': 'pool:2', 'compression': 'jpeg',
+                                  'compression_params': {'quality': 50, 'codec': 'soft'}}
+        else:
+            self._distribution = {}
+            self._distribution.update(distribution)
+
+        if ':' in nip_model:
+            nip_model, nip_pretrained_dirname = nip_model.split(':')
+        else:
+            nip_pretrained_dirname = None
+        if not (hasattr(pipelines, nip_model) and isinstance(getattr(pipelines, nip_model), type)
+                and issubclass(getattr(pipelines, nip_model), pipelines.NIPModel)):
+            raise ValueError('Invalid NIP model ({})! Available NIPs: ({})'.format(nip_model, pipelines.supported_models))
+        if loss_metric not in ['L2', 'L1', 'SSIM']:
+            raise ValueError('Invalid loss metric ({})!'.format(loss_metric))
+
+        self.nip = getattr(pipelines, nip_model)(loss_metric=loss_metric, patch_size=raw_patch_size, seed=seed)
+        if nip_pretrained_dirname is not None:
+            self.nip.load_model(nip_pretrained_dirname)
+
+        manipulations = manipulations or ['sharpen', 'resample', 'gaussian', 'jpeg']
+        self._strengths = {'sharpen': 1, 'resample': 50, 'gaussian': 0.83, 'jpeg': 80, 'awgn': 5.1, 'gamma': 3, 'median': 3}
+        self._strengths_range = {'sharpen': (0.25, 1.5), 'resample': (40, 90), 'gaussian': (0.5, 7), 'jpeg': (50, 90),
+                                 'awgn': (1, 5), 'gamma': (1, 5), 'median': (3, 9)}
+        requested = set()
+        for m in manipulations:
+            spec = m.split(':')
+            requested.add(spec[0])
+            if len(spec) > 1:
+                self._strengths[spec[0]] = float(spec[-1])
+        if any(x not in self._strengths.keys() for x in requested):
+            raise ValueError('Unsupported manipulation requested! Available: {}'.format(self._strengths.keys()))
+
+        makers = OrderedDict([('sharpen', ops.SharpenOp), ('resample', ops.ResampleOp), ('gaussian', ops.GaussianOp),
+                              ('jpeg', ops.JpegOp), ('awgn', ops.AwgnOp), ('gamma', ops.GammaOp), ('median', ops.MedianOp)])
+        self._ops = OrderedDict()
+        self._operations = OrderedDict()       # name -> callable(x, strength), as in the reference
+        self._forensics_classes = ['native']
+        for name, maker in makers.items():     # fixed order, as in the reference (:105-131)
+            if name in requested:
+                op = maker()
+                self._ops[name] = op
+                self._operations[name] = (lambda x, strength, _op=op: wrap(_op.forward(as_device(x), empty(as_device(x).shape), strength)))
+                self._forensics_classes.append('{}:{}'.format(name, self._strengths[name]))
+        assert len(self._forensics_classes) == self.n_classes
+
+        comp = self._distribution['compression']
+        if comp == 'jpeg':
+            self.codec = jpeg.JPEG(**self._distribution['compression_params'])
+        elif comp == 'dcn':
+            from ..models import compression
+            params = dict(self._distribution.get('compression_params') or {})
+            if 'dirname' in params:
+                self.codec = compression.TwitterDCN.restore(params['dirname'], key='codec') if params['dirname'] else compression.TwitterDCN()
+            else:
+                self.codec = compression.TwitterDCN(**params)
+        elif comp == 'none':
+            self.codec = None
+        else:
+            raise ValueError('Unsupported channel compression {}'.format(comp))
+        if 'dcn' in self._trainable and (self.codec is None or len(self.codec.parameters) == 0):
+            raise ValueError('The current codec does not appear to be trainable: {}!'.format(
+                None if self.codec is None else self.codec.class_name))
+
+        fan_input_patch = 2 * raw_patch_size // self.downsampling_factor
+        self.fan = forensics.FAN(n_classes=self.n_classes, patch_size=fan_input_patch, seed=seed, **fan_args)
+
+        self._stores = [self.fan._store]
+        if 'nip' in self._trainable and self.nip._store.trainable:
+            self._stores.append(self.nip._store)
+        if 'dcn' in self._trainable:
+            self._stores.append(self.codec._store)
+        self._parameters = [p for s in self._stores for p in (q.value for q in s.trainable)]
+        self._optimizer = nn.AdamKeras()
+        self._ws = Workspace()
+        self._labels = {}
+
+    # ------------------------------------------------------------------------------------------------ properties
+    @property
+    def n_classes(self):
+        return len(self._operations) + 1
+
+    @property
+    def downsampling_factor(self):
+        ds = self._distribution['downsampling']
+        if ds == 'none':
+            return 1
+        if ':' in ds:
+            return int(ds.split(':')[-1])
+        return 2
+
+    def is_trainable(self, model):
+        return model in self._trainable
+
+    @property
+    def trainable_models(self):
+        return tuple(x for x in self._trainable)
+
+    # ------------------------------------------------------------------------------------------------ forward pieces
+    def _draw_strengths(self, randomize, override=None):
+        override = override if override is not None else self._strengths
+        return OrderedDict((name, override[name] if not randomize else np.random.uniform(*self._strengths_range[name]))
+                           for name in self._ops)
+
+    def _manipulate(self, Y, strengths, out, training=False):
+        """Class-major stack [Y, op1(Y), op2(Y), ...] written slot by slot into `out` (no concat copy)."""
+        B = Y.shape[0]
+        ops.copy_into(out[:B], Y)
+        for i, (name, op) in enumerate(self._ops.items()):
+            op.forward(Y, out[(i + 1) * B:(i + 2) * B], strengths[name], training=training)
+        return out
+
+    def run_manipulations(self, batch_y, randomize=False, override=None):
+        Y = as_device(batch_y)
+        out = empty((self.n_classes * Y.shape[0],) + tuple(Y.shape[1:]))
+        return wrap(self._manipulate(Y, self._draw_strengths(randomize, override), out))
+
+    def manipulations_timing(self, batch_y):
+        Y = as_device(batch_y)
+        times = {}
+        for name, op in self._ops.items():
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            op.forward(Y, empty(Y.shape), self._strengths[name])
+            end.record()
+            end.synchronize()
+            times[name] = start.elapsed_time(end) / 1000.0
+        return times
+
+    def _downsample(self, m, out=None):
+        ds, factor = self._distribution['downsampling'], self.downsampling_factor
+        if ds.startswith('pool'):
+            return ops.avgpool_fwd(m, factor, out=out)
+        if ds == 'bilinear':
+            n, h, w = ops._nhw3(m)
+            s = h // factor                      # the reference uses shape[1] for both dims (:238)
+            y = empty((n, s, s, 3)) if out is None else out
+            _lib.lib().ni_resize_bilinear_fwd(ptr(m), ptr(y), n, h, w, s, s, 0, stream())
+            return y
+        if ds == 'none':
+            return m
+        raise ValueError('Unsupported channel down-sampling {}'.format(ds))
+
+    def run_downsampling(self, batch_y):
+        return wrap(self._downsample(as_device(batch_y)))
+
+    def run_compression(self, batch_y, return_entropy=False):
+        comp = self._distribution['compression']
+        if comp in ('jpeg', 'dcn'):
+            return self.codec.process(batch_y, return_entropy=return_entropy)
+        if comp == 'none':
+            return batch_y
+        raise ValueError('Unsupported channel compression {}'.format(comp))
+
+    def run_workflow(self, batch_x, augment=False, training=False):
+        """raw -> isp -> manipulations -> downsample -> compression -> fan. Returns (Y, c, C, entropy, probabilities)."""
+        batch_Y = self.nip.process(batch_x)
+        batch_m = self.run_manipulations(batch_Y, augment)
+        batch_c = self.run_downsampling(batch_m)
+        if self._distribution['compression'] == 'none':
+            batch_C, entropy = batch_c, np.nan
+        else:
+            batch_C, entropy = self.run_compression(batch_c, True)
+        probabilities = self.fan.process(batch_C)
+        return batch_Y, batch_c, batch_C, entropy, probabilities
+
+    def run_workflow_to_decisions(self, batch_x):
+        return self.run_workflow(batch_x)[-1].numpy().argmax(axis=1)
+
+    def run_rgb_to_fan(self, batch_Y):
+        batch_C = self.run_compression(self.run_downsampling(self.run_manipulations(batch_Y)))
+        return batch_C if isinstance(batch_C, np.ndarray) else batch_C.numpy()
+
+    def run_rgb_to_probabilities(self, batch_Y):
+        batch_C = self.run_compression(self.run_downsampling(self.run_manipulations(batch_Y)))
+        return self.fan.process(batch_C).numpy()
+
+    def _batch_labels(self, batch_size):
+        return np.concatenate([x * np.ones((batch_size,), dtype=np.int32) for x in range(self.n_classes)])
+
+    def _device_labels(self, batch_size):
+        if batch_size not in self._labels:
+            self._labels[batch_size] = as_device(self._batch_labels(batch_size), torch.int32)
+        return self._labels[batch_size]
+
+    # ------------------------------------------------------------------------------------------------ training step
+    def training_step(self, batch_x, batch_y, lambda_nip=0, lambda_dcn=0, augment=False, learning_rate=1e-4):
+        """One joint optimisation step. Returns (loss, {'ce','nip','dcn'}) like the reference (:260-285)."""
+        loss, parts = self.training_step_device(batch_x, batch_y, lambda_nip, lambda_dcn, augment, learning_rate)
+        if self._optimizer.nonfinite():
+            raise RuntimeError('∇ NaNs: non-finite gradients detected by the fused Adam kernel')
+        return loss, parts
+
+    def training_step_device(self, batch_x, batch_y, lambda_nip=0, lambda_dcn=0, augment=False, learning_rate=1e-4,
+                             grad_sync=None):
+        """The step without the host-side NaN check (no device->host sync). grad_sync(stores) is called between
+        backward and Adam (data-parallel all-reduce hook)."""
+        L, ws, s = _lib.lib(), self._ws, stream()
+        x = as_device(batch_x)
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        t = as_device(batch_y)
+        B = int(x.shape[0])
+        train_nip = 'nip' in self._trainable and bool(self.nip._store.trainable)
+        train_dcn = 'dcn' in self._trainable
+        comp = self._distribution['compression']
+        if comp == 'dcn':
+            return self._training_step_dcn(x, t, lambda_nip, lambda_dcn, augment, learning_rate, grad_sync)
+
+        # ---- forward
+        Y = self.nip._forward(x, save=train_nip)
+        strengths = self._draw_strengths(augment)
+        M = self.n_classes * B
+        m = ws.get('m', (M,) + tuple(Y.shape[1:]))
+        self._manipulate(Y, strengths, m, training=train_nip)
+        c = self._downsample(m, out=ws.get('c', (M, -(-Y.shape[1] // self.downsampling_factor), -(-Y.shape[2] // self.downsampling_factor), 3))
+                             if self._distribution['downsampling'].startswith('pool') else None)
+        if comp == 'jpeg':
+            C = ws.get('C', c.shape)
+            quality = self.codec._draw_quality(None)
+            self.codec._with_quality(quality, lambda: self.codec._model.forward_into(c, C))
+        else:
+            C, quality = c, None
+        labels = self._device_labels(B)
+        probs, loss_ce, dlogits = self.fan.forward_loss(C, labels)
+        acc = ws.get('loss_nip', (1,))
+        L.ni_fill(ptr(acc), 0.0, 1, s)
+        kind = 0 if self.nip.loss_metric == 'L2' else 1
+        L.ni_image_loss(ptr(Y), ptr(t), ptr(acc), Y.numel(), kind, s)
+
+        # ---- backward
+        dC = self.fan.backward(dlogits, need_dx=train_nip)
+        if train_nip:
+            if comp == 'jpeg':
+                dc = ws.get('dc', c.shape)
+                self.codec._with_quality(quality, lambda: self.codec._model.backward(c, dC, dc))
+            else:
+                dc = dC
+            dm = self._downsample_bwd(dc, m.shape, ws)
+            dY = ws.get('dY', Y.shape)
+            # dY = lambda_nip * d(nip loss)/dY + native slot + manipulation branches
+            L.ni_image_loss_grad(ptr(Y), ptr(t), ptr(dY), Y.numel(), kind, float(lambda_nip), 0, s)
+            L.ni_axpy(ptr(dY), ptr(dm[:B]), 1.0, dY.numel(), s)
+            for i, (name, op) in enumerate(self._ops.items()):
+                if op.has_grad:
+                    op.backward(Y, dm[(i + 1) * B:(i + 2) * B], dY, strengths[name])
+            self.nip._backward(dY)
+        if grad_sync is not None:
+            grad_sync(self._stores)
+        self._optimizer.lr = float(learning_rate)
+        self._optimizer.apply(self._stores, gscale=getattr(grad_sync, 'gscale', 1.0))
+
+        loss_ce_v = loss_ce / float(M)
+        loss_nip_v = acc / float(Y.numel())
+        loss = loss_ce_v + (float(lambda_nip) * loss_nip_v if 'nip' in self._trainable else 0.0)
+        loss_dcn = float('nan') if comp == 'jpeg' else 0.0    # Keras MSE with sample_weight = NaN entropy
+        return wrap(loss.reshape(())), {'ce': wrap(loss_ce_v.reshape(())), 'nip': wrap(loss_nip_v.reshape(())), 'dcn': loss_dcn}
+
+    def _downsample_bwd(self, dc, m_shape, ws):
+        ds, factor = self._distribution['downsampling'], self.downsampling_factor
+        if ds.startswith('pool'):
+            return ops.avgpool_bwd(dc, m_shape, factor, out=ws.get('dm', m_shape))
+        if ds == 'bilinear':
+            dm = ws.get('dm', m_shape)
+            L = _lib.lib()
+            L.ni_fill(ptr(dm), 0.0, dm.numel(), stream())
+            L.ni_resize_bilinear_bwd(ptr(dc), ptr(dm), m_shape[0], m_shape[1], m_shape[2], dc.shape[1], dc.shape[2], 1.0, stream())
+            return dm
+        return dc
+
+    def _training_step_dcn(self, x, t, lambda_nip, lambda_dcn, augment, learning_rate, grad_sync):
+        raise NotImplementedError('compression=dcn training path is under construction')
+
+    # ------------------------------------------------------------------------------------------------ summaries
+    def summary_compact(self):
+        return '{class_name}[{trainables}]: {nip} -> [{manips}] {pool}{codec}-> {fan}'.format(
+            class_name=type(self).__name__, nip=self.nip.class_name, manips=''.join([x[0] for x in self._forensics_classes]),
+            trainables=''.join([x[0] for x in self.trainable_models]),
+            pool='' if self._distribution['downsampling'] == 'none' else '-> {} '.format(self._distribution['downsampling']),
+            codec='' if self.codec is None else '-> {} '.format(self.codec.summary_compact()), fan='FAN')
+
+    def summary(self):
+        return '{class_name}[opt={trainables}]: {input} -> {nip} -> {n_ops} manipulations [{manips}] {pool}{codec}-> {fan}'.format(
+            class_name=type(self).__name__, input='(rgb)' if self.nip.x.shape[-1] == 3 else '(raw)', nip=self.nip.class_name,
+            n_ops=self.n_classes - 1, manips=''.join([x[0] for x in self._forensics_classes]),
+            trainables=''.join([x[0] for x in self.trainable_models]),
+            pool='' if self._distribution['downsampling'] == 'none' else '-> {} '.format(self._distribution['downsampling']),
+            codec='' if self.codec is None else '-> {} '.format(self.codec.summary_compact()),
+            fan='FAN -> (prob. {} classes)'.format(self.n_classes))
+
+    def details(self):
+        out = [self.summary()]
+        out.append('Input         : {} {}'.format(self.nip.x.shape, '(rgb)' if self.nip.x.shape[-1] == 3 else '(raw)'))
+        out.append('Camera ISP    : {}'.format(self.nip.summary()))
+        out.append('Manipulations : {} -> {}'.format(self.n_classes, self._forensics_classes))
+        out.append('Downsampling  : {}'.format(self._distribution['downsampling']))
+        out.append('Codec         : {}'.format('' if self.codec is None else self.codec.summary()))
+        out.append('Forensics     : {}'.format(self.fan.summary()))
+        out.append('Output        : {}'.format(self.fan.y.shape))
+        return '\n'.join(out)

