@@ -62,6 +62,11 @@ class NIError(RuntimeError):
     pass
 
 
+# Optional per-call profiler (bench.py installs one): an object with before(name, args) / after(name, args), used to
+# bracket every C-ABI call with CUDA events. None on the normal path.
+PROFILER = None
+
+
 class _Lib:
     def __init__(self):
         if not os.path.isfile(LIB_PATH):
@@ -84,9 +89,14 @@ class _Lib:
             return fn
 
         def checked(*args):
+            prof = PROFILER
+            if prof is not None:
+                prof.before(name, args)
             rc = fn(*args)
             if rc != 0:
                 raise NIError('{} failed ({}): {}'.format(name, rc, self._dll.ni_last_error().decode()))
+            if prof is not None:
+                prof.after(name, args)
             return rc
         checked.__name__ = name
         setattr(self, name, checked)

@@ -382,6 +382,7 @@ int set_smem(K kernel, size_t bytes) {
 
 extern "C" int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h, int w, const float* q_luma,
                             const float* q_chroma, int mode, cudaStream_t stream) {
+    if (n == 0) return NI_OK;
     NI_REQUIRE(x && y && q_luma && q_chroma, "ni_djpeg_fwd: null pointer");
     NI_REQUIRE(n >= 0 && h > 0 && w > 0 && h % 8 == 0 && w % 8 == 0,
                "ni_djpeg_fwd: H and W must be positive multiples of 8 (got %d x %d)", h, w);
@@ -410,6 +411,7 @@ extern "C" int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h
 
 extern "C" int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, int h, int w, const float* q_luma,
                             const float* q_chroma, int mode, cudaStream_t stream) {
+    if (n == 0) return NI_OK;
     NI_REQUIRE(x && dy && dx && q_luma && q_chroma, "ni_djpeg_bwd: null pointer");
     NI_REQUIRE(n >= 0 && h > 0 && w > 0 && h % 8 == 0 && w % 8 == 0,
                "ni_djpeg_bwd: H and W must be positive multiples of 8 (got %d x %d)", h, w);

@@ -70,8 +70,8 @@ class FAN(TFModel):
         self._out = nn.Conv2D(st, 'dense_out', 1, feat, self.n_classes, padding='VALID', rng=rng)
         st.finalize()
         self._ws = Workspace()
-        self._nf = empty((5, 5, 3, 3))        # normalised constrained filter
-        self._dnf = empty((5, 5, 3, 3))
+        self._nf = None if nn.HOST_ONLY else empty((5, 5, 3, 3))        # normalised constrained filter
+        self._dnf = None if nn.HOST_ONLY else empty((5, 5, 3, 3))
         self._saved = None
         self.optimizer = nn.AdamKeras()
 

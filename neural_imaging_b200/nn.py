@@ -35,6 +35,10 @@ def glorot_uniform(rng, shape):
     return rng.uniform(-limit, limit, size=shape).astype(np.float32)
 
 
+# bench.py's CPU-baseline leg sets this to build the models' initial weights without a GPU (specs only, no device buffers)
+HOST_ONLY = False
+
+
 class Param:
     __slots__ = ('name', 'shape', 'init', 'trainable', 'offset', 'size', 'value', 'grad')
 
@@ -59,6 +63,8 @@ class ParamStore:
         return p
 
     def finalize(self):
+        if HOST_ONLY:
+            return self
         for trainable in (True, False):
             ps = [p for p in self.params if p.trainable == trainable]
             off = 0

@@ -1,0 +1,203 @@
+"""GPU parity of the convolution entry points (fprop / dgrad / wgrad) against torch-CPU float64 convolutions."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_parity, rel_err
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n, h, w, cin, cout, k, stride, padding, act
+    (2, 16, 16, 4, 32, 3, 1, 'SAME', 'leaky_relu'),
+    (2, 16, 16, 32, 32, 3, 1, 'SAME', 'leaky_relu'),
+    (1, 12, 20, 3, 32, 5, 1, 'SAME', 'leaky_relu'),
+    (2, 16, 16, 32, 64, 5, 1, 'SAME', 'relu'),
+    (2, 8, 8, 64, 128, 3, 1, 'SAME', None),
+    (3, 16, 16, 3, 64, 5, 2, 'SAME', 'leaky_relu'),
+    (2, 16, 16, 64, 128, 5, 2, 'SAME', None),
+    (2, 9, 9, 16, 20, 3, 1, 'VALID', 'tanh'),
+    (4, 1, 1, 256, 5, 1, 1, 'VALID', None),
+    (2, 8, 8, 256, 256, 1, 1, 'VALID', 'sigmoid'),
+    (1, 16, 16, 32, 12, 3, 1, 'SAME', None),
+]
+
+
+def _mk(n, h, w, cin, cout, k, seed=0):
+    rs = np.random.RandomState(seed)
+    x = rs.normal(size=(n, h, w, cin)).astype(np.float32)
+    wgt = (rs.normal(size=(k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    b = rs.normal(size=(cout,)).astype(np.float32)
+    return x, wgt, b
+
+
+@pytest.mark.parametrize('case', CASES)
+@pytest.mark.parametrize('impl', ['dispatch', 'simt'])
+def test_conv_fwd_bwd(case, impl):
+    from neural_imaging_b200 import _lib, nn
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream
+    n, h, w, cin, cout, k, stride, padding, act = case
+    x, wgt, b = _mk(n, h, w, cin, cout, k)
+    st = nn.ParamStore()
+    conv = nn.Conv2D(st, 'c', k, cin, cout, stride=stride, padding=padding, activation=act, kernel_init=wgt, bias_init=b)
+    st.finalize()
+    L = _lib.lib()
+    d = conv.desc(n, h, w)
+    xd = as_device(x)
+    y = empty((n, d.oh, d.ow, cout))
+    fprop = L.ni_conv2d_fprop if impl == 'dispatch' else L.ni_conv2d_fprop_simt
+    fprop(ctypes.byref(d), ptr(xd), ptr(conv.w.value), ptr(conv.b.value), ptr(y), stream())
+    res = {}
+    rs = np.random.RandomState(1)
+    dy = rs.normal(size=tuple(y.shape)).astype(np.float32)
+    for dt in (torch.float64, torch.float32):
+        xt = torch.tensor(x, dtype=dt, requires_grad=True)
+        wt = torch.tensor(wgt, dtype=dt, requires_grad=True)
+        bt = torch.tensor(b, dtype=dt, requires_grad=True)
+        yt = R.ACT[act](R.conv2d(xt, wt, bt, stride, padding))
+        gx, gw, gb = torch.autograd.grad(yt, (xt, wt, bt), torch.tensor(dy, dtype=dt))
+        res[dt] = [t.detach().numpy() for t in (yt, gx, gw, gb)]
+    r64, r32 = res[torch.float64], res[torch.float32]
+    assert_parity(y.cpu().numpy(), r64[0], r32[0], tol=1e-5, what='y')
+    if impl == 'simt':
+        return
+    dyd = as_device(dy)
+    dx = empty(x.shape)
+    conv.bprop(xd, y, dyd, dx, d)
+    assert_parity(dx.cpu().numpy(), r64[1], r32[1], tol=1e-5, what='dx')
+    assert_parity(conv.w.grad.cpu().numpy(), r64[2], r32[2], tol=2e-5, what='dw')
+    assert_parity(conv.b.grad.cpu().numpy(), r64[3], r32[3], tol=2e-5, what='db')
+
+
+def test_pitch_offset_and_block2_addressing():
+    """Concat-free skip connections and Conv2DTranspose-as-1x1-conv + depth_to_space."""
+    from neural_imaging_b200 import _lib, nn
+    from neural_imaging_b200._lib import MODE_BLOCK2
+    from neural_imaging_b200.tensor import as_device, empty, zeros
+    n, h, w, cin, c = 2, 8, 8, 64, 32
+    rs = np.random.RandomState(2)
+    x = rs.normal(size=(n, h, w, cin)).astype(np.float32)
+    skip = rs.normal(size=(n, 2 * h, 2 * w, c)).astype(np.float32)
+    st = nn.ParamStore()
+    up = nn.Conv2D(st, 'up', 1, cin, 4 * c, padding='VALID', bias_mod=c,
+                   kernel_init=(rs.normal(size=(1, 1, cin, 4 * c)) / 8).astype(np.float32), bias_init=rs.normal(size=(c,)).astype(np.float32))
+    conv = nn.Conv2D(st, 'dc', 3, 2 * c, c, activation='leaky_relu', rng=rs)
+    st.finalize()
+    xd = as_device(x)
+    cat = zeros((n, 2 * h, 2 * w, 2 * c))
+    cat[..., c:] = as_device(skip)
+    du = up.desc(n, h, w, out_pitch=2 * c, out_coff=0, out_mode=MODE_BLOCK2)
+    up.fprop(xd, cat, du)
+    dc = conv.desc(n, 2 * h, 2 * w)
+    y = conv.fprop(cat, empty((n, 2 * h, 2 * w, c)), dc)
+    # oracle
+    P = {k_: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k_, v in st.state_dict().items()}
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    upt = R.conv2d_transpose_2x2(xt, P['up/kernel'], P['up/bias'])
+    catt = torch.cat((upt, torch.tensor(skip, dtype=torch.float64)), dim=3)
+    yt = R.leaky_relu(R.conv2d(catt, P['dc/kernel'], P['dc/bias']))
+    assert_parity(cat.cpu().numpy(), catt.detach().numpy(), tol=1e-5, what='parity')
+    assert_parity(y.cpu().numpy(), yt.detach().numpy(), tol=1e-5, what='parity')
+    dy = rs.normal(size=tuple(y.shape)).astype(np.float32)
+    grads = torch.autograd.grad(yt, [xt] + list(P.values()), torch.tensor(dy, dtype=torch.float64))
+    gref = dict(zip(['x'] + list(P.keys()), [g.numpy() for g in grads]))
+    dcat = empty(tuple(cat.shape))
+    conv.bprop(cat, y, as_device(dy), dcat, dc)
+    dx = empty(x.shape)
+    up.bprop(xd, None, dcat, dx, du, dy_addr=(2 * c, 0, MODE_BLOCK2))
+    assert_parity(dx.cpu().numpy(), gref['x'], tol=1e-5, what='parity')
+    for p in st.params:
+        assert_parity(p.grad.cpu().numpy(), gref[p.name], tol=2e-5, what='parity')
+
+
+def test_mirrored_pad_conv_and_fold():
+    """ConstrainedConv2D-style conv: SYMMETRIC pad folded into the addressing; dgrad via padded-domain + ni_pad_fold."""
+    from neural_imaging_b200 import _lib, nn
+    from neural_imaging_b200._lib import PAD_REFLECT, PAD_SYMMETRIC, PAD_ZERO
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream
+    L = _lib.lib()
+    for mode, name in ((PAD_SYMMETRIC, 'SYMMETRIC'), (PAD_REFLECT, 'REFLECT')):
+        n, h, w, c, k = 2, 12, 10, 3, 5
+        rs = np.random.RandomState(3)
+        x = rs.normal(size=(n, h, w, c)).astype(np.float32)
+        wgt = rs.normal(size=(k, k, c, c)).astype(np.float32)
+        st = nn.ParamStore()
+        conv = nn.Conv2D(st, 'c', k, c, c, padding='VALID', use_bias=False, pad_mode=mode, explicit_pad=k // 2, kernel_init=wgt)
+        st.finalize()
+        d = conv.desc(n, h, w)
+        xd = as_device(x)
+        y = conv.fprop(xd, empty((n, h, w, c)), d)
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        wt = torch.tensor(wgt, dtype=torch.float64, requires_grad=True)
+        yt = R.conv2d(R.tf_pad(xt, k // 2, name), wt, padding='VALID')
+        assert_parity(y.cpu().numpy(), yt.detach().numpy(), tol=1e-5, what='parity')
+        dy = rs.normal(size=(n, h, w, c)).astype(np.float32)
+        gx, gw = torch.autograd.grad(yt, (xt, wt), torch.tensor(dy, dtype=torch.float64))
+        dyd = as_device(dy)
+        L.ni_conv2d_wgrad(ctypes.byref(d), ptr(xd), ptr(dyd), ptr(conv.w.grad), stream())
+        assert_parity(conv.w.grad.cpu().numpy(), gw.numpy(), tol=1e-5, what='parity')
+        p = k // 2
+        dd = conv.desc(n, h + 2 * p, w + 2 * p)
+        dd.pad_t = dd.pad_l = 0
+        dd.oh, dd.ow, dd.pad_mode = h, w, PAD_ZERO
+        wtt = empty((k, k, c, c))
+        L.ni_weight_transpose_io(ptr(conv.w.value), ptr(wtt), k * k, c, c, stream())
+        dpad = empty((n, h + 2 * p, w + 2 * p, c))
+        L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dyd), ptr(wtt), ptr(dpad), stream())
+        dx = empty((n, h, w, c))
+        L.ni_pad_fold(ptr(dpad), ptr(dx), n, h, w, c, p, mode, 0, stream())
+        assert_parity(dx.cpu().numpy(), gx.numpy(), tol=1e-5, what='parity')
+
+
+def test_maxpool_gap_softmax_adam():
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream, zeros
+    L = _lib.lib()
+    rs = np.random.RandomState(4)
+    for same, (h, w) in ((1, (8, 8)), (0, (8, 8)), (1, (7, 9)), (0, (7, 9))):
+        n, c = 2, 6
+        x = rs.normal(size=(n, h, w, c)).astype(np.float32)
+        oh, ow = ((h + 1) // 2, (w + 1) // 2) if same else (h // 2, w // 2)
+        xd, y = as_device(x), empty((n, oh, ow, c))
+        L.ni_maxpool2_fwd(ptr(xd), ptr(y), n, h, w, c, same, c, 0, c, 0, stream())
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        yt = R.max_pool(xt, same)
+        assert np.array_equal(y.cpu().numpy(), yt.detach().numpy().astype(np.float32))
+        dy = rs.normal(size=(n, oh, ow, c)).astype(np.float32)
+        add = rs.normal(size=(n, h, w, c)).astype(np.float32)
+        g, = torch.autograd.grad(yt, xt, torch.tensor(dy, dtype=torch.float64))
+        dx, dyd, addd = empty((n, h, w, c)), as_device(dy), as_device(add)
+        L.ni_maxpool2_bwd(ptr(xd), ptr(dyd), ptr(addd), ptr(dx), n, h, w, c, same, c, 0, c, 0, c, 0, c, 0, stream())
+        assert_parity(dx.cpu().numpy(), g.numpy() + add, tol=1e-6, what='maxpool bwd')
+    # softmax + Keras sparse CE (+ gradient)
+    m, c = 37, 5
+    z = (rs.normal(size=(m, c)) * 4).astype(np.float32)
+    z[0] = [40, 0, 0, 0, -40]          # saturated probabilities exercise the 1e-7 clip
+    lab = rs.randint(0, c, size=(m,)).astype(np.int32)
+    zd, probs, loss, dz, labd = as_device(z), empty((m, c)), zeros((1,)), empty((m, c)), as_device(lab, torch.int32)
+    L.ni_softmax_ce(ptr(zd), ptr(labd), ptr(probs), ptr(loss), ptr(dz), m, c, 1.0 / m, stream())
+    zt = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    pt = torch.softmax(zt, dim=1)
+    lt = R.sparse_categorical_crossentropy(lab, pt)
+    g, = torch.autograd.grad(lt, zt)
+    assert_parity(probs.cpu().numpy(), pt.detach().numpy(), tol=1e-6, what='parity')
+    assert abs(float(loss.item()) / m - float(lt)) < 1e-5 * max(1.0, abs(float(lt)))
+    assert_parity(dz.cpu().numpy(), g.numpy(), tol=1e-4, what='parity')
+    # Keras Adam, 3 steps
+    nparam = 1003
+    p0 = rs.normal(size=(nparam,)).astype(np.float32)
+    pd, md, vd, flag = as_device(p0.copy()), zeros((nparam,)), zeros((nparam,)), zeros((1,), torch.int32)
+    pt_, mt, vt = [torch.tensor(p0, dtype=torch.float64)], [torch.zeros(nparam, dtype=torch.float64)], [torch.zeros(nparam, dtype=torch.float64)]
+    for t in range(1, 4):
+        g = rs.normal(size=(nparam,)).astype(np.float32)
+        gd = as_device(g)
+        L.ni_adam_keras(ptr(pd), ptr(gd), ptr(md), ptr(vd), nparam, 1e-3, 0.9, 0.999, 1e-7, t, 1.0, ptr(flag), stream())
+        R.adam_keras_step(pt_, [torch.tensor(g, dtype=torch.float64)], mt, vt, t, 1e-3)
+    assert rel_err(pd.cpu().numpy(), pt_[0].numpy()) < 1e-6 and int(flag.item()) == 0
+    gbad = np.zeros((nparam,), np.float32); gbad[5] = np.nan
+    gd = as_device(gbad)
+    L.ni_adam_keras(ptr(pd), ptr(gd), ptr(md), ptr(vd), nparam, 1e-3, 0.9, 0.999, 1e-7, 4, 1.0, ptr(flag), stream())
+    assert int(flag.item()) == 1

@@ -1,0 +1,164 @@
+"""GPU parity of the models (UNet, FAN) and of the joint training step against the CPU oracle restatement of
+models/pipelines.py:169-230, models/forensics.py:29-125 and workflows/manipulation_classification.py:260-285."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_parity, rel_err
+from oracle import ref_models as M
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(store):
+    return {p.name: p.grad.detach().cpu().numpy().copy() for p in store.trainable}
+
+
+def test_unet_forward_backward():
+    from neural_imaging_b200.models import pipelines
+    rs = np.random.RandomState(1234)
+    model = pipelines.UNet(patch_size=32, seed=1)
+    assert model.count_parameters() == 7763820
+    x = rs.uniform(size=(2, 32, 32, 4)).astype(np.float32)
+    t = rs.uniform(size=(2, 64, 64, 3)).astype(np.float32)
+    y = model.process(x).numpy()
+    state = model._store.state_dict()
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        P = M.to_params(state, dt)
+        yt = M.unet_forward(P, torch.tensor(x, dtype=dt))
+        loss = R.mse(yt, torch.tensor(t, dtype=dt))
+        g = torch.autograd.grad(loss, list(P.values()))
+        out[dt] = (yt.detach().numpy(), float(loss), {k: v.numpy() for k, v in zip(P.keys(), g)})
+    assert tuple(y.shape) == (2, 64, 64, 3)
+    assert_parity(y, out[torch.float64][0], out[torch.float32][0], tol=1e-5, what='UNet y')
+    # one training step: loss value + gradients (before Adam touches the weights, read them from the flat buffer)
+    loss = model.training_step(x, t, learning_rate=1e-4)
+    assert abs(float(loss.numpy()) - out[torch.float64][1]) < 1e-4 * out[torch.float64][1]
+    g = _grads(model._store)
+    for name, ref in out[torch.float64][2].items():
+        assert_parity(g[name], ref, out[torch.float32][2][name], tol=2e-5, slack=6.0, what='UNet grad ' + name)
+    # Keras-Adam update of every parameter
+    P = M.to_params(state, torch.float64, requires_grad=False)
+    ms = [torch.zeros_like(p) for p in P.values()]
+    vs = [torch.zeros_like(p) for p in P.values()]
+    R.adam_keras_step(list(P.values()), [torch.tensor(out[torch.float64][2][k]) for k in P], ms, vs, 1, 1e-4)
+    new = model._store.state_dict()
+    for k, p in P.items():
+        assert np.max(np.abs(new[k] - p.numpy())) < 2e-6, k     # |update| <= lr = 1e-4; allow 2% sign-noise on tiny grads
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(n_filters=8, n_convolutions=2, kernel=3, n_dense=2, use_gap=False, activation='relu')])
+def test_fan_forward_backward(kw):
+    from neural_imaging_b200.models import forensics
+    from neural_imaging_b200.tensor import as_device
+    rs = np.random.RandomState(99)
+    ps = 32
+    fan = forensics.FAN(n_classes=5, patch_size=ps, seed=3, **kw)
+    if not kw:
+        assert fan.count_parameters() == 1145382         # SURVEY Appendix A (5 classes)
+    m = 6
+    x = rs.uniform(size=(m, ps, ps, 3)).astype(np.float32)
+    labels = rs.randint(0, 5, size=(m,))
+    probs = fan.process(x).numpy()
+    state = fan._store.state_dict()
+    okw = dict(n_convolutions=kw.get('n_convolutions', 4), n_dense=kw.get('n_dense', 0), use_gap=kw.get('use_gap', True),
+               activation=kw.get('activation', 'leaky_relu'))
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        P = M.to_params(state, dt)
+        xt = torch.tensor(x, dtype=dt, requires_grad=True)
+        pt = M.fan_forward(P, xt, **okw)
+        loss = R.sparse_categorical_crossentropy(labels, pt)
+        g = torch.autograd.grad(loss, [xt] + list(P.values()))
+        out[dt] = (pt.detach().numpy(), float(loss), g[0].numpy(), {k: v.numpy() for k, v in zip(P.keys(), g[1:])})
+    assert_parity(probs, out[torch.float64][0], out[torch.float32][0], tol=1e-5, what='FAN probs')
+    assert np.array_equal(fan.process_and_decide(x), probs.argmax(axis=1))
+    assert abs(float(fan.loss(labels, probs).numpy()) - out[torch.float64][1]) < 1e-5
+    pr, loss, dlogits = fan.forward_loss(as_device(x), as_device(labels.astype(np.int32), torch.int32))
+    dx = fan.backward(dlogits, need_dx=True)
+    assert abs(float(loss.item()) / m - out[torch.float64][1]) < 1e-5 * max(1, out[torch.float64][1])
+    assert_parity(dx.cpu().numpy(), out[torch.float64][2], out[torch.float32][2], tol=2e-5, slack=6.0, what='FAN dx')
+    g = _grads(fan._store)
+    for name, ref in out[torch.float64][3].items():
+        assert_parity(g[name], ref, out[torch.float32][3][name], tol=2e-5, slack=6.0, what='FAN grad ' + name)
+
+
+@pytest.mark.parametrize('train_nip', [True, False])
+def test_joint_training_step(train_nip):
+    """ManipulationClassification.training_step: losses, every gradient and the Adam update vs the oracle."""
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    rs = np.random.RandomState(1234)
+    B, ps = 2, 32
+    flow = ManipulationClassification('UNet', trainable={'nip'} if train_nip else None, raw_patch_size=ps, seed=5)
+    assert flow.n_classes == 5 and flow._forensics_classes[0] == 'native'
+    x = rs.uniform(size=(B, ps, ps, 4)).astype(np.float32)
+    t = rs.uniform(size=(B, 2 * ps, 2 * ps, 3)).astype(np.float32)
+    s_nip, s_fan = flow.nip._store.state_dict(), flow.fan._store.state_dict()
+    # inference composition first (run_workflow returns Y, c, C, entropy, probs)
+    Y, c, C, ent, probs = flow.run_workflow(x)
+    assert np.isnan(ent) and tuple(C.shape) == (5 * B, ps, ps, 3) and tuple(probs.shape) == (5 * B, 5)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        Pn, Pf = M.to_params(s_nip, dt), M.to_params(s_fan, dt)
+        opt = {'t': 0, 'm': {}, 'v': {}}
+        losses, grads = M.training_step(Pn, Pf, opt, torch.tensor(x, dtype=dt), torch.tensor(t, dtype=dt), lambda_nip=0.1, lr=1e-4,
+                                        train_nip=train_nip)
+        with torch.no_grad():
+            Yt, ct, Ct, pt = M.workflow_forward(M.to_params(s_nip, dt, False), M.to_params(s_fan, dt, False), torch.tensor(x, dtype=dt))
+        res[dt] = (losses, grads, Pn, Pf, Yt.numpy(), ct.numpy(), Ct.numpy(), pt.numpy())
+    r64, r32 = res[torch.float64], res[torch.float32]
+    assert_parity(Y.numpy(), r64[4], r32[4], tol=1e-5, what='Y')
+    # rounding inside the two dJPEG stages: compare the bulk, allow isolated 8x8 blocks to flip a coefficient
+    for got, k in ((c.numpy(), 5), (C.numpy(), 6)):
+        assert np.mean(np.abs(got - r64[k]) > 1e-4) < 2e-3
+    loss, parts = flow.training_step(x, t, lambda_nip=0.1, learning_rate=1e-4)
+    assert abs(float(parts['ce'].numpy()) - r64[0]['ce']) < 2e-3 * r64[0]['ce']
+    assert abs(float(parts['nip'].numpy()) - r64[0]['nip']) < 1e-4 * r64[0]['nip']
+    assert np.isnan(parts['dcn'])
+    exp_loss = r64[0]['ce'] + (0.1 * r64[0]['nip'] if train_nip else 0)
+    assert abs(float(loss.numpy()) - exp_loss) < 2e-3 * exp_loss
+    gf = _grads(flow.fan._store)
+    for name, g in gf.items():
+        ref64, ref32 = r64[1]['fan/' + name].numpy(), r32[1]['fan/' + name].numpy()
+        e = rel_err(g, ref64)
+        assert e < max(5e-3, 4 * rel_err(ref32, ref64)), 'fan grad {} err {}'.format(name, e)
+    if train_nip:
+        gn = _grads(flow.nip._store)
+        for name, g in gn.items():
+            ref64, ref32 = r64[1]['nip/' + name].numpy(), r32[1]['nip/' + name].numpy()
+            e = rel_err(g, ref64)
+            assert e < max(2e-2, 4 * rel_err(ref32, ref64)), 'nip grad {} err {}'.format(name, e)
+    else:
+        assert float(np.abs(flow.nip._store.gflat.cpu().numpy()).max()) == 0.0
+        assert np.array_equal(flow.nip._store.state_dict()['ec11/kernel'], s_nip['ec11/kernel'])
+    # parameters moved by (at most) lr in the Adam direction
+    new_fan = flow.fan._store.state_dict()
+    moved = np.abs(new_fan['conv2d_0/kernel'] - s_fan['conv2d_0/kernel'])
+    assert 0 < moved.max() <= 1.01e-4
+
+
+def test_onet_rgb_training_and_api_surface():
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    rs = np.random.RandomState(7)
+    flow = ManipulationClassification('ONet', manipulations=['gaussian:1', 'jpeg:85', 'awgn', 'median'],
+                                      distribution={'downsampling': 'none', 'compression': 'jpeg',
+                                                    'compression_params': {'quality': (50, 90), 'codec': 'soft'}},
+                                      trainable={'nip'}, raw_patch_size=16, seed=2)
+    assert flow._forensics_classes == ['native', 'gaussian:1.0', 'jpeg:85.0', 'awgn:5.1', 'median:3']
+    y = rs.uniform(size=(3, 32, 32, 3)).astype(np.float32)
+    losses = []
+    for _ in range(3):
+        loss, parts = flow.training_step(y, y, lambda_nip=0.1, augment=True, learning_rate=1e-3)
+        losses.append(float(loss.numpy()))
+    assert all(np.isfinite(losses))
+    assert flow.run_workflow_to_decisions(y).shape == (15,)
+    assert flow.run_rgb_to_probabilities(y).shape == (15, 5)
+    assert 'FAN' in flow.summary() and 'Manipulations' in flow.details()
+    with pytest.raises(ValueError):
+        ManipulationClassification('UNet', manipulations=['bogus'], raw_patch_size=32)
+    with pytest.raises(ValueError):
+        ManipulationClassification('NoSuchNet', raw_patch_size=32)
+    with pytest.raises(ValueError):
+        ManipulationClassification('UNet', raw_patch_size=8)
