@@ -102,8 +102,15 @@ typedef struct ni_conv_desc {
 
 /* Dispatchers: tcgen05 implicit GEMM where the layer is a dense contraction, FP32 SIMT otherwise. */
 int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
-int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w_t /* (kh,kw,cout,cin) */, float* dx, ni_stream_t stream);
+int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w /* HWIO, same tensor as fprop */, float* dx, ni_stream_t stream);
 int ni_conv2d_wgrad(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+/* The tcgen05 (3xTF32, FP32-accurate) implementations; ni_conv2d_tc_supported(d, op) op: 0 fprop, 1 dgrad, 2 wgrad. */
+int ni_conv2d_tc_supported(const ni_conv_desc* d, int op);
+int ni_conv2d_fprop_tc(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
+int ni_conv2d_dgrad_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
+int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d /*128x64*/, int mn_major, ni_stream_t stream);
+void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */
 /* The SIMT implementations, callable directly (tests compare the two paths on the device). */
 int ni_conv2d_fprop_simt(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_simt(const ni_conv_desc* d, const float* dy, const float* w_t, float* dx, ni_stream_t stream);

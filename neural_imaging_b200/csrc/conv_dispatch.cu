@@ -1,17 +1,55 @@
-// Dispatch between the tcgen05 implicit-GEMM path (dense contractions) and the FP32 SIMT path (everything else).
+// Dispatch between the tcgen05 implicit-GEMM path (dense contractions) and the FP32 SIMT path (everything else:
+// 3/4-channel layers, strided / mirrored-pad / space-to-depth addressing). Both run on the GPU; there is no CPU path.
+// NI_CONV_FORCE_SIMT=1 in the environment forces the SIMT path (used by tests to compare the two on the device).
+#include <stdlib.h>
+
 #include "conv_desc.h"
 #include "ni_common.cuh"
 
 extern "C" int ni_conv2d_fprop_simt(const ni_conv_desc*, const float*, const float*, const float*, float*, cudaStream_t);
 extern "C" int ni_conv2d_dgrad_simt(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
 extern "C" int ni_conv2d_wgrad_simt(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_tc_supported(const ni_conv_desc*, int);
+extern "C" int ni_conv2d_fprop_tc(const ni_conv_desc*, const float*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_dgrad_tc(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_weight_transpose_io(const float*, float*, int, int, int, cudaStream_t);
+int ni_get_scratch2(size_t bytes, float** out);
+
+static bool force_simt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NI_CONV_FORCE_SIMT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int g_force_simt_override = -1;   // -1: follow the environment, 0 / 1: explicit
+extern "C" void ni_conv2d_set_force_simt(int on) { g_force_simt_override = on; }
+static bool use_simt() { return g_force_simt_override >= 0 ? g_force_simt_override == 1 : force_simt(); }
 
 extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    if (!use_simt() && ni_conv2d_tc_supported(d, 0) && aligned16(x) && aligned16(y)) return ni_conv2d_fprop_tc(d, x, w, bias, y, st);
     return ni_conv2d_fprop_simt(d, x, w, bias, y, st);
 }
-extern "C" int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* wt, float* dx, cudaStream_t st) {
+
+// w: the layer's HWIO weights (kh, kw, cin, cout).
+extern "C" int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st) {
+    NI_REQUIRE(d && w, "ni_conv2d_dgrad: null pointer");
+    if (!use_simt() && ni_conv2d_tc_supported(d, 1) && aligned16(dy) && aligned16(dx)) return ni_conv2d_dgrad_tc(d, dy, w, dx, st);
+    float* wt = nullptr;
+    const int taps = d->kh * d->kw;
+    int rc = ni_get_scratch2(sizeof(float) * (size_t)taps * d->cin * d->cout, &wt);
+    if (rc) return rc;
+    rc = ni_weight_transpose_io(w, wt, taps, d->cin, d->cout, st);
+    if (rc) return rc;
     return ni_conv2d_dgrad_simt(d, dy, wt, dx, st);
 }
+
 extern "C" int ni_conv2d_wgrad(const ni_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
+    if (!use_simt() && ni_conv2d_tc_supported(d, 2) && aligned16(x) && aligned16(dy)) return ni_conv2d_wgrad_tc(d, x, dy, dw, st);
     return ni_conv2d_wgrad_simt(d, x, dy, dw, st);
 }

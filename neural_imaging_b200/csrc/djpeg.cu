@@ -16,10 +16,12 @@
 
 namespace {
 
-constexpr int kTileBlocks = 64;                 // 8x8 pixel blocks per CTA tile
-constexpr int kBlockFloats = 192;               // 8*8*3
+constexpr int kTileBlocks = 32;                 // 8x8 pixel blocks per CTA tile
+constexpr int kBlockFloats = 196;               // 8*8*3 = 192 payload + 4 pad: the 16-byte bank group rotates from block to
+                                                // block, which removes the 11-way shared-memory conflicts of a 192-word stride
 constexpr int kThreads = kTileBlocks * 3;       // one thread per (block, channel)
 constexpr int kTileFloats = kTileBlocks * kBlockFloats;
+constexpr int kUnitsPerBlock = 16;              // 4-pixel (3 x float4) units per block in the per-pixel passes
 
 struct DjpegTables {
     float q[2][64];   // [0] luma, [1] chroma (reference compression/jpeg_helpers.py:264-305), row-major [k][l]
@@ -122,40 +124,44 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// Global float offset of (block g, row, 0) in an (N,H,W,3) tensor.
-__device__ __forceinline__ long long block_row_offset(long long g, int row, int nbw, int nbh, int W) {
+// Float offset of (block g, row 0, col 0) in an (N,H,W,3) tensor; computed once per block per tile.
+__device__ __forceinline__ long long block_base_offset(long long g, int nbw, int nbh, int W) {
     const int bx = (int)(g % nbw);
     const long long t = g / nbw;
     const int by = (int)(t % nbh);
     const long long n = t / nbh;
-    return (((n * nbh + by) * 8 + row) * (long long)W + bx * 8) * 3;
+    return (((n * nbh + by) * 8) * (long long)W + bx * 8) * 3;
 }
-
-// Stage a tile of 64 blocks (block-major [blk][row][24]) global -> shared with 16-byte async copies. Consecutive
-// threads copy consecutive 16-byte chunks of the same image row (adjacent blocks of a strip are contiguous).
-__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, long long g0, long long nblk,
-                                          int nbw, int nbh, int W) {
-    for (int idx = threadIdx.x; idx < kTileBlocks * 8 * 6; idx += kThreads) {
-        const int f4 = idx % 6;
-        const int blk = (idx / 6) % kTileBlocks;
-        const int row = idx / (6 * kTileBlocks);
-        const long long g = g0 + blk;
-        if (g < nblk) cp_async16(tile + blk * kBlockFloats + row * 24 + f4 * 4, src + block_row_offset(g, row, nbw, nbh, W) + f4 * 4);
+__device__ __forceinline__ void fill_base_table(long long* base, long long g0, long long nblk, int nbw, int nbh, int W) {
+    if (threadIdx.x < kTileBlocks) {
+        const long long g = g0 + threadIdx.x;
+        base[threadIdx.x] = g < nblk ? block_base_offset(g, nbw, nbh, W) : -1;
     }
 }
-__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, long long g0, long long nblk,
-                                           int nbw, int nbh, int W) {
+
+// Stage a tile (block-major [blk][row][24], block stride 196) global -> shared with 16-byte async copies. Consecutive
+// threads copy consecutive 16-byte chunks of the same image row (adjacent blocks of a strip are contiguous in memory).
+__device__ __forceinline__ void tile_load(float* tile, const float* __restrict__ src, const long long* base, int rowf) {
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < kTileBlocks * 8 * 6; idx += kThreads) {
-        const int f4 = idx % 6;
-        const int blk = (idx / 6) % kTileBlocks;
-        const int row = idx / (6 * kTileBlocks);
-        const long long g = g0 + blk;
-        if (g < nblk) {
+        const int f4 = idx % 6, blk = (idx / 6) % kTileBlocks, row = idx / (6 * kTileBlocks);
+        const long long b = base[blk];
+        if (b >= 0) cp_async16(tile + blk * kBlockFloats + row * 24 + f4 * 4, src + b + row * rowf + f4 * 4);
+    }
+}
+__device__ __forceinline__ void tile_store(const float* tile, float* __restrict__ dst, const long long* base, int rowf) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kTileBlocks * 8 * 6; idx += kThreads) {
+        const int f4 = idx % 6, blk = (idx / 6) % kTileBlocks, row = idx / (6 * kTileBlocks);
+        const long long b = base[blk];
+        if (b >= 0) {
             const float4 v = *reinterpret_cast<const float4*>(tile + blk * kBlockFloats + row * 24 + f4 * 4);
-            __stcs(reinterpret_cast<float4*>(dst + block_row_offset(g, row, nbw, nbh, W) + f4 * 4), v);
+            __stcs(reinterpret_cast<float4*>(dst + b + row * rowf + f4 * 4), v);
         }
     }
 }
+// address of 4-pixel unit u of the per-pixel passes
+__device__ __forceinline__ int unit_offset(int u) { return (u / kUnitsPerBlock) * kBlockFloats + (u % kUnitsPerBlock) * 12; }
 
 // Load this thread's channel of its block (level-shifted YCbCr) from the interleaved RGB tile.
 __device__ __forceinline__ void load_channel(const float* bp, int c, float (&v)[8][8]) {
@@ -196,17 +202,20 @@ __device__ __forceinline__ void load_tables(float2* sq, const DjpegTables& tab) 
 
 // ---------------------------------------------------------------------------------------------------- forward
 template <int MODE, bool WRITE_X>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 6)
 djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ Xd, int H, int W,
                  long long nblk, DjpegTables tab) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float2* sq = reinterpret_cast<float2*>(smem + kTileFloats);
-    const int nbw = W / 8, nbh = H / 8;
+    long long* base = reinterpret_cast<long long*>(sq + 128);
+    const int nbw = W / 8, nbh = H / 8, rowf = W * 3;
     const long long g0 = (long long)blockIdx.x * kTileBlocks;
 
-    tile_load(tile, x, g0, nblk, nbw, nbh, W);
+    fill_base_table(base, g0, nblk, nbw, nbh, W);
     load_tables(sq, tab);
+    __syncthreads();
+    tile_load(tile, x, base, rowf);
     cp_async_wait_all();
     __syncthreads();
 
@@ -243,8 +252,8 @@ djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __re
     __syncthreads();
 
     // per-pixel inverse colour transform + /255 + clip, 4 pixels (3 float4) per step, in place
-    for (int u = threadIdx.x; u < kTileFloats / 12; u += kThreads) {
-        float4* p = reinterpret_cast<float4*>(tile + u * 12);
+    for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
+        float4* p = reinterpret_cast<float4*>(tile + unit_offset(u));
         float4 a = p[0], b = p[1], d = p[2];
         float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -258,7 +267,7 @@ djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __re
         p[2] = make_float4(f[8], f[9], f[10], f[11]);
     }
     __syncthreads();
-    tile_store(tile, y, g0, nblk, nbw, nbh, W);
+    tile_store(tile, y, base, rowf);
 }
 
 // ---------------------------------------------------------------------------------------------------- backward
@@ -267,19 +276,22 @@ djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __re
 //   g_ypre = dy * 1[0<=ypre<=1] ; g_xi = C_I[:,1:]^T g_ypre / 255 ; G = F g_xi F^T ; g_Z-path: G*Q*q'(Z)/Q = G*q'(Z)
 //   g_r = F^T (G q') F ; dx = 255 * C_F[:,1:]^T g_r
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 djpeg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int H, int W,
                  long long nblk, DjpegTables tab) {
     extern __shared__ __align__(16) float smem[];
     float* tx = smem;                 // x tile -> xi -> g_r -> dx
     float* tg = smem + kTileFloats;   // dy tile -> g_xi
     float2* sq = reinterpret_cast<float2*>(smem + 2 * kTileFloats);
-    const int nbw = W / 8, nbh = H / 8;
+    long long* base = reinterpret_cast<long long*>(sq + 128);
+    const int nbw = W / 8, nbh = H / 8, rowf = W * 3;
     const long long g0 = (long long)blockIdx.x * kTileBlocks;
 
-    tile_load(tx, x, g0, nblk, nbw, nbh, W);
-    tile_load(tg, dy, g0, nblk, nbw, nbh, W);
+    fill_base_table(base, g0, nblk, nbw, nbh, W);
     load_tables(sq, tab);
+    __syncthreads();
+    tile_load(tx, x, base, rowf);
+    tile_load(tg, dy, base, rowf);
     cp_async_wait_all();
     __syncthreads();
 
@@ -305,9 +317,9 @@ djpeg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     __syncthreads();
 
     // pixel pass 1: clip mask from recomputed ypre, g_xi = C_I[:,1:]^T (mask*dy)/255, written over the dy tile
-    for (int u = threadIdx.x; u < kTileFloats / 12; u += kThreads) {
-        const float4* px = reinterpret_cast<const float4*>(tx + u * 12);
-        float4* pg = reinterpret_cast<float4*>(tg + u * 12);
+    for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
+        const float4* px = reinterpret_cast<const float4*>(tx + unit_offset(u));
+        float4* pg = reinterpret_cast<float4*>(tg + unit_offset(u));
         float4 a = px[0], b = px[1], d = px[2];
         float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
         a = pg[0]; b = pg[1]; d = pg[2];
@@ -341,8 +353,8 @@ djpeg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
     __syncthreads();
 
     // pixel pass 2: dx = 255 * C_F[:,1:]^T g_r
-    for (int u = threadIdx.x; u < kTileFloats / 12; u += kThreads) {
-        float4* p = reinterpret_cast<float4*>(tx + u * 12);
+    for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
+        float4* p = reinterpret_cast<float4*>(tx + unit_offset(u));
         float4 a = p[0], b = p[1], d = p[2];
         float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -357,7 +369,7 @@ djpeg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, floa
         p[2] = make_float4(f[8], f[9], f[10], f[11]);
     }
     __syncthreads();
-    tile_store(tx, dx, g0, nblk, nbw, nbh, W);
+    tile_store(tx, dx, base, rowf);
 }
 
 int fill_tables(DjpegTables& t, const float* q_luma, const float* q_chroma) {
@@ -369,8 +381,8 @@ int fill_tables(DjpegTables& t, const float* q_luma, const float* q_chroma) {
     return 0;
 }
 
-constexpr size_t kFwdSmem = kTileFloats * sizeof(float) + 128 * sizeof(float2);
-constexpr size_t kBwdSmem = 2 * kTileFloats * sizeof(float) + 128 * sizeof(float2);
+constexpr size_t kFwdSmem = kTileFloats * sizeof(float) + 128 * sizeof(float2) + kTileBlocks * sizeof(long long);
+constexpr size_t kBwdSmem = 2 * kTileFloats * sizeof(float) + 128 * sizeof(float2) + kTileBlocks * sizeof(long long);
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {

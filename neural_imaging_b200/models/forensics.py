@@ -188,9 +188,7 @@ class FAN(TFModel):
             dd = self._cconv.desc(m, h + 2 * pad, w + 2 * pad)   # VALID conv on the padded domain
             dd.pad_t = dd.pad_l = 0
             dd.oh, dd.ow, dd.pad_mode = h, w, PAD_ZERO
-            wt = ws.get('nf_t', (5, 5, 3, 3))
-            L.ni_weight_transpose_io(ptr(self._nf), ptr(wt), 25, 3, 3, s)
-            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dp), ptr(wt), ptr(dpad), s)
+            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dp), ptr(self._nf), ptr(dpad), s)
             dx = ws.get('dx', (m, h, w, 3))
             L.ni_pad_fold(ptr(dpad), ptr(dx), m, h, w, 3, pad, PAD_SYMMETRIC, 0, s)
         return dx

@@ -189,10 +189,7 @@ class Conv2D:
             dd.accumulate = int(dx_accumulate)
             dd.pad_mode = PAD_ZERO
             wv = self.w.value if weight is None else weight
-            if self._wt is None:
-                self._wt = empty((self.k, self.k, self.cout, self.cin))
-            L.ni_weight_transpose_io(ptr(wv), ptr(self._wt), self.k * self.k, self.cin, self.cout, st)
-            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(self._wt), ptr(dx), st)
+            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dx), st)
         return dx
 
 
