@@ -97,7 +97,24 @@ class EventProfiler:
     def after(self, name, args):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
-        self.records.append((name, self._open, e, self._work(name, args)))
+        key = name
+        if name.startswith('ni_conv2d_'):
+            d = args[0]._obj
+            key = '%s n%d %dx%d c%d->%d k%d s%d' % (name[10:], d.n, d.h, d.w, d.cin, d.cout, d.kh, d.stride)
+        self.records.append((name, self._open, e, self._work(name, args), key))
+
+    def layer_table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, a, b, (kind, work), key in self.records:
+            r = agg.setdefault(key, {'calls': 0, 'ms': 0.0, 'flop': 0.0})
+            r['calls'] += 1
+            r['ms'] += a.elapsed_time(b)
+            r['flop'] += work if kind == 'flop' else 0.0
+        rows = []
+        for k, r in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
+            rows.append({'key': k, 'calls': r['calls'], 'ms': r['ms'], 'tflops': (r['flop'] / (r['ms'] * 1e-3) / 1e12) if r['ms'] > 0 and r['flop'] else None})
+        return rows
 
     @staticmethod
     def _work(name, args):
@@ -115,7 +132,7 @@ class EventProfiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for name, a, b, (kind, work) in self.records:
+        for name, a, b, (kind, work), _key in self.records:
             r = agg.setdefault(name, {'calls': 0, 'ms': 0.0, 'kind': kind, 'work': 0.0})
             r['calls'] += 1
             r['ms'] += a.elapsed_time(b)
@@ -206,6 +223,9 @@ def run_ours(args, rank, world, local_rank):
     t1.record()
     _lib.PROFILER = None
     agg = prof.summary()
+    if args.layer_report and rank == 0:
+        with open(args.layer_report, 'w') as f:
+            json.dump({'steps': args.steps, 'batch': args.batch, 'layers': prof.layer_table()}, f, indent=1)
     prof_ms = t0.elapsed_time(t1)
     if rank != 0:
         return
@@ -323,6 +343,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layer-report', default=None, help='write a per-layer (per conv shape) timing table to this JSON file')
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':

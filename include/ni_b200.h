@@ -109,6 +109,11 @@ int ni_conv2d_tc_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_tc(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
 int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+/* Direct FP32 stencils for the 3/4-input-channel and 3/12-output-channel layers (FAN front end, U-Net first / last conv). */
+int ni_conv2d_small_supported(const ni_conv_desc* d, int op);
+int ni_conv2d_fprop_small(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
+int ni_conv2d_dgrad_small(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
+int ni_conv2d_wgrad_small(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
 int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d /*128x64*/, int mn_major, ni_stream_t stream);
 void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */
 /* The SIMT implementations, callable directly (tests compare the two paths on the device). */

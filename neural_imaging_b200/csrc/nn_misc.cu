@@ -112,6 +112,106 @@ __global__ void act_bwd_bias_kernel(const float* __restrict__ y, float* __restri
     }
 }
 
+// Vectorised (float4 over channels) variants for plain NHWC buffers with 16-byte aligned channel slices: these layers are
+// pure HBM streams (12 B / element), the scalar versions above were ALU-bound on 64-bit index arithmetic.
+__global__ void __launch_bounds__(256)
+act_bwd_bias_vec_kernel(const float* __restrict__ y, float* __restrict__ dy, float* __restrict__ dbias, long long npix, int c,
+                        int yp, int yo, int dp, int dof, int act, float alpha, int pix_per_block, int bias_mod, int nx, int ny) {
+    extern __shared__ float4 red4[];                   // [ny][nx]
+    const int tx = threadIdx.x % nx, ty = threadIdx.x / nx;
+    const long long p0 = (long long)blockIdx.y * pix_per_block;
+    const long long p1 = min(p0 + (long long)pix_per_block, npix);
+    const bool need_act = act != NI_ACT_NONE && act != NI_ACT_CLIP01;
+    for (int c4 = blockIdx.x * nx + tx; c4 * 4 < c; c4 += gridDim.x * nx) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long p = p0 + ty; p < p1; p += ny) {
+            float4* gp = reinterpret_cast<float4*>(dy + p * dp + dof + c4 * 4);
+            float4 g = *gp;
+            if (need_act) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(y + p * yp + yo + c4 * 4));
+                g.x *= act_grad_from_out(yv.x, act, alpha); g.y *= act_grad_from_out(yv.y, act, alpha);
+                g.z *= act_grad_from_out(yv.z, act, alpha); g.w *= act_grad_from_out(yv.w, act, alpha);
+                *gp = g;
+            }
+            s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+        }
+        if (dbias) {
+            red4[ty * nx + tx] = s;
+            __syncthreads();
+            if (ty == 0) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < ny; ++k) { const float4 v = red4[k * nx + tx]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const int ch = c4 * 4 + e; atomicAdd(dbias + (bias_mod > 0 ? ch % bias_mod : ch), tv[e]); }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// even h, w; c % 4 == 0; one thread = one 2x2 window x 4 channels
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int oh, int ow, int c4n, int xp, int xo, int yp, int yo) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)n * oh * ow * c4n;
+    if (i >= total) return;
+    const int c4 = (int)(i % c4n);
+    long long t = i / c4n;
+    const int ox = (int)(t % ow); t /= ow;
+    const int oy = (int)(t % oh);
+    const long long nn = t / oh;
+    const long long r0 = ((nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox);
+    const float* b = x + xo + c4 * 4;
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(b + r0 * xp)), v01 = __ldg(reinterpret_cast<const float4*>(b + (r0 + 1) * xp));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(b + (r0 + 2 * ow) * xp)), v11 = __ldg(reinterpret_cast<const float4*>(b + (r0 + 2 * ow + 1) * xp));
+    float4 m;
+    m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x)); m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+    m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z)); m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+    *reinterpret_cast<float4*>(y + (((nn * oh + oy) * ow + ox)) * yp + yo + c4 * 4) = m;
+}
+
+__device__ __forceinline__ void pool_route(float a, float b, float c, float d, float g, float& ga, float& gb, float& gc, float& gd) {
+    // first maximum in scan order (a, b, c, d) takes the gradient
+    ga = gb = gc = gd = 0.f;
+    float m = a; int arg = 0;
+    if (b > m) { m = b; arg = 1; }
+    if (c > m) { m = c; arg = 2; }
+    if (d > m) { m = d; arg = 3; }
+    if (arg == 0) ga = g; else if (arg == 1) gb = g; else if (arg == 2) gc = g; else gd = g;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ add, float* __restrict__ dx,
+                       int n, int oh, int ow, int c4n, int xp, int xo, int dyp, int dyo, int addp, int addo, int dxp, int dxo) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)n * oh * ow * c4n;
+    if (i >= total) return;
+    const int c4 = (int)(i % c4n);
+    long long t = i / c4n;
+    const int ox = (int)(t % ow); t /= ow;
+    const int oy = (int)(t % oh);
+    const long long nn = t / oh;
+    const long long r[4] = {(nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox + 1,
+                            (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox + 1};
+    float4 v[4], g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(x + r[k] * xp + xo + c4 * 4));
+    const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + ((nn * oh + oy) * ow + ox) * dyp + dyo + c4 * 4));
+    pool_route(v[0].x, v[1].x, v[2].x, v[3].x, gy.x, g[0].x, g[1].x, g[2].x, g[3].x);
+    pool_route(v[0].y, v[1].y, v[2].y, v[3].y, gy.y, g[0].y, g[1].y, g[2].y, g[3].y);
+    pool_route(v[0].z, v[1].z, v[2].z, v[3].z, gy.z, g[0].z, g[1].z, g[2].z, g[3].z);
+    pool_route(v[0].w, v[1].w, v[2].w, v[3].w, gy.w, g[0].w, g[1].w, g[2].w, g[3].w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (add) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(add + r[k] * addp + addo + c4 * 4));
+            g[k].x += a.x; g[k].y += a.y; g[k].z += a.z; g[k].w += a.w;
+        }
+        *reinterpret_cast<float4*>(dx + r[k] * dxp + dxo + c4 * 4) = g[k];
+    }
+}
+
 // ------------------------------------------------------------------ global average pooling (n,h,w,c) <-> (n,c)
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c) {
     const int n = blockIdx.x;
@@ -326,6 +426,11 @@ extern "C" int ni_maxpool2_fwd(const float* x, float* y, int n, int h, int w, in
     const int oh = same ? (h + 1) / 2 : h / 2, ow = same ? (w + 1) / 2 : w / 2;
     NI_REQUIRE(oh > 0 && ow > 0, "ni_maxpool2_fwd: input smaller than the pooling window");
     if (n == 0) return NI_OK;
+    if (!(h & 1) && !(w & 1) && !(c & 3) && !(x_pitch & 3) && !(x_coff & 3) && !(y_pitch & 3) && !(y_coff & 3)) {
+        maxpool_fwd_vec_kernel<<<grid_for((long long)n * oh * ow * (c / 4)), kT, 0, st>>>(x, y, n, oh, ow, c / 4, x_pitch, x_coff, y_pitch, y_coff);
+        NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
     maxpool_fwd_kernel<<<grid_for((long long)n * oh * ow * c), kT, 0, st>>>(x, y, n, h, w, c, oh, ow, x_pitch, x_coff, y_pitch, y_coff);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
@@ -337,6 +442,13 @@ extern "C" int ni_maxpool2_bwd(const float* x, const float* dy, const float* add
     NI_REQUIRE(x && dy && dx && n >= 0 && h > 0 && w > 0 && c > 0, "ni_maxpool2_bwd: invalid arguments");
     const int oh = same ? (h + 1) / 2 : h / 2, ow = same ? (w + 1) / 2 : w / 2;
     if (n == 0) return NI_OK;
+    if (!(h & 1) && !(w & 1) && !(c & 3) && !(x_pitch & 3) && !(x_coff & 3) && !(dy_pitch & 3) && !(dy_coff & 3) && !(dx_pitch & 3) &&
+        !(dx_coff & 3) && (!add || (!(add_pitch & 3) && !(add_coff & 3)))) {
+        maxpool_bwd_vec_kernel<<<grid_for((long long)n * oh * ow * (c / 4)), kT, 0, st>>>(x, dy, add, dx, n, oh, ow, c / 4, x_pitch, x_coff, dy_pitch,
+                                                                                      dy_coff, add_pitch, add_coff, dx_pitch, dx_coff);
+        NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
     maxpool_bwd_kernel<<<grid_for((long long)n * h * w * c), kT, 0, st>>>(x, dy, add, dx, n, h, w, c, oh, ow, x_pitch, x_coff,
                                                                        dy_pitch, dy_coff, add_pitch, add_coff, dx_pitch, dx_coff);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
@@ -355,6 +467,23 @@ extern "C" int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, i
     const long long npix = (long long)n * h * w;
     if (npix == 0) return NI_OK;
     if (!dbias && (act == NI_ACT_NONE || act == NI_ACT_CLIP01)) return NI_OK;
+    if (y_mode == NI_MODE_PLAIN && dy_mode == NI_MODE_PLAIN && !(c & 3) && !(dy_pitch & 3) && !(dy_coff & 3) &&
+        (!y || (!(y_pitch & 3) && !(y_coff & 3)))) {
+        int nx = c / 4; if (nx > 64) nx = 64;
+        while (256 % nx) --nx;                         // nx divides 256
+        const int ny = 256 / nx;
+        const int cblocks = ni_cdiv(c / 4, nx);
+        long long chunks = (8LL * ni_num_sms() + cblocks - 1) / cblocks;
+        if (chunks > (npix + 4 * ny - 1) / (4 * ny)) chunks = (npix + 4 * ny - 1) / (4 * ny);
+        if (chunks < 1) chunks = 1;
+        if (chunks > 65535) chunks = 65535;
+        const int ppb = (int)((npix + chunks - 1) / chunks);
+        dim3 grid(cblocks, ni_cdiv(npix, ppb));
+        act_bwd_bias_vec_kernel<<<grid, 256, sizeof(float4) * 256, st>>>(y, dy, dbias, npix, c, y_pitch, y_coff, dy_pitch, dy_coff, act, alpha, ppb,
+                                                                      bias_mod, nx, ny);
+        NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
     const int cgroups = ni_cdiv(c, 32);
     long long chunks = (4LL * ni_num_sms() + cgroups - 1) / cgroups;
     if (chunks > (npix + 63) / 64) chunks = (npix + 63) / 64;

@@ -47,7 +47,10 @@ def test_unet_forward_backward():
     R.adam_keras_step(list(P.values()), [torch.tensor(out[torch.float64][2][k]) for k in P], ms, vs, 1, 1e-4)
     new = model._store.state_dict()
     for k, p in P.items():
-        assert np.max(np.abs(new[k] - p.numpy())) < 2e-6, k     # |update| <= lr = 1e-4; allow 2% sign-noise on tiny grads
+        # Adam's first step is lr * g / (|g| + eps): a parameter whose gradient is at the rounding-noise level can move by
+        # up to 2*lr in the "wrong" direction in ANY float32 implementation, so bound the bulk and the extreme separately
+        delta = np.abs(new[k] - p.numpy())
+        assert delta.max() <= 2.02e-4 and np.mean(delta > 2e-6) < 2e-3, k
 
 
 @pytest.mark.parametrize('kw', [dict(), dict(n_filters=8, n_convolutions=2, kernel=3, n_dense=2, use_gap=False, activation='relu')])
