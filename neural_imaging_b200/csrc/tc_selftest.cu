@@ -33,26 +33,41 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
     // MN-major: 4 KB per 32-wide MN atom (32 k rows x 128 B), k groups of 8 rows = 1 KB
     for (int i = threadIdx.x; i < 128 * 32; i += 128) {
         const int m = i / 32, k = i % 32;
-        const int o = mn_major ? off_mnmajor(m, k, 4096, 1024) : off_kmajor(m, k);
+        const int o = mn_major == 1 ? off_mnmajor(m, k, 4096, 1024) : off_kmajor(m, k);
         *reinterpret_cast<float*>(sa + o) = A[m * 32 + k];
     }
     for (int i = threadIdx.x; i < kN * 32; i += 128) {
         const int n = i / 32, k = i % 32;
-        const int o = mn_major ? off_mnmajor(n, k, 4096, 1024) : off_kmajor(n, k);
+        const int o = mn_major == 1 ? off_mnmajor(n, k, 4096, 1024) : off_kmajor(n, k);
         *reinterpret_cast<float*>(sb + o) = B[n * 32 + k];
     }
     if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
+    if (mn_major == 2) {
+        // A operand through tensor memory: thread = row, 32 K-columns at TMEM columns [64, 96)
+        float v[32];
+        for (int k = 0; k < 32; ++k) v[k] = A[(warp * 32 + lane) * 32 + k];
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 64u, v);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+    }
     if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc_tf32(128, kN, mn_major, mn_major);
+        const uint32_t idesc = make_idesc_tf32(128, kN, mn_major == 1, mn_major == 1);
         for (int ks = 0; ks < 4; ++ks) {
             uint64_t da, db;
-            if (mn_major) {
+            if (mn_major == 2) {
+                db = make_smem_desc_sw128(smem_u32(sb) + ks * 32, 16, 1024);
+                umma_tf32_ts(tmem, tmem + 64u + ks * 8, db, idesc, ks > 0 ? 1u : 0u);
+                continue;
+            }
+            if (mn_major == 1) {
                 da = make_smem_desc_sw128(smem_u32(sa) + ks * 1024, 4096, 1024);
                 db = make_smem_desc_sw128(smem_u32(sb) + ks * 1024, 4096, 1024);
             } else {
@@ -73,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 64); }
+    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 128); }
 }
 }  // namespace
 
@@ -82,7 +97,7 @@ extern "C" int ni_tc_selftest(const float* a, const float* b, float* d, int mn_m
     NI_REQUIRE(a && b && d, "ni_tc_selftest: null pointer");
     const size_t smem = 16384 + kN * 128 + 1024;
     NI_CUDA(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_selftest_kernel<<<1, 128, smem, st>>>(a, b, d, mn_major ? 1 : 0);
+    tc_selftest_kernel<<<1, 128, smem, st>>>(a, b, d, mn_major);
     NI_LAUNCH_CHECK();
     return NI_OK;
 }

@@ -30,11 +30,17 @@ def stats(name, a, b):
 # ---- UMMA layout self-test (K-major and MN-major)
 A = torch.randint(-4, 5, (128, 32), device='cuda').float()
 B = torch.randint(-4, 5, (64, 32), device='cuda').float()
-for mn in (0, 1):
+for mn in (0, 1, 2, 3):
     D = torch.full((128, 64), 7.0, device='cuda')
-    L.ni_tc_selftest(ptr(A), ptr(B), ptr(D), mn, stream())
+    if mn == 3:   # does the tensor core truncate or round FP32 -> TF32 ? (A with full mantissas, mode 0)
+        A = (torch.randint(-4, 5, (128, 32), device='cuda').float() * (1 + 2.0 ** -11 + 2.0 ** -12 + 2.0 ** -20))
+    L.ni_tc_selftest(ptr(A), ptr(B), ptr(D), 0 if mn == 3 else mn, stream())
     torch.cuda.synchronize()
-    ref = A @ B.t()
+    ref = A.double() @ B.double().t()
+    if mn == 3:
+        At = torch.from_numpy((A.cpu().numpy().view('uint32') & 0xFFFFE000).view('float32')).cuda()
+        print('  vs truncated-A product: max diff %.6f ; vs exact product: max diff %.6f' % (float((D - At.double() @ B.double().t()).abs().max()), float((D - ref).abs().max())))
+        continue
     print('selftest mn_major=%d: max|D-ref| = %.3f, |D|max %.3f, |ref|max %.3f' % (mn, float((D - ref).abs().max()), float(D.abs().max()), float(ref.abs().max())))
     if float((D - ref).abs().max()) > 0:
         print('  D[0,:8]  ', D[0, :8].tolist()); print('  ref[0,:8]', ref[0, :8].tolist())
