@@ -1,0 +1,375 @@
+// tcgen05 convolution kernels, generation 2: the A operand travels through TENSOR MEMORY.
+//
+// Generation 1 (conv_tc.cu) kept A in shared memory: per 32-channel k-iteration the 16 KB A tile was written by TMA,
+// read + re-written as hi / lo by the splitter (48 KB) and read 12 more times by the MMAs (48 KB): 112+ KB of shared-
+// memory traffic per k-iteration against a 128 B/clk port, i.e. 2x (N = 128) to 5x (N = 32) the MMA time.
+// Here converter warps read each pixel row ONCE from the TMA-landed tile (8 conflict-free 128-bit loads through the
+// XOR swizzle), split it in registers and write hi and lo to TMEM with tcgen05.st; tcgen05.mma then takes A from TMEM
+// ([d], [a], b-desc form, validated by ni_tc_selftest) and only B (weights) is read from shared memory.
+// Shared-memory traffic per k-iteration drops to 32 KB + B tiles.
+#pragma once
+#include "conv_desc.h"
+#include "ni_common.cuh"
+#include "tc_common.cuh"
+
+namespace tcv2 {
+using namespace tc;
+
+constexpr int kSmemStages = 3;   // TMA ring: raw A tile + B hi + B lo
+constexpr int kTmemSlots = 2;    // A (hi | lo) slots in tensor memory, 64 columns each
+constexpr int kAraw = 16384;
+constexpr int kThreadsGemm = 192;
+
+struct GemmParams {
+    int n, oh, ow;
+    int bw, bh, bn;
+    int tiles_w, tiles_h;
+    int kh, kw, off_y0, off_x0, off_sign;
+    int kchunks, ntot;
+    int out_pitch, out_coff, out_mode;
+    int bias_mod, act, accumulate, nacc;
+    float alpha;
+    const float* bias;
+    float* out;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act, float alpha) {
+    switch (act) {
+        case NI_ACT_LEAKY_RELU: return v > 0.f ? v : alpha * v;
+        case NI_ACT_RELU: return fmaxf(v, 0.f);
+        case NI_ACT_TANH: return tanhf(v);
+        case NI_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case NI_ACT_CLIP01: return ni_clamp01(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ uint32_t pow2_cols(uint32_t want) {
+    return want <= 32 ? 32 : (want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 256 ? 256 : 512)));
+}
+
+// TMEM map: [0, (nacc+1)*BNT) accumulators (D1_0.. D1_{nacc-1}, D2), then kTmemSlots x 64 columns of A (hi 32 | lo 32).
+template <int BNT>
+__global__ void __launch_bounds__(kThreadsGemm, 1)
+conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int B_BYTES = BNT * 128;
+    constexpr int STAGE_BYTES = kAraw + 2 * B_BYTES;
+    const uint32_t acc_cols = (uint32_t)(p.nacc + 1) * BNT;
+    const uint32_t TMEM_COLS = pow2_cols(acc_cols + kTmemSlots * 64);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar_full[kSmemStages], bar_sfree[kSmemStages], bar_aready[kTmemSlots], bar_afree[kTmemSlots], bar_accum;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw = blockIdx.x % p.tiles_w, th = (blockIdx.x / p.tiles_w) % p.tiles_h, tn = blockIdx.x / (p.tiles_w * p.tiles_h);
+    const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+    const int ntile0 = blockIdx.y * BNT;
+    const int taps = p.kh * p.kw;
+    const int iters = taps * p.kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSmemStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_sfree[s], 1); }
+        for (int t = 0; t < kTmemSlots; ++t) { mbar_init(&bar_aready[t], 128); mbar_init(&bar_afree[t], 1); }
+        mbar_init(&bar_accum, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_base = tmem + acc_cols;
+
+    auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
+    auto b_hi = [&](int s) { return smem + s * STAGE_BYTES + kAraw; };
+    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + kAraw + B_BYTES; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
+                mbar_wait(&bar_sfree[s], ph ^ 1, 0);
+                mbar_expect_tx(&bar_full[s], kAraw + 2 * B_BYTES);
+                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                const int a = tap / p.kw, b = tap - a * p.kw;
+                tma_load_4d(a_raw(s), &tmA, &bar_full[s], kc * 32, x0 + p.off_x0 + p.off_sign * b, y0 + p.off_y0 + p.off_sign * a, n0);
+                tma_load_3d(b_hi(s), &tmB, &bar_full[s], kc * 32, ntile0, tap);
+                tma_load_3d(b_lo(s), &tmB, &bar_full[s], kc * 32, ntile0, taps + tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
+                const int t = it % kTmemSlots, pt = (it / kTmemSlots) & 1;
+                mbar_wait(&bar_full[s], ph, 1);
+                mbar_wait(&bar_aready[t], pt, 2);
+                tcgen05_fence_after();
+                const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+                const uint32_t ahi = a_base + t * 64, alo = ahi + 32;
+                const uint32_t d2 = tmem + (uint32_t)p.nacc * BNT, d1 = tmem + (uint32_t)(it % p.nacc) * BNT;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t dbh = make_smem_desc_sw128(bh + ks * 32, 16, 1024), dbl = make_smem_desc_sw128(bl + ks * 32, 16, 1024);
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    umma_tf32_ts(d2, alo + ks * 8, dbh, idesc, acc);
+                    umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
+                    umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (it >= p.nacc || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&bar_sfree[s]);
+                umma_commit(&bar_afree[t]);
+            }
+            umma_commit(&bar_accum);
+        }
+    } else {
+        const int q = warp & 3, row = q * 32 + lane;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
+            const int t = it % kTmemSlots, pt = (it / kTmemSlots) & 1;
+            mbar_wait(&bar_full[s], ph, 3);
+            float hi[32], lo[32];
+            const uint8_t* rp = a_raw(s) + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xFFFFE000u);
+                    hi[4 * c + e] = h;
+                    lo[4 * c + e] = vv[e] - h;
+                }
+            }
+            mbar_wait(&bar_afree[t], pt ^ 1, 5);
+            tcgen05_fence_after();
+            const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + t * 64;
+            tmem_st_32x32(dst, hi);
+            tmem_st_32x32(dst + 32, lo);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bar_aready[t]);
+        }
+        // ---- epilogue
+        mbar_wait(&bar_accum, 0, 4);
+        tcgen05_fence_after();
+        const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ln = row / (p.bw * p.bh);
+        const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;
+        const bool valid = on < p.n && oy < p.oh && ox < p.ow;
+#pragma unroll 1
+        for (int c = 0; c < BNT / 32; ++c) {
+            float v[32], v2[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            for (int a2 = 1; a2 <= p.nacc; ++a2) {
+                tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a2 * BNT + c * 32), v2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j];
+            }
+            if (!valid) continue;
+            const int co0 = ntile0 + c * 32;
+            float* o;
+            if (p.out_mode == NI_MODE_PLAIN) {
+                o = p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff + co0;
+            } else {
+                const int F = p.ntot >> 2, blk = co0 / F, f0 = co0 - blk * F;
+                o = p.out + (((long long)on * 2 * p.oh + 2 * oy + (blk >> 1)) * (2 * p.ow) + 2 * ox + (blk & 1)) * p.out_pitch + p.out_coff + f0;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float tv = v[j];
+                if (p.bias) { const int bi = co0 + j; tv += __ldg(p.bias + (p.bias_mod > 0 ? bi % p.bias_mod : bi)); }
+                v[j] = act_apply(tv, p.act, p.alpha);
+            }
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 w4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (p.accumulate) { const float4 old = o4[j]; w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
+                o4[j] = w4;
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------------------ wgrad
+// dW[(tap,ci), co] = sum_pixels X_tap[pixel, ci] * dY[pixel, co]. M = (tap, ci) flattened in 32-row atoms, N = co, K = pixels.
+// A (X^T): each of the 4 A-converter warps owns one atom: lane = channel, reads its 32 pixels from the TMA-landed
+// [pixel][channel] tile (conflict-free through the swizzle) and writes hi / lo rows straight to TMEM.
+// B (dY^T) has to be K-major in shared memory (kind::tf32 has no MN-major mode): 4 transposer warps turn the pixel-major
+// tile around with scalar stores (also conflict-free).
+constexpr int kWgStages = 2;
+constexpr int kThreadsWg = 64 + 128 + 128;
+
+struct WgradParams {
+    int n, oh, ow;
+    int bw, bh, bn;
+    int tiles_w, tiles_h;
+    int kw, pad_t, pad_l;
+    int cin_chunks, atoms, mtot, cout;
+    int steps_total, steps_per_split;
+    float* dw;
+};
+
+__device__ __forceinline__ void transpose_split_chunk(const uint8_t* raw, uint8_t* hi, uint8_t* lo, int row0, int r) {
+    const int p = r & 31, c4 = r >> 5;
+    const float4 v = *reinterpret_cast<const float4*>(raw + p * 128 + ((c4 ^ (p & 7)) << 4));
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int m = row0 + c4 * 4 + e;
+        const int off = (m >> 3) * 1024 + (m & 7) * 128 + (((p >> 2) ^ (m & 7)) << 4) + (p & 3) * 4;
+        const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xFFFFE000u);
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = vv[e] - h;
+    }
+}
+
+// TMEM map: D1 [0,BNT), D2 [BNT, 2 BNT), A slots 2 x 64 columns.
+template <int BNT>
+__global__ void __launch_bounds__(kThreadsWg, 1)
+conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+    constexpr int B_BYTES = BNT * 128;
+    constexpr int STAGE_BYTES = kAraw + 3 * B_BYTES;   // raw A (4 atoms), raw B, B hi, B lo
+    const uint32_t TMEM_COLS = pow2_cols(2 * BNT + kWgStages * 64);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar_full[kWgStages], bar_aready[kWgStages], bar_bready[kWgStages], bar_free[kWgStages], bar_accum;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int atom0 = blockIdx.x * 4;
+    const int valid_atoms = min(4, p.atoms - atom0);
+    const int co0 = blockIdx.y * BNT;
+    const int step0 = blockIdx.z * p.steps_per_split;
+    const int iters = min(p.steps_per_split, p.steps_total - step0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) {
+            mbar_init(&bar_full[s], 1); mbar_init(&bar_aready[s], 128); mbar_init(&bar_bready[s], 128); mbar_init(&bar_free[s], 1);
+        }
+        mbar_init(&bar_accum, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDY);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_base = tmem + 2 * BNT;
+
+    auto raw_a = [&](int s) { return smem + s * STAGE_BYTES; };
+    auto raw_b = [&](int s) { return smem + s * STAGE_BYTES + kAraw; };
+    auto b_hi = [&](int s) { return smem + s * STAGE_BYTES + kAraw + B_BYTES; };
+    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + kAraw + 2 * B_BYTES; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+                mbar_wait(&bar_free[s], ph ^ 1, 0);
+                mbar_expect_tx(&bar_full[s], valid_atoms * 4096 + B_BYTES);
+                const int st = step0 + it;
+                const int tw = st % p.tiles_w, th = (st / p.tiles_w) % p.tiles_h, tn = st / (p.tiles_w * p.tiles_h);
+                const int x0 = tw * p.bw, y0 = th * p.bh, n0 = tn * p.bn;
+                for (int j = 0; j < valid_atoms; ++j) {
+                    const int atom = atom0 + j, tap = atom / p.cin_chunks, cc = atom - tap * p.cin_chunks;
+                    const int a = tap / p.kw, b = tap - a * p.kw;
+                    tma_load_4d(raw_a(s) + j * 4096, &tmX, &bar_full[s], cc * 32, x0 + b - p.pad_l, y0 + a - p.pad_t, n0);
+                }
+                for (int j = 0; j < BNT / 32; ++j) tma_load_4d(raw_b(s) + j * 4096, &tmDY, &bar_full[s], co0 + j * 32, x0, y0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+                mbar_wait(&bar_aready[s], ph, 1);
+                mbar_wait(&bar_bready[s], ph, 2);
+                tcgen05_fence_after();
+                const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+                const uint32_t ahi = a_base + s * 64, alo = ahi + 32;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t dbh = make_smem_desc_sw128(bh + ks * 32, 16, 1024), dbl = make_smem_desc_sw128(bl + ks * 32, 16, 1024);
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    umma_tf32_ts(tmem + BNT, alo + ks * 8, dbh, idesc, acc);
+                    umma_tf32_ts(tmem + BNT, ahi + ks * 8, dbl, idesc, 1u);
+                    umma_tf32_ts(tmem, ahi + ks * 8, dbh, idesc, acc);
+                }
+                umma_commit(&bar_free[s]);
+            }
+            umma_commit(&bar_accum);
+        }
+    } else if (warp < 6) {
+        // ---- A converters: warp q <-> atom q (rows 32q .. 32q+31 of the M tile), lane = channel
+        // a warp may only touch TMEM lanes [32 (warp % 4), +32): warp with quarter q converts atom q (M rows 32q .. 32q+31)
+        const int q = warp & 3;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+            mbar_wait(&bar_full[s], ph, 3);
+            float hi[32], lo[32];
+            if (q < valid_atoms) {
+                const uint8_t* ap = raw_a(s) + q * 4096 + (lane & 3) * 4;
+#pragma unroll
+                for (int px = 0; px < 32; ++px) {
+                    // element (pixel px, channel lane): 16-byte chunk (lane / 4) XOR (px % 8), word lane % 4
+                    const float v = *reinterpret_cast<const float*>(ap + px * 128 + (((lane >> 2) ^ (px & 7)) << 4));
+                    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                    hi[px] = h; lo[px] = v - h;
+                }
+            } else {
+#pragma unroll
+                for (int px = 0; px < 32; ++px) { hi[px] = 0.f; lo[px] = 0.f; }
+            }
+            // slot s was last read by the MMAs of iteration it - kWgStages, whose completion released bar_free[s] to the
+            // producer before this stage was refilled, so the slot is free once bar_full[s] has fired
+            tcgen05_fence_after();
+            const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + s * 64;
+            tmem_st_32x32(dst, hi);
+            tmem_st_32x32(dst + 32, lo);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bar_aready[s]);
+        }
+        mbar_wait(&bar_accum, 0, 4);
+        tcgen05_fence_after();
+        const int row = q * 32 + lane;
+        const int mm = blockIdx.x * 128 + row;
+        const bool valid = mm < p.mtot && iters > 0;
+#pragma unroll 1
+        for (int c = 0; c < BNT / 32; ++c) {
+            float v[32], v2[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(BNT + c * 32), v2);
+            if (!valid) continue;
+            float* o = p.dw + (long long)mm * p.cout + co0 + c * 32;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) atomicAdd(o + jj, v[jj] + v2[jj]);
+        }
+        tcgen05_fence_before();
+    } else {
+        // ---- B transposers (128 threads)
+        const int tid = threadIdx.x - 192;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+            mbar_wait(&bar_full[s], ph, 6);
+            for (int qq = tid; qq < (BNT / 32) * 256; qq += 128)
+                transpose_split_chunk(raw_b(s) + (qq >> 8) * 4096, b_hi(s), b_lo(s), (qq >> 8) * 32, qq & 255);
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_bready[s]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+}  // namespace tcv2
