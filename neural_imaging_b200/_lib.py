@@ -26,7 +26,7 @@ PAD_ZERO, PAD_SYMMETRIC, PAD_REFLECT = 0, 1, 2
 
 _CTYPES = {
     'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
-    'unsigned long long': ctypes.c_ulonglong, 'ni_stream_t': ctypes.c_void_p, 'void': None,
+    'unsigned long long': ctypes.c_ulonglong, 'long long*': ctypes.c_void_p, 'ni_stream_t': ctypes.c_void_p, 'void': None,
 }
 
 
@@ -85,7 +85,7 @@ class _Lib:
         if name not in protos:
             raise AttributeError(name)
         fn = getattr(self._dll, name)
-        if protos[name][0] is not ctypes.c_int or name in ('ni_version', 'ni_device_arch', 'ni_conv2d_tc_supported', 'ni_conv2d_small_supported'):
+        if protos[name][0] is not ctypes.c_int or name in ('ni_version', 'ni_device_arch', 'ni_conv2d_tc_supported', 'ni_conv2d_small_supported', 'ni_tma_probe'):
             return fn
 
         def checked(*args):

@@ -16,6 +16,8 @@
 // (tap, ci) in 32-row atoms (fills the 128-row tile even for 32-channel layers), split-K over pixel ranges.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "conv_desc.h"
@@ -25,23 +27,24 @@
 
 namespace {
 
-// w (taps, cin, cout) HWIO -> out (2, taps, N, K) K-major hi / lo. transpose: N = cout, K = cin (fprop); else N = cin, K = cout.
-__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int transpose) {
+// w (taps, cin, cout) HWIO -> tiles for the gemm kernel: block ((tap * K/32 + kc) * N/bnt + nt) = [hi | lo], each a
+// (bnt rows x 32 k) K-major SWIZZLE_128B tile exactly as the MMA reads it. transpose: N = cout, K = cin (fprop); else N = cin, K = cout.
+__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int transpose, int bnt) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)taps * cin * cout;
     if (i >= total) return;
-    float v;
-    if (transpose) {
-        const int ci = (int)(i % cin);
-        const long long t = i / cin;
-        const int co = (int)(t % cout), tap = (int)(t / cout);
-        v = w[((long long)tap * cin + ci) * cout + co];
-    } else {
-        v = w[i];
-    }
+    const int N = transpose ? cout : cin, K = transpose ? cin : cout;
+    const int k = (int)(i % K);
+    const long long t = i / K;
+    const int n = (int)(t % N), tap = (int)(t / N);
+    const float v = transpose ? w[((long long)tap * cin + k) * cout + n] : w[((long long)tap * cin + n) * cout + k];
+    const int kc = k >> 5, kl = k & 31, nt = n / bnt, nl = n - nt * bnt;
+    const long long block = ((long long)tap * (K >> 5) + kc) * (N / bnt) + nt;
+    const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) + (kl & 3));
     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    out[i] = h;
-    out[total + i] = v - h;
+    float* o = out + block * (2 * bnt * 32);
+    o[off] = h;
+    o[bnt * 32 + off] = v - h;
 }
 
 std::mutex g_scratch_mutex;
@@ -96,7 +99,17 @@ bool pick_tile(int h, int w, int pixels, int& bw, int& bh, int& bn) {
     return bn <= 256;
 }
 
-int pick_bnt(int n) { return n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 0)); }
+int bnt_cap() {
+    static int cap = 0;
+    if (!cap) { const char* e = getenv("NI_TC_BNT_MAX"); cap = e ? atoi(e) : 128; if (cap != 32 && cap != 64) cap = 128; }
+    return cap;
+}
+int pick_bnt(int n) {
+    const int cap = bnt_cap();
+    if (n % 128 == 0 && cap >= 128) return 128;
+    if (n % 64 == 0 && cap >= 64) return 64;
+    return n % 32 == 0 ? 32 : 0;
+}
 
 template <typename K>
 int set_dyn_smem(K kern, size_t bytes) {
@@ -123,18 +136,11 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     int rc = get_scratch(wbytes, &scratch);
     if (rc) return rc;
     const long long total = (long long)taps * K * N;
-    tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1);
+    tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1, bnt);
     NI_LAUNCH_CHECK();
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA;
     rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.bw, p.bh, p.bn);
     if (rc) return rc;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)(2 * taps)};
-        cuuint64_t str[2] = {(cuuint64_t)K * 4, (cuuint64_t)K * N * 4};
-        cuuint32_t box[3] = {32, (cuuint32_t)bnt, 1};
-        rc = encode_map(&tmB, scratch, 3, dims, str, box);
-        if (rc) return rc;
-    }
     p.n = d->n; p.oh = th; p.ow = tw;
     p.tiles_w = tw / p.bw; p.tiles_h = th / p.bh;
     const int tiles_n = (d->n + p.bn - 1) / p.bn;
@@ -156,10 +162,17 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)(N / bnt));
 #define NI_TC_GEMM(B)                                                                                          \
     {                                                                                                          \
-        const size_t smem = (size_t)tcv2::kSmemStages * (tcv2::kAraw + 2 * B * 128) + 1024;                    \
+        const size_t smem = (size_t)tcv2::Rings<B>::SMEM + 1024;                                               \
         rc = set_dyn_smem(tcv2::conv_tc2_gemm_kernel<B>, smem);                                                \
         if (rc) return rc;                                                                                     \
-        tcv2::conv_tc2_gemm_kernel<B><<<grid, tcv2::kThreadsGemm, smem, st>>>(tmA, tmB, p);                    \
+        if (getenv("NI_TC_DEBUG")) {                                                                           \
+            int nb = -1;                                                                                       \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tcv2::conv_tc2_gemm_kernel<B>, tcv2::Roles<B>::THREADS, smem); \
+            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, tcv2::conv_tc2_gemm_kernel<B>);                  \
+            fprintf(stderr, "tc gemm<%d>: grid %u x %u, threads %d, smem %zu, regs %d, static smem %zu, occupancy %d CTA/SM, nacc %d\n", B, grid.x, grid.y, \
+                    tcv2::Roles<B>::THREADS, smem, fa.numRegs, fa.sharedSizeBytes, nb, p.nacc);                \
+        }                                                                                                      \
+        tcv2::conv_tc2_gemm_kernel<B><<<grid, tcv2::Roles<B>::THREADS, smem, st>>>(tmA, scratch, p);           \
     }
     if (bnt == 128) NI_TC_GEMM(128) else if (bnt == 64) NI_TC_GEMM(64) else NI_TC_GEMM(32)
 #undef NI_TC_GEMM

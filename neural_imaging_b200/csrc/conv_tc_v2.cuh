@@ -15,10 +15,15 @@
 namespace tcv2 {
 using namespace tc;
 
-constexpr int kSmemStages = 3;   // TMA ring: raw A tile + B hi + B lo
 constexpr int kTmemSlots = 2;    // A (hi | lo) slots in tensor memory, 64 columns each
 constexpr int kAraw = 16384;
-constexpr int kThreadsGemm = 192;
+// warp 0: A producer, 1: MMA issuer, 2 .. 2+NCW-1: converters + epilogue, last: B producer. NCW = 8 for the N = 128 tile
+// (+20 %: one warp per scheduler cannot hide its own latencies), NCW = 4 for N <= 64 so that two CTAs share an SM.
+template <int BNT> struct Roles {
+    static constexpr int NCW = BNT == 128 ? 8 : 4;
+    static constexpr int THREADS = (3 + NCW) * 32;
+    static constexpr int MIN_CTAS = BNT == 128 ? 1 : 2;   // caps registers at 128 so that two 7-warp CTAs really co-reside
+};
 
 struct GemmParams {
     int n, oh, ow;
@@ -48,17 +53,27 @@ __device__ __forceinline__ uint32_t pow2_cols(uint32_t want) {
     return want <= 32 ? 32 : (want <= 64 ? 64 : (want <= 128 ? 128 : (want <= 256 ? 256 : 512)));
 }
 
+// Ring depths. The kernel is bound by how many bytes of TMA loads one SM keeps in flight (ncu: converters stalled on the
+// "tile landed" barrier 26 % of all samples, L2 at 17 %, tensor pipe at 27 % with a single 3-deep ring): activations stream
+// from HBM and need depth, weights are L2-resident and big, so the two operands get their own rings.
+template <int BNT> struct Rings {
+    static constexpr int SA = BNT == 128 ? 4 : 3;               // A stages, 16 KB each
+    static constexpr int SB = 3;                                // B stages, hi + lo = 2 * BNT * 128 bytes each
+    // BNT <= 64: 72 / 96 KB per CTA so that TWO CTAs share an SM (measured: one CTA with deeper rings is 1.7-1.9x slower)
+    static constexpr int B_BYTES = BNT * 128;
+    static constexpr int SMEM = SA * kAraw + SB * 2 * B_BYTES;
+};
+
 // TMEM map: [0, (nacc+1)*BNT) accumulators (D1_0.. D1_{nacc-1}, D2), then kTmemSlots x 64 columns of A (hi 32 | lo 32).
 template <int BNT>
-__global__ void __launch_bounds__(kThreadsGemm, 1)
-conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-    constexpr int B_BYTES = BNT * 128;
-    constexpr int STAGE_BYTES = kAraw + 2 * B_BYTES;
+__global__ void __launch_bounds__(Roles<BNT>::THREADS, Roles<BNT>::MIN_CTAS)
+conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ wtiled, const GemmParams p) {
+    constexpr int SA = Rings<BNT>::SA, SB = Rings<BNT>::SB, B_BYTES = Rings<BNT>::B_BYTES, NCW = Roles<BNT>::NCW;
     const uint32_t acc_cols = (uint32_t)(p.nacc + 1) * BNT;
     const uint32_t TMEM_COLS = pow2_cols(acc_cols + kTmemSlots * 64);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar_full[kSmemStages], bar_sfree[kSmemStages], bar_aready[kTmemSlots], bar_afree[kTmemSlots], bar_accum;
+    __shared__ uint64_t bar_afull[SA], bar_afree[SA], bar_bfull[SB], bar_bfree[SB], bar_tready[kTmemSlots], bar_tfree[kTmemSlots], bar_accum;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,12 +84,12 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int iters = taps * p.kchunks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSmemStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_sfree[s], 1); }
-        for (int t = 0; t < kTmemSlots; ++t) { mbar_init(&bar_aready[t], 128); mbar_init(&bar_afree[t], 1); }
+        for (int s = 0; s < SA; ++s) { mbar_init(&bar_afull[s], 1); mbar_init(&bar_afree[s], NCW * 32); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bfree[s], 1); }
+        for (int t = 0; t < kTmemSlots; ++t) { mbar_init(&bar_tready[t], NCW * 32); mbar_init(&bar_tfree[t], 1); }
         mbar_init(&bar_accum, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
     }
     if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
     tcgen05_fence_before();
@@ -83,31 +98,41 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem = tmem_slot;
     const uint32_t a_base = tmem + acc_cols;
 
-    auto a_raw = [&](int s) { return smem + s * STAGE_BYTES; };
-    auto b_hi = [&](int s) { return smem + s * STAGE_BYTES + kAraw; };
-    auto b_lo = [&](int s) { return smem + s * STAGE_BYTES + kAraw + B_BYTES; };
+    auto a_raw = [&](int s) { return smem + s * kAraw; };
+    auto b_hi = [&](int s) { return smem + SA * kAraw + s * 2 * B_BYTES; };
+    auto b_lo = [&](int s) { return smem + SA * kAraw + s * 2 * B_BYTES + B_BYTES; };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0) {   // ---- A producer
             for (int it = 0; it < iters; ++it) {
-                const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
-                mbar_wait(&bar_sfree[s], ph ^ 1, 0);
-                mbar_expect_tx(&bar_full[s], kAraw + 2 * B_BYTES);
+                const int s = it % SA, ph = (it / SA) & 1;
+                mbar_wait(&bar_afree[s], ph ^ 1, 0);
+                mbar_expect_tx(&bar_afull[s], kAraw);
                 const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
                 const int a = tap / p.kw, b = tap - a * p.kw;
-                tma_load_4d(a_raw(s), &tmA, &bar_full[s], kc * 32, x0 + p.off_x0 + p.off_sign * b, y0 + p.off_y0 + p.off_sign * a, n0);
-                tma_load_3d(b_hi(s), &tmB, &bar_full[s], kc * 32, ntile0, tap);
-                tma_load_3d(b_lo(s), &tmB, &bar_full[s], kc * 32, ntile0, taps + tap);
+                tma_load_4d(a_raw(s), &tmA, &bar_afull[s], kc * 32, x0 + p.off_x0 + p.off_sign * b, y0 + p.off_y0 + p.off_sign * a, n0);
+            }
+        }
+    } else if (warp == 2 + NCW) {
+        if (lane == 0) {   // ---- B producer
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % SB, ph = (it / SB) & 1;
+                mbar_wait(&bar_bfree[s], ph ^ 1, 7);
+                mbar_expect_tx(&bar_bfull[s], 2 * B_BYTES);
+                // weights are pre-tiled by the prep kernel: block (tap, kc, n-tile) = [hi tile | lo tile], already in the swizzled
+                // K-major order, so one contiguous bulk copy replaces two 128-row tensor boxes (TMA cost is per box row)
+                const float* src = wtiled + ((size_t)it * gridDim.y + blockIdx.y) * (size_t)(2 * BNT * 32);
+                bulk_load_1d(b_hi(s), src, 2 * B_BYTES, &bar_bfull[s]);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0) {   // ---- MMA issuer
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
             for (int it = 0; it < iters; ++it) {
-                const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
+                const int s = it % SB, ph = (it / SB) & 1;
                 const int t = it % kTmemSlots, pt = (it / kTmemSlots) & 1;
-                mbar_wait(&bar_full[s], ph, 1);
-                mbar_wait(&bar_aready[t], pt, 2);
+                mbar_wait(&bar_bfull[s], ph, 1);
+                mbar_wait(&bar_tready[t], pt, 2);
                 tcgen05_fence_after();
                 const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
                 const uint32_t ahi = a_base + t * 64, alo = ahi + 32;
@@ -120,22 +145,27 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
                     umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (it >= p.nacc || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(&bar_sfree[s]);
-                umma_commit(&bar_afree[t]);
+                umma_commit(&bar_bfree[s]);
+                umma_commit(&bar_tfree[t]);
             }
             umma_commit(&bar_accum);
         }
     } else {
-        const int q = warp & 3, row = q * 32 + lane;
+        // ---- converters (warps 2-9): A tile row -> registers -> hi / lo -> TMEM. Two warps share each TMEM lane quarter
+        // (a warp may only touch lanes [32 (warp % 4), +32)) and take 16 of the 32 K-columns each: with one warp per
+        // quarter the conversion (one warp per scheduler, nothing to hide its latencies) was slower than the MMAs it feeds.
+        constexpr int NH = NCW / 4;            // warps per TMEM lane quarter (1 or 2)
+        constexpr int CW = 32 / NH;            // K-columns converted by one thread
+        const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % kSmemStages, ph = (it / kSmemStages) & 1;
+            const int s = it % SA, ph = (it / SA) & 1;
             const int t = it % kTmemSlots, pt = (it / kTmemSlots) & 1;
-            mbar_wait(&bar_full[s], ph, 3);
-            float hi[32], lo[32];
+            mbar_wait(&bar_afull[s], ph, 3);
+            float hi[CW], lo[CW];
             const uint8_t* rp = a_raw(s) + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = *reinterpret_cast<const float4*>(rp + ((c ^ (row & 7)) << 4));
+            for (int c = 0; c < CW / 4; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(rp + ((((CW / 4) * half + c) ^ (row & 7)) << 4));
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -144,14 +174,15 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     lo[4 * c + e] = vv[e] - h;
                 }
             }
-            mbar_wait(&bar_afree[t], pt ^ 1, 5);
+            mbar_arrive(&bar_afree[s]);          // the tile is in registers: hand the stage back to the A producer
+            mbar_wait(&bar_tfree[t], pt ^ 1, 5);
             tcgen05_fence_after();
-            const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + t * 64;
-            tmem_st_32x32(dst, hi);
-            tmem_st_32x32(dst + 32, lo);
+            const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + t * 64 + CW * half;
+            if constexpr (CW == 32) { tmem_st_32x32(dst, hi); tmem_st_32x32(dst + 32, lo); }
+            else { tmem_st_32x16(dst, hi); tmem_st_32x16(dst + 32, lo); }
             tmem_st_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bar_aready[t]);
+            mbar_arrive(&bar_tready[t]);
         }
         // ---- epilogue
         mbar_wait(&bar_accum, 0, 4);
@@ -160,7 +191,7 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;
         const bool valid = on < p.n && oy < p.oh && ox < p.ow;
 #pragma unroll 1
-        for (int c = 0; c < BNT / 32; ++c) {
+        for (int c = half; c < BNT / 32; c += NH) {   // the warps of a lane quarter interleave the 32-column chunks
             float v[32], v2[32];
             tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             for (int a2 = 1; a2 <= p.nacc; ++a2) {
