@@ -153,6 +153,16 @@ int ni_pad_fold(const float* dpad, float* dx, int n, int h, int w, int c, int pa
  * also replaces the host-side NaN scan (:281): *nonfinite_flag |= 1 if any gradient is NaN/Inf. */
 int ni_adam_keras(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   long long step, float gscale, int* nonfinite_flag, ni_stream_t stream);
+/* DiscreteLatent + Quantization('soft-codebook') + tf_helpers.entropy histogram (models/layers.py:139-170,195-203,
+ * helpers/tf_helpers.py:290-333), float64 inside like the reference. hist_acc: ncodes doubles zeroed by the caller (sum of the
+ * normalised weights per bin); gh: ncodes doubles = d loss / d hist_k / n; dscale_acc: one double zeroed by the caller. */
+int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc, long long n,
+                               int ncodes, double nu, double gamma, ni_stream_t stream);
+int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* g_out, const double* gh, float* dx,
+                               double* dscale_acc, long long n, int ncodes, double nu, double gamma, ni_stream_t stream);
+/* tf.nn.leaky_relu on a residual-branch input (models/compression.py:224) */
+int ni_leaky_relu_fwd(const float* x, float* y, long long n, float alpha, ni_stream_t stream);
+int ni_leaky_relu_bwd(const float* x, const float* dy, float* dx, long long n, float alpha, int accumulate, ni_stream_t stream);
 int ni_fill(float* p, float value, long long n, ni_stream_t stream);
 int ni_affine(const float* x, float* y, float a, float b, int clip, long long n, ni_stream_t stream);
 

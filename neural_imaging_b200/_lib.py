@@ -25,7 +25,7 @@ MODE_PLAIN, MODE_BLOCK2 = 0, 1
 PAD_ZERO, PAD_SYMMETRIC, PAD_REFLECT = 0, 1, 2
 
 _CTYPES = {
-    'int': ctypes.c_int, 'float': ctypes.c_float, 'long long': ctypes.c_longlong,
+    'int': ctypes.c_int, 'float': ctypes.c_float, 'double': ctypes.c_double, 'long long': ctypes.c_longlong,
     'unsigned long long': ctypes.c_ulonglong, 'long long*': ctypes.c_void_p, 'ni_stream_t': ctypes.c_void_p, 'void': None,
 }
 

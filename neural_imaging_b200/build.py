@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             if verbose and out:
                 print(out)
     if force or jobs or _stale(LIB, objs):
-        run([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart', '-lcuda'])
+        run([NVCC, '-shared', '-o', LIB] + objs + ['-lcudart'])   # no -lcuda: driver entry points are resolved at run time
     return LIB
 
 

@@ -66,18 +66,35 @@ int get_scratch(size_t bytes, float** out) {
     return NI_OK;
 }
 
-int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+}  // namespace
+
+// cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so that the library has no link-time
+// dependency on libcuda.so.1: it must still load (and export its symbols) on a build box without a GPU driver.
+int ni_encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        NI_REQUIRE(ptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+        fn = reinterpret_cast<EncodeFn>(ptr);
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        const char* msg = nullptr;
-        cuGetErrorString(r, &msg);
-        ni_set_error("cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+        ni_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return NI_ERR_CUDA;
     }
     return NI_OK;
+}
+
+namespace {
+
+int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    return ni_encode_tiled(tm, base, rank, dims, strides_bytes, box);
 }
 
 // NHWC activation view (n, h, w, c) with channel pitch: 4-D map, box (32, bw, bh, bn)

@@ -1,0 +1,176 @@
+// Fused discrete-latent kernels of the learned codec (TwitterDCN): scaling -> soft-codebook quantisation -> soft
+// histogram for the differentiable entropy, forward and backward, in float64 like the reference.
+//
+// Replaces DiscreteLatent.call (models/layers.py:195-203), Quantization('soft-codebook') (models/layers.py:139-170) and
+// tf_helpers.entropy (helpers/tf_helpers.py:290-333). The reference materialises the (n_values x 32) float64 weight
+// matrix TWICE (2.7 GB each at M = 1280); here the weights of one value live in registers and only the 32-bin
+// histogram leaves the kernel.
+//   w_k   = (1 + (gamma (v - c_k))^2 / nu)^(-(nu+1)/2)           (t-Student, nu > 0)   or   exp(-gamma (v - c_k)^2)  (nu <= 0)
+//   wn_k  = (w_k + 1e-72) / sum_j (w_j + 1e-72)
+//   soft  = sum_k wn_k c_k ;  hard = c[argmax_k wn_k] ;  out = float(hard - soft) + float(soft)      (straight-through)
+//   hist_k = mean_i wn_ik ;  h = clip(hist, 1e-9) / sum clip ;  H = -sum h ln h / 0.6931
+#include "ni_common.cuh"
+
+namespace {
+
+constexpr int kMaxCodes = 256;
+constexpr int kT = 128;
+
+struct LatentParams {
+    long long n;
+    int ncodes;
+    double nu, gamma;
+};
+
+__device__ __forceinline__ double kernel_weight(double diff, double nu, double gamma, double& dlog) {
+    // returns w and d(ln w)/dv (diff = v - c)
+    if (nu > 0) {
+        const double g = gamma * diff;
+        const double base = 1.0 + g * g / nu;
+        dlog = -(nu + 1.0) / 2.0 * (2.0 * gamma * g / nu) / base;
+        return pow(base, -(nu + 1.0) / 2.0);
+    }
+    dlog = -2.0 * gamma * diff;
+    return exp(-gamma * diff * diff);
+}
+
+// hist_acc[k] += sum_i wn_ik (double atomics, one per block and bin)
+__global__ void __launch_bounds__(kT)
+latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ codebook, float* __restrict__ out,
+                  double* __restrict__ hist_acc, LatentParams p) {
+    __shared__ double sh[kMaxCodes];
+    __shared__ float cb[kMaxCodes];
+    for (int k = threadIdx.x; k < p.ncodes; k += kT) { sh[k] = 0.0; cb[k] = codebook[k]; }
+    __syncthreads();
+    const float sc = scale ? *scale : 1.f;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < p.n; i += (long long)gridDim.x * kT) {
+        const float vf = x[i] * sc;                  // float32 multiply, as the reference (latent * scaling_factor)
+        const double v = (double)vf;
+        double S = 0.0, soft = 0.0, best = -1.0;
+        int arg = 0;
+        for (int k = 0; k < p.ncodes; ++k) {
+            double dl;
+            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
+            S += w;
+            soft += w * (double)cb[k];
+            if (w > best) { best = w; arg = k; }
+        }
+        soft /= S;
+        const float softf = (float)soft, hard = cb[arg];
+        out[i] = (hard - softf) + softf;
+        if (hist_acc) {
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = (kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72) / S;
+                atomicAdd(&sh[k], w);
+            }
+        }
+    }
+    __syncthreads();
+    if (hist_acc)
+        for (int k = threadIdx.x; k < p.ncodes; k += kT) atomicAdd(hist_acc + k, sh[k]);
+}
+
+// dx_i = scale * dv_i, dv_i = g_out_i * dsoft/dv + sum_k gh_k * dwn_ik/dv ; dscale += sum_i dv_i * x_i
+// gh_k = (entropy upstream) * dH/dhist_k / n   (computed by the caller from the global histogram)
+__global__ void __launch_bounds__(kT)
+latent_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ codebook,
+                  const float* __restrict__ g_out, const double* __restrict__ gh, float* __restrict__ dx, double* __restrict__ dscale_acc,
+                  LatentParams p) {
+    __shared__ float cb[kMaxCodes];
+    __shared__ double sgh[kMaxCodes];
+    __shared__ double red[kT / 32];
+    for (int k = threadIdx.x; k < p.ncodes; k += kT) { cb[k] = codebook[k]; sgh[k] = gh ? gh[k] : 0.0; }
+    __syncthreads();
+    const float sc = scale ? *scale : 1.f;
+    double ds = 0.0;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < p.n; i += (long long)gridDim.x * kT) {
+        const float xf = x[i];
+        const double v = (double)(xf * sc);
+        double S = 0.0, A = 0.0;            // S = sum (w+eps), A = sum w a   (a = dlnw/dv)
+        for (int k = 0; k < p.ncodes; ++k) {
+            double dl;
+            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
+            S += w + 1e-72;
+            A += w * dl;
+        }
+        double dsoft = 0.0, dent = 0.0;
+        for (int k = 0; k < p.ncodes; ++k) {
+            double dl;
+            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
+            const double dwn = (w * dl) / S - (w + 1e-72) * A / (S * S);
+            dsoft += (double)cb[k] * dwn;
+            dent += sgh[k] * dwn;
+        }
+        const double dv = (g_out ? (double)g_out[i] : 0.0) * dsoft + dent;
+        dx[i] = (float)(dv * (double)sc);
+        ds += dv * (double)xf;
+    }
+    if (dscale_acc) {
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int k = 0; k < kT / 32; ++k) t += red[k];
+            atomicAdd(dscale_acc, t);
+        }
+    }
+}
+
+// y = act(x) elementwise (leaky-relu on a residual-branch input, models/compression.py:224) and its backward
+__global__ void lrelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float alpha) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) { const float v = x[i]; y[i] = v > 0.f ? v : alpha * v; }
+}
+// dx (+)= dy * act'(x)
+__global__ void lrelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n, float alpha,
+                                 int accumulate) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) { const float g = dy[i] * (x[i] > 0.f ? 1.f : alpha); dx[i] = accumulate ? dx[i] + g : g; }
+}
+
+}  // namespace
+
+// out: quantised latent (n floats). hist_acc: 32 (ncodes) doubles, zeroed by the caller, receives sum_i wn_ik (may be NULL).
+// scale: device pointer to the trainable scaling factor (NULL = 1). codebook: ncodes floats on the device.
+extern "C" int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc,
+                                          long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
+    NI_REQUIRE(x && codebook && out && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes, "ni_latent_softcodebook_fwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    LatentParams p{n, ncodes, nu, gamma};
+    int grid = ni_cdiv(n, kT * 4);
+    if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
+    latent_fwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, out, hist_acc, p);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// g_out: gradient w.r.t. the quantised latent (NULL = 0). gh: ncodes doubles = d(loss)/d(hist_k) / n (NULL = no entropy term).
+// dscale_acc: one double, zeroed by the caller, receives d(loss)/d(scale) (may be NULL).
+extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* g_out, const double* gh,
+                                          float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
+    NI_REQUIRE(x && codebook && dx && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes, "ni_latent_softcodebook_bwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    LatentParams p{n, ncodes, nu, gamma};
+    int grid = ni_cdiv(n, kT * 4);
+    if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
+    latent_bwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, g_out, gh, dx, dscale_acc, p);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_leaky_relu_fwd(const float* x, float* y, long long n, float alpha, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0, "ni_leaky_relu_fwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    lrelu_fwd_kernel<<<ni_cdiv(n, 256), 256, 0, st>>>(x, y, n, alpha);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+extern "C" int ni_leaky_relu_bwd(const float* x, const float* dy, float* dx, long long n, float alpha, int accumulate, cudaStream_t st) {
+    NI_REQUIRE(x && dy && dx && n >= 0, "ni_leaky_relu_bwd: invalid arguments");
+    if (n == 0) return NI_OK;
+    lrelu_bwd_kernel<<<ni_cdiv(n, 256), 256, 0, st>>>(x, dy, dx, n, alpha, accumulate);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}

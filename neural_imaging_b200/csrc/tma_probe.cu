@@ -6,6 +6,8 @@
 #include "ni_common.cuh"
 #include "tc_common.cuh"
 
+int ni_encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
 namespace {
 using namespace tc;
 
@@ -47,11 +49,9 @@ extern "C" int ni_tma_probe(const float* x, int n, int h, int w, int c, int stag
     CUtensorMap tm;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t str[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1}, estr[4] = {1, 1, 1, 1};
-    CUresult r = cuTensorMapEncodeTiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, str, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NI_REQUIRE(r == CUDA_SUCCESS, "ni_tma_probe: cuTensorMapEncodeTiled failed");
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    int rc = ni_encode_tiled(&tm, x, 4, dims, str, box);
+    if (rc) return rc;
     const long long total_boxes = (long long)n * (h / bh) * (w / bw) * (c / 32);
     int grid = (int)(total_boxes / boxes_per_cta);
     if (grid > max_grid) grid = max_grid;
