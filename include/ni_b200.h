@@ -155,11 +155,14 @@ int ni_adam_keras(float* p, const float* g, float* m, float* v, long long n, flo
                   long long step, float gscale, int* nonfinite_flag, ni_stream_t stream);
 /* DiscreteLatent + Quantization('soft-codebook') + tf_helpers.entropy histogram (models/layers.py:139-170,195-203,
  * helpers/tf_helpers.py:290-333), float64 inside like the reference. hist_acc: ncodes doubles zeroed by the caller (sum of the
- * normalised weights per bin); gh: ncodes doubles = d loss / d hist_k / n; dscale_acc: one double zeroed by the caller. */
+ * normalised weights per bin, evaluated at the QUANTISED values like the reference); q: the forward's output;
+ * gh: ncodes doubles = d loss / d hist_k / n; dscale_acc: one double zeroed by the caller. */
 int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc, long long n,
                                int ncodes, double nu, double gamma, ni_stream_t stream);
-int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* g_out, const double* gh, float* dx,
-                               double* dscale_acc, long long n, int ncodes, double nu, double gamma, ni_stream_t stream);
+int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
+                               const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, ni_stream_t stream);
+/* entropy estimate from the accumulated soft histogram (helpers/tf_helpers.py:326-331) and its gradient w.r.t. the histogram */
+int ni_entropy_from_hist(const double* hist_acc, long long n, int ncodes, double upstream, float* h_out, double* gh_out, ni_stream_t stream);
 /* tf.nn.leaky_relu on a residual-branch input (models/compression.py:224) */
 int ni_leaky_relu_fwd(const float* x, float* y, long long n, float alpha, ni_stream_t stream);
 int ni_leaky_relu_bwd(const float* x, const float* dy, float* dx, long long n, float alpha, int accumulate, ni_stream_t stream);

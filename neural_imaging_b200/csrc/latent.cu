@@ -57,12 +57,20 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
         }
         soft /= S;
         const float softf = (float)soft, hard = cb[arg];
-        out[i] = (hard - softf) + softf;
+        const float q = (hard - softf) + softf;
+        out[i] = q;
         if (hist_acc) {
+            // the reference estimates the entropy of the QUANTISED latent (models/layers.py:200-201): weights at q
+            const double vq = (double)q;
+            double Sq = 0.0;
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                const double w = (kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72) / S;
-                atomicAdd(&sh[k], w);
+                Sq += kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
+            }
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = (kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl) + 1e-72) / Sq;
+                if (w > 1e-30) atomicAdd(&sh[k], w);          // contributions below 1e-30 cannot change a float64 sum >= 1e-9 * n
             }
         }
     }
@@ -71,11 +79,12 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
         for (int k = threadIdx.x; k < p.ncodes; k += kT) atomicAdd(hist_acc + k, sh[k]);
 }
 
-// dx_i = scale * dv_i, dv_i = g_out_i * dsoft/dv + sum_k gh_k * dwn_ik/dv ; dscale += sum_i dv_i * x_i
-// gh_k = (entropy upstream) * dH/dhist_k / n   (computed by the caller from the global histogram)
+// dx_i = scale * dv_i, dv_i = (g_out_i + sum_k gh_k * dwn_k(q_i)/dq) * dsoft/dv ; dscale += sum_i dv_i * x_i
+// (the quantised value q = stop_gradient(hard - soft) + soft has dq/dsoft = 1; the entropy is a function of q)
+// gh_k = (entropy upstream) * dH/dhist_k / n   (computed by ni_entropy_from_hist from the global histogram)
 __global__ void __launch_bounds__(kT)
 latent_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ codebook,
-                  const float* __restrict__ g_out, const double* __restrict__ gh, float* __restrict__ dx, double* __restrict__ dscale_acc,
+                  const float* __restrict__ q, const float* __restrict__ g_out, const double* __restrict__ gh, float* __restrict__ dx, double* __restrict__ dscale_acc,
                   LatentParams p) {
     __shared__ float cb[kMaxCodes];
     __shared__ double sgh[kMaxCodes];
@@ -98,11 +107,24 @@ latent_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
         for (int k = 0; k < p.ncodes; ++k) {
             double dl;
             const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
-            const double dwn = (w * dl) / S - (w + 1e-72) * A / (S * S);
-            dsoft += (double)cb[k] * dwn;
-            dent += sgh[k] * dwn;
+            dsoft += (double)cb[k] * ((w * dl) / S - (w + 1e-72) * A / (S * S));
         }
-        const double dv = (g_out ? (double)g_out[i] : 0.0) * dsoft + dent;
+        if (gh) {
+            const double vq = (double)q[i];
+            double Sq = 0.0, Aq = 0.0;
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl);
+                Sq += w + 1e-72;
+                Aq += w * dl;
+            }
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl);
+                dent += sgh[k] * ((w * dl) / Sq - (w + 1e-72) * Aq / (Sq * Sq));
+            }
+        }
+        const double dv = ((g_out ? (double)g_out[i] : 0.0) + dent) * dsoft;
         dx[i] = (float)(dv * (double)sc);
         ds += dv * (double)xf;
     }
@@ -146,16 +168,17 @@ extern "C" int ni_latent_softcodebook_fwd(const float* x, const float* scale, co
     return NI_OK;
 }
 
-// g_out: gradient w.r.t. the quantised latent (NULL = 0). gh: ncodes doubles = d(loss)/d(hist_k) / n (NULL = no entropy term).
+// q: the quantised latent written by the forward (needed when gh != NULL). g_out: gradient w.r.t. the quantised latent (NULL = 0). gh: ncodes doubles = d(loss)/d(hist_k) / n (NULL = no entropy term).
 // dscale_acc: one double, zeroed by the caller, receives d(loss)/d(scale) (may be NULL).
-extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* g_out, const double* gh,
-                                          float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
-    NI_REQUIRE(x && codebook && dx && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes, "ni_latent_softcodebook_bwd: invalid arguments");
+extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
+                                          const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
+    NI_REQUIRE(x && codebook && dx && (q || !gh) && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes,
+               "ni_latent_softcodebook_bwd: invalid arguments");
     if (n == 0) return NI_OK;
     LatentParams p{n, ncodes, nu, gamma};
     int grid = ni_cdiv(n, kT * 4);
     if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
-    latent_bwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, g_out, gh, dx, dscale_acc, p);
+    latent_bwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, q, g_out, gh, dx, dscale_acc, p);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
@@ -171,6 +194,43 @@ extern "C" int ni_leaky_relu_bwd(const float* x, const float* dy, float* dx, lon
     NI_REQUIRE(x && dy && dx && n >= 0, "ni_leaky_relu_bwd: invalid arguments");
     if (n == 0) return NI_OK;
     lrelu_bwd_kernel<<<ni_cdiv(n, 256), 256, 0, st>>>(x, dy, dx, n, alpha, accumulate);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+namespace {
+// Single-block epilogue of the entropy estimate: H (float) and gh_k = upstream * dH/dhist_k / n from the accumulated histogram.
+__global__ void entropy_from_hist_kernel(const double* __restrict__ hist_acc, double n, int ncodes, double upstream, float* __restrict__ H_out,
+                                         double* __restrict__ gh_out) {
+    __shared__ double hc[256], dHdp[256];
+    __shared__ double T, dot;
+    const int k = threadIdx.x;
+    if (k < ncodes) hc[k] = fmax(hist_acc[k] / n, 1e-9);
+    __syncthreads();
+    if (k == 0) { double t = 0; for (int j = 0; j < ncodes; ++j) t += hc[j]; T = t; }
+    __syncthreads();
+    if (k < ncodes) { const double p = hc[k] / T; dHdp[k] = -(log(p) + 1.0) / 0.6931; }
+    __syncthreads();
+    if (k == 0) {
+        double h = 0, d = 0;
+        for (int j = 0; j < ncodes; ++j) { const double p = hc[j] / T; h -= p * log(p); d += p * dHdp[j]; }
+        dot = d;
+        if (H_out) *H_out = (float)(h / 0.6931);
+    }
+    __syncthreads();
+    if (k < ncodes && gh_out) {
+        const double pass = (hist_acc[k] / n) >= 1e-9 ? 1.0 : 0.0;     // clip_by_value passes the gradient inside the range
+        gh_out[k] = upstream * pass * (dHdp[k] - dot) / T / n;
+    }
+}
+}  // namespace
+
+// hist_acc: ncodes doubles (sum over the n values of the normalised weights). H_out: float entropy estimate (may be NULL).
+// gh_out: ncodes doubles = upstream * dH/dhist_k / n for ni_latent_softcodebook_bwd (may be NULL).
+extern "C" int ni_entropy_from_hist(const double* hist_acc, long long n, int ncodes, double upstream, float* h_out, double* gh_out,
+                                    cudaStream_t st) {
+    NI_REQUIRE(hist_acc && n > 0 && ncodes > 1 && ncodes <= 256, "ni_entropy_from_hist: invalid arguments");
+    entropy_from_hist_kernel<<<1, 256, 0, st>>>(hist_acc, (double)n, ncodes, upstream, h_out, gh_out);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }

@@ -103,7 +103,7 @@ class ParamStore:
             a = np.asarray(state[p.name], dtype=np.float32)
             if tuple(a.shape) != p.shape:
                 raise ValueError('shape mismatch for {}: {} vs {}'.format(p.name, a.shape, p.shape))
-            p.value.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            p.value.copy_(torch.from_numpy(np.ascontiguousarray(a)).reshape(p.shape))
 
 
 class Conv2D:
@@ -164,7 +164,7 @@ class Conv2D:
         return y
 
     def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
-              dx_accumulate=False):
+              dx_accumulate=False, need_dw=True):
         """Backward of fprop(x -> y) described by the forward descriptor `d`.
 
         dy is modified in place (multiplied by the activation derivative). dW / db go to the flat gradient buffer
@@ -173,7 +173,7 @@ class Conv2D:
         L = _lib.lib()
         st = stream()
         dyp, dyo, dym = dy_addr if dy_addr is not None else (d.out_pitch, d.out_coff, d.out_mode)
-        db = ptr(self.b.grad) if (self.b is not None and self.b.trainable) else None
+        db = ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
         if db is not None or d.act not in (ACT_NONE, ACT_CLIP01):
             L.ni_act_bwd_bias(ptr(y), ptr(dy), db, d.n, d.oh, d.ow, d.cout, d.out_pitch, d.out_coff, d.out_mode,
                               dyp, dyo, dym, d.act, d.act_alpha, self.bias_mod, st)
@@ -181,7 +181,7 @@ class Conv2D:
         ctypes.memmove(ctypes.byref(dd), ctypes.byref(d), ctypes.sizeof(ConvDesc))
         dd.out_pitch, dd.out_coff, dd.out_mode = dyp, dyo, dym
         dd.accumulate = 0
-        if self.w.trainable or dweight is not None:
+        if need_dw and (self.w.trainable or dweight is not None):
             L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(self.w.grad if dweight is None else dweight), st)
         if need_dx:
             if dx_addr is not None:

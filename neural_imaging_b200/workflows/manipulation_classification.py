@@ -233,8 +233,10 @@ class ManipulationClassification(object):
         train_nip = 'nip' in self._trainable and bool(self.nip._store.trainable)
         train_dcn = 'dcn' in self._trainable
         comp = self._distribution['compression']
-        if comp == 'dcn':
-            return self._training_step_dcn(x, t, lambda_nip, lambda_dcn, augment, learning_rate, grad_sync)
+        # sum-type loss terms (the codec's l2_loss and its global-histogram entropy) are scaled by the world size so that the
+        # 1/world average applied to the all-reduced gradients leaves them as the reference's single-process sums
+        world = getattr(grad_sync, 'world', 1)
+        lam_dcn = float(lambda_dcn) * world if train_dcn else 0.0
 
         # ---- forward
         Y = self.nip._forward(x, save=train_nip)
@@ -248,6 +250,13 @@ class ManipulationClassification(object):
             C = ws.get('C', c.shape)
             quality = self.codec._draw_quality(None)
             self.codec._with_quality(quality, lambda: self.codec._model.forward_into(c, C))
+        elif comp == 'dcn':
+            quality = None
+            self.codec.set_data_parallel(world)
+            C, entropy = self.codec.forward(c, save=(train_nip or train_dcn))
+            acc_dcn = ws.get('loss_dcn', (1,))
+            L.ni_fill(ptr(acc_dcn), 0.0, 1, s)
+            L.ni_image_loss(ptr(c), ptr(C), ptr(acc_dcn), c.numel(), 0, s)
         else:
             C, quality = c, None
         labels = self._device_labels(B)
@@ -258,12 +267,20 @@ class ManipulationClassification(object):
         L.ni_image_loss(ptr(Y), ptr(t), ptr(acc), Y.numel(), kind, s)
 
         # ---- backward
-        dC = self.fan.backward(dlogits, need_dx=train_nip)
+        codec_bwd = comp == 'dcn' and (train_nip or train_dcn)
+        dC = self.fan.backward(dlogits, need_dx=train_nip or codec_bwd)
+        if codec_bwd:
+            # d/dC of lambda_dcn * (l2_loss(c - C) + w * H); the entropy enters through the latent inside codec.backward
+            if lam_dcn:
+                L.ni_image_loss_grad(ptr(C), ptr(c), ptr(dC), C.numel(), 0, lam_dcn * C.numel() / (2.0 * 255.0 * 255.0), 1, s)
+            dc = self.codec.backward(dC, lam_dcn * float(self.codec._h.entropy_weight), need_dx=train_nip, need_dw=train_dcn)
+            if train_nip and lam_dcn:           # c is also the TARGET of the codec loss
+                L.ni_image_loss_grad(ptr(c), ptr(C), ptr(dc), c.numel(), 0, lam_dcn * c.numel() / (2.0 * 255.0 * 255.0), 1, s)
         if train_nip:
             if comp == 'jpeg':
                 dc = ws.get('dc', c.shape)
                 self.codec._with_quality(quality, lambda: self.codec._model.backward(c, dC, dc))
-            else:
+            elif comp != 'dcn':
                 dc = dC
             dm = self._downsample_bwd(dc, m.shape, ws)
             dY = ws.get('dY', Y.shape)
@@ -282,7 +299,13 @@ class ManipulationClassification(object):
         loss_ce_v = loss_ce / float(M)
         loss_nip_v = acc / float(Y.numel())
         loss = loss_ce_v + (float(lambda_nip) * loss_nip_v if 'nip' in self._trainable else 0.0)
-        loss_dcn = float('nan') if comp == 'jpeg' else 0.0    # Keras MSE with sample_weight = NaN entropy
+        if comp == 'dcn':
+            loss_dcn = acc_dcn / (2.0 * 255.0 * 255.0) + float(self.codec._h.entropy_weight) * entropy
+            if train_dcn:
+                loss = loss + float(lambda_dcn) * loss_dcn
+            loss_dcn = wrap(loss_dcn.reshape(()))
+        else:
+            loss_dcn = float('nan') if comp == 'jpeg' else 0.0    # Keras MSE with sample_weight = NaN entropy
         return wrap(loss.reshape(())), {'ce': wrap(loss_ce_v.reshape(())), 'nip': wrap(loss_nip_v.reshape(())), 'dcn': loss_dcn}
 
     def _downsample_bwd(self, dc, m_shape, ws):
@@ -296,9 +319,6 @@ class ManipulationClassification(object):
             L.ni_resize_bilinear_bwd(ptr(dc), ptr(dm), m_shape[0], m_shape[1], m_shape[2], dc.shape[1], dc.shape[2], 1.0, stream())
             return dm
         return dc
-
-    def _training_step_dcn(self, x, t, lambda_nip, lambda_dcn, augment, learning_rate, grad_sync):
-        raise NotImplementedError('compression=dcn training path is under construction')
 
     # ------------------------------------------------------------------------------------------------ summaries
     def summary_compact(self):

@@ -82,11 +82,15 @@ def run_manipulations(Y, names, strengths=None):
     return torch.cat([Y] + [MANIPULATIONS[n](Y, strengths[n]) for n in names], dim=0)
 
 
-def workflow_forward(P_nip, P_fan, x, names=('sharpen', 'resample', 'gaussian', 'jpeg'), quality=50, pool=2, nip='UNet'):
-    """run_workflow (:162-176) for the default distribution channel (pool:k + dJPEG(quality,'soft'))."""
+def workflow_forward(P_nip, P_fan, x, names=('sharpen', 'resample', 'gaussian', 'jpeg'), quality=50, pool=2, nip='UNet', P_dcn=None):
+    """run_workflow (:162-176) for the default distribution channel (pool:k + dJPEG(quality,'soft')), or, with P_dcn, the
+    learned codec (compression='dcn'). Returns (Y, c, C, probs[, entropy])."""
     Y = unet_forward(P_nip, x) if nip == 'UNet' else x
     m = run_manipulations(Y, names)
     c = R.avg_pool(m, pool) if pool > 1 else m
+    if P_dcn is not None:
+        C, ent = twitter_dcn_forward(P_dcn, c)[:2]
+        return Y, c, C, fan_forward(P_fan, C), ent
     C = R.djpeg(c, R.jpeg_qtable(quality, 0), R.jpeg_qtable(quality, 1), 'soft')[0] if quality else c
     probs = fan_forward(P_fan, C)
     return Y, c, C, probs
@@ -97,17 +101,24 @@ def batch_labels(batch_size, n_classes):
 
 
 def training_step(P_nip, P_fan, opt_state, x, y_target, lambda_nip=0.1, lr=1e-4, train_nip=True,
-                  names=('sharpen', 'resample', 'gaussian', 'jpeg'), quality=50, pool=2, nip='UNet'):
+                  names=('sharpen', 'resample', 'gaussian', 'jpeg'), quality=50, pool=2, nip='UNet',
+                  P_dcn=None, lambda_dcn=0.0, train_dcn=False):
     """ManipulationClassification.training_step (:260-285): loss = ce + lambda_nip * mse; shared Keras Adam.
     opt_state = {'t': int, 'm': {name: tensor}, 'v': {...}}; parameters are updated in place. Returns loss dict + grads."""
-    Y, c, C, probs = workflow_forward(P_nip, P_fan, x, names, quality, pool, nip)
+    out = workflow_forward(P_nip, P_fan, x, names, quality, pool, nip, P_dcn)
+    Y, c, C, probs = out[:4]
     n_classes = len(names) + 1
     loss_ce = R.sparse_categorical_crossentropy(batch_labels(x.shape[0], n_classes), probs)
     loss_nip = R.mse(y_target, Y)
     loss = loss_ce + (lambda_nip * loss_nip if train_nip else 0)
+    loss_dcn = dcn_loss(c, C, out[4]) if P_dcn is not None else None
+    if train_dcn:
+        loss = loss + lambda_dcn * loss_dcn
     params = [('fan/' + k, v) for k, v in P_fan.items()]
     if train_nip and nip == 'UNet':
         params += [('nip/' + k, v) for k, v in P_nip.items()]
+    if train_dcn:
+        params += [('dcn/' + k, v) for k, v in P_dcn.items()]
     grads = torch.autograd.grad(loss, [p for _, p in params], allow_unused=True)
     grads = [torch.zeros_like(p) if g is None else g for g, (_, p) in zip(grads, params)]
     opt_state['t'] += 1
@@ -115,5 +126,65 @@ def training_step(P_nip, P_fan, opt_state, x, y_target, lambda_nip=0.1, lr=1e-4,
         ms = [opt_state['m'].setdefault(k, torch.zeros_like(p)) for k, p in params]
         vs = [opt_state['v'].setdefault(k, torch.zeros_like(p)) for k, p in params]
         R.adam_keras_step([p for _, p in params], grads, ms, vs, opt_state['t'], lr)
-    return ({'loss': float(loss), 'ce': float(loss_ce), 'nip': float(loss_nip)},
-            OrderedDict((k, g) for (k, _), g in zip(params, grads)))
+    losses = {'loss': float(loss), 'ce': float(loss_ce), 'nip': float(loss_nip)}
+    if loss_dcn is not None:
+        losses['dcn'] = float(loss_dcn)
+    return losses, OrderedDict((k, g) for (k, _), g in zip(params, grads))
+
+
+# ------------------------------------------------------------------------------------------------ TwitterDCN
+def dcn_codebook(latent_bpf=5, dtype=torch.float32):
+    """models/layers.py:108-114."""
+    return torch.arange(-2 ** (latent_bpf - 1) + 1, 2 ** (latent_bpf - 1) + 1, dtype=dtype)
+
+
+def twitter_dcn_encode(P, x, latent_bpf=5):
+    """models/compression.py:213-241. P uses the product's names (encoder/conv2d[_k], .../latent_scaling)."""
+    act = R.ACT['leaky_relu']
+    cv = lambda t, name, stride=1: R.conv2d(t, P[name + '/kernel'], P[name + '/bias'], stride=stride)
+    net = 2 * (x - 0.5)
+    net = act(cv(net, 'encoder/conv2d', 2))
+    net = cv(net, 'encoder/conv2d_1', 2)
+    for i in range(3):
+        inp = R.leaky_relu(net) if i == 0 else net
+        net = net + cv(act(cv(inp, 'encoder/conv2d_%d' % (2 + 2 * i))), 'encoder/conv2d_%d' % (3 + 2 * i))
+    z = cv(net, 'encoder/conv2d_8', 2)
+    return R.discrete_latent(z, P.get('encoder/discrete_latent/latent_scaling'), dcn_codebook(latent_bpf)) + (z,)
+
+
+def twitter_dcn_decode(P, q):
+    """models/compression.py:247-272."""
+    act = R.ACT['leaky_relu']
+    cv = lambda t, name: R.conv2d(t, P[name + '/kernel'], P[name + '/bias'])
+    inet = R.depth_to_space(cv(q, 'decoder/conv2d_9'), 2)
+    for i in range(3):
+        inet = inet + cv(act(cv(inet, 'decoder/conv2d_%d' % (10 + 2 * i))), 'decoder/conv2d_%d' % (11 + 2 * i))
+    inet = R.depth_to_space(act(cv(inet, 'decoder/conv2d_16')), 2)
+    inet = R.depth_to_space(cv(inet, 'decoder/conv2d_17'), 2)
+    return R.ste_clip((inet + 1) / 2)
+
+
+def twitter_dcn_forward(P, x, latent_bpf=5):
+    q, ent, z = twitter_dcn_encode(P, x, latent_bpf)
+    return twitter_dcn_decode(P, q), ent, q, z
+
+
+def dcn_loss(x, y, ent, entropy_weight=250.0):
+    """models/compression.py:89-92."""
+    return R.l2_loss(x - y) + entropy_weight * ent.to(x.dtype)
+
+
+def dcn_training_step(P, opt_state, x, lr=1e-3, entropy_weight=250.0, latent_bpf=5):
+    """DCN.training_step (models/compression.py:123-139) with Keras Adam; parameters updated in place."""
+    y, ent, q, z = twitter_dcn_forward(P, x, latent_bpf)
+    loss = dcn_loss(x, y, ent, entropy_weight)
+    names = list(P.keys())
+    grads = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    grads = [torch.zeros_like(P[k]) if g is None else g for g, k in zip(grads, names)]
+    opt_state['t'] += 1
+    with torch.no_grad():
+        ms = [opt_state['m'].setdefault(k, torch.zeros_like(P[k])) for k in names]
+        vs = [opt_state['v'].setdefault(k, torch.zeros_like(P[k])) for k in names]
+        R.adam_keras_step([P[k] for k in names], grads, ms, vs, opt_state['t'], lr)
+    return ({'loss': float(torch.sqrt(2 * loss)), 'entropy': float(ent), 'raw_loss': float(loss)},
+            OrderedDict(zip(names, grads)), y.detach(), q.detach())

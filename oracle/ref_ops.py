@@ -362,3 +362,50 @@ def adam_keras_step(params, grads, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-7
         mi += (g - mi) * (1 - beta1)
         vi += (g * g - vi) * (1 - beta2)
         p -= lr_t * mi / (torch.sqrt(vi) + eps)
+
+
+# ------------------------------------------------------------------------------------------------ learned codec (DCN)
+def _codebook_weights(values, codebook, v=50, gamma=25):
+    """float64 kernel weights of every value w.r.t. every code word, normalised over the code book
+    (models/layers.py:139-156 and helpers/tf_helpers.py:308-321 are the same computation)."""
+    eps = 1e-72
+    dff = values.reshape(-1, 1).double() - codebook.reshape(1, -1).double()
+    if v <= 0:
+        weights = torch.exp(-gamma * dff ** 2)
+    else:
+        weights = (1 + (gamma * dff) ** 2 / v) ** (-(v + 1) / 2)
+    return (weights + eps) / (weights + eps).sum(dim=1, keepdim=True)
+
+
+def soft_codebook_quantization(x, codebook, v=50, gamma=25):
+    """Quantization('soft-codebook').call, models/layers.py:139-170: soft value through the gradient, hard value forward."""
+    weights = _codebook_weights(x, codebook, v, gamma)
+    soft = (weights @ codebook.reshape(-1, 1).double()).mean(dim=1).to(torch.float32).reshape(x.shape)
+    hard = codebook.reshape(-1)[weights.argmax(dim=1)].reshape(x.shape).to(torch.float32)
+    return (hard - soft).detach() + soft
+
+
+def entropy(values, codebook, v=50, gamma=25):
+    """helpers/tf_helpers.py:290-333: entropy of the soft histogram (returned as float32 like the reference)."""
+    weights = _codebook_weights(values, codebook, v, gamma)
+    histogram = weights.mean(dim=0).clamp(1e-9, float(np.finfo(np.float32).max))
+    histogram = histogram / histogram.sum()
+    return (-(histogram * torch.log(histogram)).sum() / 0.6931).to(torch.float32), histogram
+
+
+def discrete_latent(z, scale, codebook, v=50, gamma=25):
+    """DiscreteLatent.call, models/layers.py:195-203: the entropy is estimated on the QUANTISED latent."""
+    latent = z * scale.to(z.dtype) if scale is not None else z
+    if z.dtype == torch.float32:
+        q = soft_codebook_quantization(latent, codebook, v, gamma)
+    else:       # float64 truth run: keep the soft value in float64
+        weights = _codebook_weights(latent, codebook, v, gamma)
+        soft = (weights @ codebook.reshape(-1, 1).double()).reshape(z.shape)
+        hard = codebook.reshape(-1).double()[weights.argmax(dim=1)].reshape(z.shape)
+        q = (hard - soft).detach() + soft
+    return q, entropy(q, codebook, v, gamma)[0]
+
+
+def l2_loss(t):
+    """tf.nn.l2_loss."""
+    return (t * t).sum() / 2
