@@ -166,6 +166,12 @@ int ni_entropy_from_hist(const double* hist_acc, long long n, int ncodes, double
 /* tf.nn.leaky_relu on a residual-branch input (models/compression.py:224) */
 int ni_leaky_relu_fwd(const float* x, float* y, long long n, float alpha, ni_stream_t stream);
 int ni_leaky_relu_bwd(const float* x, const float* dy, float* dx, long long n, float alpha, int accumulate, ni_stream_t stream);
+/* ClassicISP tails: straight-through clip + gamma (models/pipelines.py:441-445) and the residual demosaicing combination
+ * y = x_bilinear - alpha * f with a trainable device scalar alpha (models/layers.py:249-256). dalpha is accumulated into. */
+int ni_gamma_clip_fwd(const float* x, float* y, long long n, float lo, float hi, float exponent, ni_stream_t stream);
+int ni_gamma_clip_bwd(const float* x, const float* dy, float* dx, long long n, float lo, float hi, float exponent, ni_stream_t stream);
+int ni_residual_alpha_fwd(const float* xb, const float* f, const float* alpha, float* y, long long n, int clip, ni_stream_t stream);
+int ni_residual_alpha_bwd(const float* dy, const float* f, const float* alpha, float* df, float* dalpha, long long n, ni_stream_t stream);
 int ni_fill(float* p, float value, long long n, ni_stream_t stream);
 int ni_affine(const float* x, float* y, float a, float b, int clip, long long n, ni_stream_t stream);
 

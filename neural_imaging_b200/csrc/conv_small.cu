@@ -249,7 +249,11 @@ int launch_wgrad(SmallWgradParams p, const float* x, const float* dy, float* dw,
     return NI_OK;
 }
 
-#define NI_SMALL_SHAPES(X) X(3, 3, 5) X(3, 32, 5) X(4, 32, 3) X(32, 12, 3) X(32, 3, 5) X(12, 32, 3)
+// FAN / U-Net ends; INet + ClassicISP 1x1 chains; DNet ends; TwitterDCN output layer
+#define NI_SMALL_SHAPES(X)                                                                              \
+    X(3, 3, 5) X(3, 32, 5) X(4, 32, 3) X(32, 12, 3) X(32, 3, 5) X(12, 32, 3)                            \
+    X(4, 12, 1) X(3, 3, 1) X(3, 12, 1) X(12, 3, 1) X(12, 12, 1) X(3, 3, 3)                              \
+    X(4, 64, 3) X(6, 64, 3) X(64, 6, 3) X(64, 3, 1) X(3, 64, 1) X(64, 12, 3) X(12, 64, 3)
 
 bool has_shape(int cin, int cout, int k) {
 #define X(a, b, c) if (cin == a && cout == b && k == c) return true;

@@ -35,6 +35,19 @@ def glorot_uniform(rng, shape):
     return rng.uniform(-limit, limit, size=shape).astype(np.float32)
 
 
+def variance_scaling(rng, shape, scale=1.0):
+    """tf.keras.initializers.VarianceScaling() defaults (fan_in, truncated normal at 2 sigma; models/pipelines.py:313):
+    stddev = sqrt(scale / fan_in) / 0.87962566103423978 (the truncation's variance correction)."""
+    receptive = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    std = math.sqrt(scale / max(1.0, shape[-2] * receptive)) / 0.87962566103423978
+    out = rng.normal(size=shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():                       # resample the tails (truncated normal)
+        out[bad] = rng.normal(size=int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (out * std).astype(np.float32)
+
+
 # bench.py's CPU-baseline leg sets this to build the models' initial weights without a GPU (specs only, no device buffers)
 HOST_ONLY = False
 
@@ -164,8 +177,11 @@ class Conv2D:
         return y
 
     def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
-              dx_accumulate=False, need_dw=True):
+              dx_accumulate=False, need_dw=True, dpad=None):
         """Backward of fprop(x -> y) described by the forward descriptor `d`.
+
+        For mirrored padding (REFLECT / SYMMETRIC + VALID conv) the input gradient is computed on the padded domain into
+        `dpad` (n, h+2p, w+2p, cin) and folded back into the plain tensor dx (the transpose of tf.pad).
 
         dy is modified in place (multiplied by the activation derivative). dW / db go to the flat gradient buffer
         (or `dweight`). dy_addr / dx_addr = (pitch, coff, mode) of the gradient buffers when they are laid out
@@ -184,11 +200,22 @@ class Conv2D:
         if need_dw and (self.w.trainable or dweight is not None):
             L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(self.w.grad if dweight is None else dweight), st)
         if need_dx:
+            wv = self.w.value if weight is None else weight
+            if d.pad_mode != PAD_ZERO:
+                pad = d.pad_t
+                if dpad is None or tuple(dpad.shape) != (d.n, d.h + 2 * pad, d.w + 2 * pad, self.cin):
+                    raise ValueError('mirrored padding: bprop needs a dpad buffer of shape (n, h+2p, w+2p, cin)')
+                if dx_addr is not None:
+                    raise ValueError('mirrored padding: dx must be a plain tensor')
+                dd.h, dd.w, dd.pad_t, dd.pad_l, dd.pad_mode = d.h + 2 * pad, d.w + 2 * pad, 0, 0, PAD_ZERO
+                dd.in_pitch, dd.in_coff, dd.in_mode, dd.accumulate = self.cin, 0, MODE_PLAIN, 0
+                L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dpad), st)
+                L.ni_pad_fold(ptr(dpad), ptr(dx), d.n, d.h, d.w, self.cin, pad, d.pad_mode, int(dx_accumulate), st)
+                return dx
             if dx_addr is not None:
                 dd.in_pitch, dd.in_coff, dd.in_mode = dx_addr
             dd.accumulate = int(dx_accumulate)
             dd.pad_mode = PAD_ZERO
-            wv = self.w.value if weight is None else weight
             L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dx), st)
         return dx
 

@@ -188,3 +188,53 @@ def dcn_training_step(P, opt_state, x, lr=1e-3, entropy_weight=250.0, latent_bpf
         R.adam_keras_step([P[k] for k in names], grads, ms, vs, opt_state['t'], lr)
     return ({'loss': float(torch.sqrt(2 * loss)), 'entropy': float(ent), 'raw_loss': float(loss)},
             OrderedDict(zip(names, grads)), y.detach(), q.detach())
+
+
+# ------------------------------------------------------------------------------------------------ INet / DNet / ClassicISP
+def _conv_named(P, t, name, act=None, padding='SAME', pad=0):
+    """Keras Conv2D by parameter name; pad > 0: tf.pad(REFLECT) then a VALID convolution."""
+    if pad > 0:
+        t, padding = R.tf_pad(t, pad, 'REFLECT'), 'VALID'
+    y = R.conv2d(t, P[name + '/kernel'], P.get(name + '/bias'), padding=padding)
+    return R.ACT[act](y) if act in R.ACT else y
+
+
+def inet_forward(P, x, kernel=5):
+    """models/pipelines.py:273-292."""
+    bayer = R.depth_to_space(_conv_named(P, x, 'upsampling'), 2)
+    rgb = _conv_named(P, bayer, 'demosaicing', pad=(kernel - 1) // 2)
+    srgb = _conv_named(P, rgb, 'srgb')
+    g0 = _conv_named(P, srgb, 'gamma_d1', 'tanh')
+    return R.ste_clip(_conv_named(P, g0, 'gamma_d2'))
+
+
+def dnet_forward(P, x, n_layers=15, kernel=3):
+    """models/pipelines.py:318-345: conv VALID + ReLU followed by a REFLECT pad, n_layers times; d2s; concat; project; pad; 1x1."""
+    pad = (kernel - 1) // 2
+    deep = x
+    for r in range(n_layers):
+        deep = R.tf_pad(_conv_named(P, deep, 'conv2d_%d' % r, 'relu', padding='VALID'), pad, 'REFLECT')
+    bayer = R.depth_to_space(_conv_named(P, x, 'upsampling'), 2)
+    cat = torch.cat((R.depth_to_space(deep, 2), bayer), dim=3)
+    pu = R.tf_pad(_conv_named(P, cat, 'conv2d_%d' % n_layers, 'relu', padding='VALID'), pad, 'REFLECT')
+    return R.ste_clip(_conv_named(P, pu, 'conv2d_%d' % (n_layers + 1), padding='VALID'))
+
+
+def classic_isp_forward(P, x, kernel=5, n_cnn=0, residual=True):
+    """_ClassicISP.call (models/pipelines.py:432-446) over DemosaicingLayer.call (models/layers.py:238-258).
+    n_cnn = len(c_filters); the CNN branch has n_cnn k x k layers + the final 1x1."""
+    bayer = R.depth_to_space(_conv_named(P, x, 'upsampling'), 2)
+
+    def cnn(t):
+        for i in range(n_cnn):
+            t = _conv_named(P, t, 'demosaicing/conv2d_%d' % i, 'leaky_relu')
+        return _conv_named(P, t, 'demosaicing/conv2d_%d' % n_cnn, 'tanh' if residual else 'sigmoid')
+    if residual:
+        xb = _conv_named(P, bayer, 'demosaicing/bilinear', pad=(kernel - 1) // 2)
+        f = cnn(bayer) if n_cnn > 0 else 0
+        y = xb - P['demosaicing/alpha'] * f
+    else:
+        y = cnn(bayer)
+    y = R.ste_clip(y)
+    rgb = _conv_named(P, y, 'srgb')
+    return torch.pow(R.ste_clip(rgb, 1.0 / 255, 1.0), 1 / 2.2)

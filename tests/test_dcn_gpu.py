@@ -101,7 +101,24 @@ def test_twitter_dcn_api_and_forward():
         assert rel_err(y.numpy(), yr) < 2e-5
 
 
-def test_twitter_dcn_training_step():
+@pytest.fixture(params=['tcgen05', 'simt'])
+def conv_path(request):
+    """Run a test with the production convolution path (tcgen05 3xTF32, ~1e-5 relative) and with the FP32 SIMT path (~1e-6).
+    Gradients UPSTREAM of the soft-codebook quantiser amplify the convolution rounding: soft(v) is a train of sigmoids of
+    slope ~154 (width 0.0065) at the decision boundaries, so d soft/dv changes by ~154 |dv| relative; |dv| ~ 1e-5 |v| on the
+    tensor-core path gives percent-level differences on the few boundary latents that carry the whole gradient. The SIMT run
+    pins the chain rule tightly, the tcgen05 run bounds the production path."""
+    from neural_imaging_b200 import _lib
+    L = _lib.lib()
+    L.ni_conv2d_set_force_simt(1 if request.param == "simt" else -1)
+    yield request.param
+    L.ni_conv2d_set_force_simt(-1)
+
+
+UPSTREAM_TOL = {'simt': 5e-3, 'tcgen05': 6e-2}
+
+
+def test_twitter_dcn_training_step(conv_path):
     from neural_imaging_b200.models import compression
     model = compression.TwitterDCN(patch_size=64, seed=11)
     state = _dcn_state(model, 5.0)
@@ -128,7 +145,7 @@ def test_twitter_dcn_training_step():
         # relative, in the float32 oracle just as on the GPU -> compare against the float32 oracle's own error
         # (encoder side: dsoft/dv changes by ~|dz| / 0.04 relative, and the tcgen05 3xTF32 convolutions carry |dz| ~ 1e-5 |z|)
         up = name.startswith('encoder/')
-        assert_parity(g[name].reshape(ref.shape), ref, out[torch.float32][1][name], tol=5e-3 if up else 1e-4, slack=8.0, what='DCN grad ' + name)
+        assert_parity(g[name].reshape(ref.shape), ref, out[torch.float32][1][name], tol=UPSTREAM_TOL[conv_path] if up else 1e-4, slack=8.0, what='DCN grad ' + name)
     new = model._store.state_dict()
     for k, p in out[torch.float64][2].items():
         delta = np.abs(new[k].reshape(p.shape) - p)
@@ -150,7 +167,7 @@ def test_dcn_loss_matches_reference_definition():
 
 
 @pytest.mark.parametrize('trainable', [('nip', 'dcn'), ('dcn',), ('nip',)])
-def test_joint_training_step_with_learned_codec(trainable):
+def test_joint_training_step_with_learned_codec(trainable, conv_path):
     """compression='dcn' in ManipulationClassification.training_step (reference :260-285 with codec = TwitterDCN):
     loss = ce + lambda_nip * nip + lambda_dcn * (l2_loss(c - C) + 250 H); gradients of all three models vs the oracle."""
     from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
@@ -196,6 +213,6 @@ def test_joint_training_step_with_learned_codec(trainable):
             ref32 = res[torch.float32][1][prefix + p.name].numpy()
             # everything upstream of the quantiser sees the spike-train derivative of the soft code book (see above)
             up = prefix == 'nip/' or (prefix == 'dcn/' and p.name.startswith('encoder/'))
-            assert_parity(p.grad.cpu().numpy().reshape(ref64.shape), ref64, ref32, tol=5e-3 if up else 2e-4, slack=8.0, what=prefix + p.name)
+            assert_parity(p.grad.cpu().numpy().reshape(ref64.shape), ref64, ref32, tol=UPSTREAM_TOL[conv_path] if up else 2e-4, slack=8.0, what=prefix + p.name)
     if not train_dcn:
         assert float(flow.codec._store.gflat.abs().max()) == 0.0
