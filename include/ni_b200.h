@@ -117,6 +117,8 @@ int ni_conv2d_wgrad_small(const ni_conv_desc* d, const float* x, const float* dy
 int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d /*128x64*/, int mn_major, ni_stream_t stream);
 /* measurement probe: TMA box streaming rate vs channel pitch / boxes in flight; returns the grid size (> 0) or an error (< 0) */
 int ni_tma_probe(const float* x, int n, int h, int w, int c, int stages, int boxes_per_cta, long long* cycles_out, int max_grid, ni_stream_t stream);
+/* debug: per-role clock64 spans of the persistent tcgen05 gemm (zeros unless built with -DNI_TC_PROFILE) */
+int ni_tc_prof_read(long long* out32, int reset);
 void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */
 /* The SIMT implementations, callable directly (tests compare the two paths on the device). */
 int ni_conv2d_fprop_simt(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);

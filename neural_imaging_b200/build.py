@@ -10,7 +10,7 @@ OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libni_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
-         '--expt-relaxed-constexpr']
+         '--expt-relaxed-constexpr'] + os.environ.get('NI_NVCC_EXTRA', '').split()      # e.g. -DNI_TC_PROFILE (tools/gpu_tcprof.sh)
 
 
 def _sources():

@@ -22,6 +22,7 @@
 
 #include "conv_desc.h"
 #include "conv_tc_v2.cuh"
+#include "conv_tc_v3.cuh"
 #include "ni_common.cuh"
 #include "tc_common.cuh"
 
@@ -105,6 +106,21 @@ int encode_act_map(CUtensorMap* tm, const float* base, int n, int h, int w, int 
     return encode_map(tm, base, 4, dims, str, box);
 }
 
+// gemm tiles: 16 x 8 pixels where the image allows it (smallest halo), else the row-major rule of pick_tile
+bool pick_tile(int h, int w, int pixels, int& bw, int& bh, int& bn);
+bool pick_tile_gemm(int h, int w, int& bw, int& bh, int& bn) {
+    if (w % 16 == 0 && h % 8 == 0) { bw = 16; bh = 8; bn = 1; return true; }
+    return pick_tile(h, w, 128, bw, bh, bn);
+}
+
+// tile + halo geometry of the gemm kernel for a (th x tw) target and a kh x kw filter; false if it does not fit
+bool gemm_geometry(int th, int tw, int kh, int kw, int& bw, int& bh, int& bn, int& hw, int& hh, int& a_stage) {
+    if (!pick_tile_gemm(th, tw, bw, bh, bn)) return false;
+    hw = bw + kw - 1; hh = bh + kh - 1;
+    a_stage = (hw * hh * bn * 128 + 1023) / 1024 * 1024;
+    return hw <= 256 && hh <= 256 && bn <= 256 && a_stage <= 48 * 1024;
+}
+
 bool pick_tile(int h, int w, int pixels, int& bw, int& bh, int& bn) {
     if (w >= pixels) { if (w % pixels) return false; bw = pixels; bh = 1; bn = 1; return true; }
     if (pixels % w) return false;
@@ -146,7 +162,11 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     const int dmode = dgrad ? d->in_mode : d->out_mode;
     const int taps = d->kh * d->kw;
     tcv2::GemmParams p;
-    if (!pick_tile(th, tw, 128, p.bw, p.bh, p.bn)) { ni_set_error("conv_tc: unsupported spatial tile"); return NI_ERR_UNSUPPORTED; }
+    if (!gemm_geometry(th, tw, d->kh, d->kw, p.bw, p.bh, p.bn, p.hw, p.hh, p.a_stage)) {
+        ni_set_error("conv_tc: unsupported spatial tile");
+        return NI_ERR_UNSUPPORTED;
+    }
+    p.sa = (K / 32) > 1 ? tcv2::kMaxSA : 1;
     const int bnt = pick_bnt(N);
     float* scratch = nullptr;
     const size_t wbytes = (size_t)2 * taps * K * N * sizeof(float);
@@ -156,7 +176,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1, bnt);
     NI_LAUNCH_CHECK();
     CUtensorMap tmA;
-    rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.bw, p.bh, p.bn);
+    rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.hw, p.hh, p.bn);
     if (rc) return rc;
     p.n = d->n; p.oh = th; p.ow = tw;
     p.tiles_w = tw / p.bw; p.tiles_h = th / p.bh;
@@ -167,28 +187,55 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     p.out_pitch = dpitch; p.out_coff = dcoff; p.out_mode = dmode;
     p.bias_mod = dgrad ? 0 : d->bias_mod; p.act = dgrad ? NI_ACT_NONE : d->act; p.accumulate = d->accumulate; p.alpha = d->act_alpha;
     p.bias = dgrad ? nullptr : bias; p.out = dst;
+    const int ktot = taps * K;
+    const int want_nacc = ktot > 2304 ? 3 : (ktot > 1024 ? 2 : 1);
+    static const bool use_v2 = getenv("NI_TC_GEMM_V2") != nullptr;
+    const int mtiles = p.tiles_w * p.tiles_h * tiles_n;
+    if (!use_v2) {
+        // generation 3: persistent CTAs (one per SM), see conv_tc_v3.cuh
+        tcv3::PersistParams q;
+        q.mtiles = mtiles; q.total_tiles = mtiles * (N / bnt);
+        // TMEM budget (tcv3::Cfg): N = 128 -> one set of (nacc + 1) accumulators + 2 A slots; N <= 64 -> fixed 4 accumulators per set
+        int nacc = want_nacc;
+        while (bnt == 128 && (nacc + 1) * bnt + 2 * 64 > 512) --nacc;
+        if (nacc > taps * (K / 32)) nacc = taps * (K / 32);
+        p.nacc = nacc < 1 ? 1 : nacc;
+        const int bstage = 2 * bnt * 128;
+        int sb = (220 * 1024 - p.sa * p.a_stage) / bstage;
+        q.sb = sb > tcv3::kMaxSB ? tcv3::kMaxSB : sb;
+        if (q.sb < 2) { ni_set_error("conv_tc: not enough shared memory for the B ring"); return NI_ERR_UNSUPPORTED; }
+        const size_t smem = (size_t)p.sa * p.a_stage + (size_t)q.sb * bstage + 1024;
+        const int grid = q.total_tiles < ni_num_sms() ? q.total_tiles : ni_num_sms();
+#define NI_TC_GEMM3(B)                                                                                         \
+    {                                                                                                          \
+        rc = set_dyn_smem(tcv3::conv_tc3_gemm_kernel<B>, smem);                                                \
+        if (rc) return rc;                                                                                     \
+        if (getenv("NI_TC_DEBUG")) {                                                                           \
+            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, tcv3::conv_tc3_gemm_kernel<B>);                  \
+            fprintf(stderr, "tc gemm3<%d>: grid %d, tiles %d, iters %d, smem %zu, regs %d, local %zu, sb %d, sa %d, nacc %d\n", B, grid,  \
+                    q.total_tiles, taps * (K / 32), smem, fa.numRegs, fa.localSizeBytes, q.sb, p.sa, p.nacc);  \
+        }                                                                                                      \
+        tcv3::conv_tc3_gemm_kernel<B><<<grid, tcv3::kThreads, smem, st>>>(tmA, scratch, p, q);                 \
+    }
+        if (bnt == 128) NI_TC_GEMM3(128) else if (bnt == 64) NI_TC_GEMM3(64) else NI_TC_GEMM3(32)
+#undef NI_TC_GEMM3
+        NI_LAUNCH_CHECK();
+        NI_COUNT_LAUNCH(2);
+        return NI_OK;
+    }
     {
-        // accumulator rotation: deeper contractions get more D1 accumulators, bounded by the 512 TMEM columns
-        // (accumulators + 2 x 64 columns of A operand slots)
-        const int ktot = taps * K;
-        int nacc = ktot > 2304 ? 3 : (ktot > 1024 ? 2 : 1);
+        // generation 2 (one CTA per tile): accumulator rotation bounded by the 512 TMEM columns
+        int nacc = want_nacc;
         while ((nacc + 1) * bnt + tcv2::kTmemSlots * 64 > 512) --nacc;
         if (nacc > taps * (K / 32)) nacc = taps * (K / 32);
         p.nacc = nacc < 1 ? 1 : nacc;
     }
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)(N / bnt));
+    dim3 grid((unsigned)mtiles, (unsigned)(N / bnt));
 #define NI_TC_GEMM(B)                                                                                          \
     {                                                                                                          \
-        const size_t smem = (size_t)tcv2::Rings<B>::SMEM + 1024;                                               \
+        const size_t smem = (size_t)p.sa * p.a_stage + tcv2::Rings<B>::SMEM_B + 1024;                          \
         rc = set_dyn_smem(tcv2::conv_tc2_gemm_kernel<B>, smem);                                                \
         if (rc) return rc;                                                                                     \
-        if (getenv("NI_TC_DEBUG")) {                                                                           \
-            int nb = -1;                                                                                       \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tcv2::conv_tc2_gemm_kernel<B>, tcv2::Roles<B>::THREADS, smem); \
-            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, tcv2::conv_tc2_gemm_kernel<B>);                  \
-            fprintf(stderr, "tc gemm<%d>: grid %u x %u, threads %d, smem %zu, regs %d, static smem %zu, occupancy %d CTA/SM, nacc %d\n", B, grid.x, grid.y, \
-                    tcv2::Roles<B>::THREADS, smem, fa.numRegs, fa.sharedSizeBytes, nb, p.nacc);                \
-        }                                                                                                      \
         tcv2::conv_tc2_gemm_kernel<B><<<grid, tcv2::Roles<B>::THREADS, smem, st>>>(tmA, scratch, p);           \
     }
     if (bnt == 128) NI_TC_GEMM(128) else if (bnt == 64) NI_TC_GEMM(64) else NI_TC_GEMM(32)
@@ -199,6 +246,19 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
 }
 
 }  // namespace
+
+// In-kernel timing counters of the persistent gemm (all zero unless the library was built with -DNI_TC_PROFILE)
+extern "C" int ni_tc_prof_read(long long* out32, int reset) {
+    NI_REQUIRE(out32, "ni_tc_prof_read: null pointer");
+#ifdef NI_TC_PROFILE
+    NI_CUDA(cudaDeviceSynchronize());
+    NI_CUDA(cudaMemcpyFromSymbol(out32, tcv3::g_tc_prof, sizeof(long long) * 32));
+    if (reset) { long long z[32] = {0}; NI_CUDA(cudaMemcpyToSymbol(tcv3::g_tc_prof, z, sizeof(z))); }
+#else
+    for (int i = 0; i < 32; ++i) out32[i] = 0;
+#endif
+    return NI_OK;
+}
 
 // Second internal scratch (transposed / flipped weights of the SIMT and direct dgrad paths), same grow-on-demand policy.
 int ni_get_scratch2(size_t bytes, float** out) {
@@ -224,16 +284,16 @@ extern "C" int ni_conv2d_tc_supported(const ni_conv_desc* d, int op) {
     if (d->cin % 32 || d->cout % 32) return 0;
     if (d->kh * d->kw > 64) return 0;
     if ((d->in_pitch % 4) || (d->in_coff % 4) || (d->out_pitch % 4) || (d->out_coff % 4)) return 0;
-    int bw, bh, bn;
+    int bw, bh, bn, hw, hh, ast;
     if (op == 0) {
         if (d->in_mode != NI_MODE_PLAIN) return 0;
         if (d->out_mode == NI_MODE_BLOCK2 && ((d->cout / 4) % 32)) return 0;
-        return pick_tile(d->oh, d->ow, 128, bw, bh, bn) ? 1 : 0;
+        return gemm_geometry(d->oh, d->ow, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
     if (op == 1) {
         if (d->out_mode != NI_MODE_PLAIN) return 0;                    // dy is the TMA source
         if (d->in_mode == NI_MODE_BLOCK2 && ((d->cin / 4) % 32)) return 0;
-        return pick_tile(d->h, d->w, 128, bw, bh, bn) ? 1 : 0;
+        return gemm_geometry(d->h, d->w, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
     if (d->in_mode != NI_MODE_PLAIN || d->out_mode != NI_MODE_PLAIN) return 0;
     if (!pick_tile(d->oh, d->ow, 32, bw, bh, bn)) return 0;

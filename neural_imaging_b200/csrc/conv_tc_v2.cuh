@@ -30,6 +30,7 @@ struct GemmParams {
     int bw, bh, bn;
     int tiles_w, tiles_h;
     int kh, kw, off_y0, off_x0, off_sign;
+    int hw, hh, sa, a_stage;       // halo box (bw + kw - 1) x (bh + kh - 1) pixels, A stages and their byte size (1024-aligned)
     int kchunks, ntot;
     int out_pitch, out_coff, out_mode;
     int bias_mod, act, accumulate, nacc;
@@ -56,19 +57,23 @@ __device__ __forceinline__ uint32_t pow2_cols(uint32_t want) {
 // Ring depths. The kernel is bound by how many bytes of TMA loads one SM keeps in flight (ncu: converters stalled on the
 // "tile landed" barrier 26 % of all samples, L2 at 17 %, tensor pipe at 27 % with a single 3-deep ring): activations stream
 // from HBM and need depth, weights are L2-resident and big, so the two operands get their own rings.
+// A is staged as a HALO tile: for one 32-channel chunk the (bw + kw - 1) x (bh + kh - 1) input pixels that all kh*kw taps of
+// the 128-pixel tile touch are loaded ONCE (one TMA box) and every tap reads its shifted window from shared memory while
+// converting to TMEM. Per k-iteration the per-tap design moved 16 KB of activations + 2*BNT*128 B of weights through TMA,
+// and TMA ingest (~25 B/clk per CTA, tools/tma_probe.py) bounded the kernel at 2-5x the MMA time; now activations cost
+// 16 KB * halo_ratio / taps per iteration.
+constexpr int kMaxSA = 2;
 template <int BNT> struct Rings {
-    static constexpr int SA = BNT == 128 ? 4 : 3;               // A stages, 16 KB each
     static constexpr int SB = 3;                                // B stages, hi + lo = 2 * BNT * 128 bytes each
-    // BNT <= 64: 72 / 96 KB per CTA so that TWO CTAs share an SM (measured: one CTA with deeper rings is 1.7-1.9x slower)
     static constexpr int B_BYTES = BNT * 128;
-    static constexpr int SMEM = SA * kAraw + SB * 2 * B_BYTES;
+    static constexpr int SMEM_B = SB * 2 * B_BYTES;
 };
 
 // TMEM map: [0, (nacc+1)*BNT) accumulators (D1_0.. D1_{nacc-1}, D2), then kTmemSlots x 64 columns of A (hi 32 | lo 32).
 template <int BNT>
 __global__ void __launch_bounds__(Roles<BNT>::THREADS, Roles<BNT>::MIN_CTAS)
 conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ wtiled, const GemmParams p) {
-    constexpr int SA = Rings<BNT>::SA, SB = Rings<BNT>::SB, B_BYTES = Rings<BNT>::B_BYTES, NCW = Roles<BNT>::NCW;
+    constexpr int SA = kMaxSA, SB = Rings<BNT>::SB, B_BYTES = Rings<BNT>::B_BYTES, NCW = Roles<BNT>::NCW;
     const uint32_t acc_cols = (uint32_t)(p.nacc + 1) * BNT;
     const uint32_t TMEM_COLS = pow2_cols(acc_cols + kTmemSlots * 64);
     extern __shared__ uint8_t smem_raw[];
@@ -98,19 +103,20 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     const uint32_t tmem = tmem_slot;
     const uint32_t a_base = tmem + acc_cols;
 
-    auto a_raw = [&](int s) { return smem + s * kAraw; };
-    auto b_hi = [&](int s) { return smem + SA * kAraw + s * 2 * B_BYTES; };
-    auto b_lo = [&](int s) { return smem + SA * kAraw + s * 2 * B_BYTES + B_BYTES; };
+    auto a_halo = [&](int s) { return smem + s * p.a_stage; };
+    auto b_hi = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES; };
+    auto b_lo = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES + B_BYTES; };
+    // iteration it = kc * taps + tap (channel chunk outer, taps inner: one halo tile serves all taps)
 
     if (warp == 0) {
-        if (lane == 0) {   // ---- A producer
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % SA, ph = (it / SA) & 1;
+        if (lane == 0) {   // ---- A producer: one halo box per 32-channel chunk
+            const int bx = x0 + p.off_x0 + (p.off_sign < 0 ? -(p.kw - 1) : 0), by = y0 + p.off_y0 + (p.off_sign < 0 ? -(p.kh - 1) : 0);
+            const uint32_t bytes = (uint32_t)(p.hw * p.hh * p.bn) * 128u;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                const int s = kc % p.sa, ph = (kc / p.sa) & 1;
                 mbar_wait(&bar_afree[s], ph ^ 1, 0);
-                mbar_expect_tx(&bar_afull[s], kAraw);
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                const int a = tap / p.kw, b = tap - a * p.kw;
-                tma_load_4d(a_raw(s), &tmA, &bar_afull[s], kc * 32, x0 + p.off_x0 + p.off_sign * b, y0 + p.off_y0 + p.off_sign * a, n0);
+                mbar_expect_tx(&bar_afull[s], bytes);
+                tma_load_4d(a_halo(s), &tmA, &bar_afull[s], kc * 32, bx, by, n0);
             }
         }
     } else if (warp == 2 + NCW) {
@@ -121,7 +127,8 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 mbar_expect_tx(&bar_bfull[s], 2 * B_BYTES);
                 // weights are pre-tiled by the prep kernel: block (tap, kc, n-tile) = [hi tile | lo tile], already in the swizzled
                 // K-major order, so one contiguous bulk copy replaces two 128-row tensor boxes (TMA cost is per box row)
-                const float* src = wtiled + ((size_t)it * gridDim.y + blockIdx.y) * (size_t)(2 * BNT * 32);
+                const int kc = it / taps, tap = it - kc * taps;
+                const float* src = wtiled + ((size_t)(tap * p.kchunks + kc) * gridDim.y + blockIdx.y) * (size_t)(2 * BNT * 32);
                 bulk_load_1d(b_hi(s), src, 2 * B_BYTES, &bar_bfull[s]);
             }
         }
@@ -157,15 +164,20 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         constexpr int NH = NCW / 4;            // warps per TMEM lane quarter (1 or 2)
         constexpr int CW = 32 / NH;            // K-columns converted by one thread
         const int q = warp & 3, row = q * 32 + lane, half = (warp - 2) >> 2;
+        // this thread's pixel inside the halo box (tap (0,0) position); tap (a, b) adds (sy(a) * hw + sx(b)) pixels
+        const int prow0 = ((row / (p.bw * p.bh)) * p.hh + (row / p.bw) % p.bh) * p.hw + row % p.bw;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % SA, ph = (it / SA) & 1;
+            const int kc = it / taps, tap = it - kc * taps;
+            const int s = kc % p.sa, ph = (kc / p.sa) & 1;
             const int t = it % kTmemSlots, pt = (it / kTmemSlots) & 1;
-            mbar_wait(&bar_afull[s], ph, 3);
+            if (tap == 0) mbar_wait(&bar_afull[s], ph, 3);
+            const int ta = tap / p.kw, tb = tap - ta * p.kw;
+            const int prow = prow0 + (p.off_sign > 0 ? ta : p.kh - 1 - ta) * p.hw + (p.off_sign > 0 ? tb : p.kw - 1 - tb);
             float hi[CW], lo[CW];
-            const uint8_t* rp = a_raw(s) + row * 128;
+            const uint8_t* rp = a_halo(s) + prow * 128;
 #pragma unroll
             for (int c = 0; c < CW / 4; ++c) {
-                const float4 v = *reinterpret_cast<const float4*>(rp + ((((CW / 4) * half + c) ^ (row & 7)) << 4));
+                const float4 v = *reinterpret_cast<const float4*>(rp + ((((CW / 4) * half + c) ^ (prow & 7)) << 4));
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -174,7 +186,7 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     lo[4 * c + e] = vv[e] - h;
                 }
             }
-            mbar_arrive(&bar_afree[s]);          // the tile is in registers: hand the stage back to the A producer
+            if (tap == taps - 1) mbar_arrive(&bar_afree[s]);   // last tap is in registers: hand the stage back to the A producer
             mbar_wait(&bar_tfree[t], pt ^ 1, 5);
             tcgen05_fence_after();
             const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + t * 64 + CW * half;

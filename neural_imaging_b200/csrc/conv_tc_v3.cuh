@@ -1,0 +1,321 @@
+// tcgen05 convolution gemm, generation 3: PERSISTENT, one CTA per SM, epilogue overlapped with the next tile's main loop.
+//
+// Measured on generation 2 (one CTA per output tile): per-tile time = T_fixed + iters * T_iter with T_fixed ~ 25 main-loop
+// iterations (launch + TMEM allocation + first TMA round trip + accumulator drain + stores, none of it overlapped because a
+// second CTA does not fit / blocks on the TMEM allocation), while the layers of this workload have only 9 - 100 iterations
+// per tile (K = taps * cin / 32). Layers with 9 - 25 iterations ran at 40 - 100 TFLOP/s, the 100-iteration layer at 160.
+// Here a CTA walks over tiles: barriers, TMEM and the tensor map are set up once; the producers run ahead into the next tile;
+// dedicated epilogue warps drain one accumulator set while the MMA warp fills the other (N <= 64; N = 128 has TMEM room for
+// one set only and just overlaps the stores).
+//
+// Warp roles (16 warps): 0 A producer (halo tiles, see conv_tc_v2.cuh), 1 MMA issuer, 2 B producer, 3 TMEM allocator + second MMA issuer,
+// 4-11 converters (two per TMEM lane quarter, 16 K-columns each), 12-15 epilogue (one per lane quarter).
+#pragma once
+#include "conv_desc.h"
+#include "conv_tc_v2.cuh"
+#include "ni_common.cuh"
+#include "tc_common.cuh"
+
+namespace tcv3 {
+using namespace tc;
+using tcv2::act_apply;
+using tcv2::GemmParams;
+using tcv2::pow2_cols;
+
+// Optional in-kernel timing (build with -DNI_TC_PROFILE): CTA 0 accumulates clock64() spans per role into g_tc_prof.
+#ifdef NI_TC_PROFILE
+__device__ long long g_tc_prof[32];
+#define TCP_DECL long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0;
+#define TCP_START() do { if (tcp_on) tcp_t = clock64(); } while (0)
+#define TCP_ADD(i) do { if (tcp_on) { const long long n_ = clock64(); atomicAdd((unsigned long long*)&g_tc_prof[i], (unsigned long long)(n_ - tcp_t)); tcp_t = n_; } } while (0)
+#else
+#define TCP_DECL
+#define TCP_START() do {} while (0)
+#define TCP_ADD(i) do {} while (0)
+#endif
+
+constexpr int kThreads = 512;
+constexpr int kNCW = 8;            // converter warps
+constexpr int kMaxSA = 2, kMaxSB = 8;
+
+// In-kernel clock64 spans: ONE thread needs ~74 cycles per tcgen05.mma (ELECT + uniform-datapath descriptor arithmetic + UTCHMMA),
+// whatever N is and wherever A comes from; N = 128 executes for 64 cycles anyway, but N <= 64 is issue-bound. Those tiles get
+// TWO issuer warps (different scheduler partitions) that take alternate k-iterations and own separate accumulators
+// [D1_0, D2_0, D1_1, D2_1]; the epilogue adds them up (the sum is order-independent, only each accumulator's FIRST MMA has to
+// overwrite, and that is a per-issuer property).
+template <int BNT> struct Cfg {
+    static constexpr int ISSUERS = BNT == 128 ? 1 : 2;
+    static constexpr int SLOTS = BNT == 128 ? 2 : 4;     // A (hi | lo) slots in tensor memory, 64 columns each
+    static constexpr int NSETS = BNT == 32 ? 2 : 1;      // accumulator sets (512 TMEM columns: sets * set_cols + SLOTS * 64)
+    static constexpr int B_BYTES = BNT * 128;            // one (BNT x 32) tf32 tile; a B stage is hi + lo
+};
+
+struct PersistParams {
+    int mtiles, total_tiles;       // pixel tiles, pixel tiles * n tiles
+    int sb;                        // B stages in use (<= kMaxSB)
+};
+
+template <int BNT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ wtiled, const GemmParams p, const PersistParams q) {
+    constexpr int SLOTS = Cfg<BNT>::SLOTS, NSETS = Cfg<BNT>::NSETS, B_BYTES = Cfg<BNT>::B_BYTES, ISSUERS = Cfg<BNT>::ISSUERS;
+    const uint32_t set_cols = ISSUERS == 2 ? 4u * BNT : (uint32_t)(p.nacc + 1) * BNT;
+    const uint32_t acc_cols = set_cols * NSETS;
+    const uint32_t TMEM_COLS = pow2_cols(acc_cols + SLOTS * 64);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar_afull[kMaxSA], bar_afree[kMaxSA], bar_bfull[kMaxSB], bar_bfree[kMaxSB], bar_tready[SLOTS], bar_tfree[SLOTS],
+        bar_accfull[NSETS], bar_accfree[NSETS];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = p.kh * p.kw;
+    const int iters = taps * p.kchunks;
+    const int ntiles_n = p.ntot / BNT;
+    const int n_iss = (ISSUERS == 2 && iters >= 2) ? 2 : 1;          // active issuer warps
+    const int nsum = ISSUERS == 2 ? 2 * n_iss : p.nacc + 1;         // accumulators the epilogue adds up
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxSA; ++s) { mbar_init(&bar_afull[s], 1); mbar_init(&bar_afree[s], kNCW * 32); }
+        for (int s = 0; s < kMaxSB; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bfree[s], 1); }
+        for (int t = 0; t < SLOTS; ++t) { mbar_init(&bar_tready[t], kNCW * 32); mbar_init(&bar_tfree[t], 1); }
+        for (int a = 0; a < NSETS; ++a) { mbar_init(&bar_accfull[a], n_iss); mbar_init(&bar_accfree[a], 128); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+    }
+    if (warp == 3) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a_base = tmem + acc_cols;
+
+    auto a_halo = [&](int s) { return smem + s * p.a_stage; };
+    auto b_hi = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES; };
+    auto b_lo = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES + B_BYTES; };
+    // tile t -> (pixel tile m = t % mtiles, n tile = t / mtiles): neighbouring CTAs share the weight slice in L2
+    auto tile_origin = [&](int tile, int& x0, int& y0, int& n0, int& nt) {
+        const int m = tile % q.mtiles;
+        nt = tile / q.mtiles;
+        const int tw = m % p.tiles_w, th = (m / p.tiles_w) % p.tiles_h, tn = m / (p.tiles_w * p.tiles_h);
+        x0 = tw * p.bw; y0 = th * p.bh; n0 = tn * p.bn;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---- A producer: one halo box per (tile, 32-channel chunk)
+            const uint32_t bytes = (uint32_t)(p.hw * p.hh * p.bn) * 128u;
+            int gkc = 0;
+            TCP_DECL
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+                int x0, y0, n0, nt;
+                tile_origin(tile, x0, y0, n0, nt);
+                const int bx = x0 + p.off_x0 + (p.off_sign < 0 ? -(p.kw - 1) : 0), by = y0 + p.off_y0 + (p.off_sign < 0 ? -(p.kh - 1) : 0);
+                for (int kc = 0; kc < p.kchunks; ++kc, ++gkc) {
+                    const int s = gkc % p.sa, ph = (gkc / p.sa) & 1;
+                    TCP_START();
+                    mbar_wait(&bar_afree[s], ph ^ 1, 0);
+                    TCP_ADD(12);
+                    mbar_expect_tx(&bar_afull[s], bytes);
+                    tma_load_4d(a_halo(s), &tmA, &bar_afull[s], kc * 32, bx, by, n0);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {   // ---- B producer: pre-tiled [hi | lo] weight blocks, one contiguous bulk copy per iteration
+            int git = 0;
+            TCP_DECL
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+                const int nt = tile / q.mtiles;
+                for (int it = 0; it < iters; ++it, ++git) {
+                    const int s = git % q.sb, ph = (git / q.sb) & 1;
+                    TCP_START();
+                    mbar_wait(&bar_bfree[s], ph ^ 1, 7);
+                    TCP_ADD(13);
+                    mbar_expect_tx(&bar_bfull[s], 2 * B_BYTES);
+                    const int kc = it / taps, tap = it - kc * taps;
+                    const float* src = wtiled + ((size_t)(tap * p.kchunks + kc) * ntiles_n + nt) * (size_t)(2 * BNT * 32);
+                    bulk_load_1d(b_hi(s), src, 2 * B_BYTES, &bar_bfull[s]);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        const int iss = warp == 1 ? 0 : 1;
+        if (lane == 0 && iss < n_iss) {   // ---- MMA issuer(s)
+            constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
+            int gbase = 0, tcount = 0;
+            TCP_DECL
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tcount, gbase += iters) {
+                const int aset = tcount % NSETS, use = tcount / NSETS;
+                TCP_START();
+                mbar_wait(&bar_accfree[aset], (use & 1) ^ 1, 8);          // epilogue has drained this accumulator set
+                TCP_ADD(3);
+                tcgen05_fence_after();
+                const uint32_t dbase = tmem + (uint32_t)aset * set_cols;
+                for (int it = iss; it < iters; it += n_iss) {
+                    const int git = gbase + it;
+                    const int s = git % q.sb, ph = (git / q.sb) & 1;
+                    const int t = git % SLOTS, pt = (git / SLOTS) & 1;
+                    TCP_START();
+                    mbar_wait(&bar_bfull[s], ph, 1);
+                    TCP_ADD(1);
+                    mbar_wait(&bar_tready[t], pt, 2);
+                    TCP_ADD(2);
+                    tcgen05_fence_after();
+                    const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+                    const uint32_t ahi = a_base + t * 64, alo = ahi + 32;
+                    uint32_t d1, d2, first1, first2;
+                    if (ISSUERS == 2) {
+                        d1 = dbase + (uint32_t)(2 * iss) * BNT; d2 = d1 + BNT;
+                        first1 = first2 = it == iss ? 1u : 0u;
+                    } else {
+                        d1 = dbase + (uint32_t)(it % p.nacc) * BNT; d2 = dbase + (uint32_t)p.nacc * BNT;
+                        first1 = it < p.nacc ? 1u : 0u; first2 = it == 0 ? 1u : 0u;
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dbh = make_smem_desc_sw128(bh + ks * 32, 16, 1024), dbl = make_smem_desc_sw128(bl + ks * 32, 16, 1024);
+                        umma_tf32_ts(d2, alo + ks * 8, dbh, idesc, (first2 && ks == 0) ? 0u : 1u);
+                        umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
+                        umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (first1 && ks == 0) ? 0u : 1u);
+                    }
+                    TCP_ADD(17);
+                    umma_commit(&bar_bfree[s]);
+                    umma_commit(&bar_tfree[t]);
+                    TCP_ADD(4);
+                }
+                umma_commit(&bar_accfull[aset]);
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + kNCW) {
+        // ---- converters: A halo row -> registers -> hi / lo -> TMEM (two warps per lane quarter, 16 K-columns each)
+        const int qd = warp & 3, row = qd * 32 + lane, half = (warp - 4) >> 2;
+        const int prow0 = ((row / (p.bw * p.bh)) * p.hh + (row / p.bw) % p.bh) * p.hw + row % p.bw;
+        int git = 0, gkc = 0;
+#ifdef NI_TC_PROFILE
+        long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 128;
+#endif
+        for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < p.kchunks; ++kc, ++gkc) {
+                const int s = gkc % p.sa, ph = (gkc / p.sa) & 1;
+                TCP_START();
+                mbar_wait(&bar_afull[s], ph, 3);
+                TCP_ADD(6);
+                const uint8_t* stage = a_halo(s);
+                for (int tap = 0; tap < taps; ++tap, ++git) {
+                    const int t = git % SLOTS, pt = (git / SLOTS) & 1;
+                    const int ta = tap / p.kw, tb = tap - ta * p.kw;
+                    const int prow = prow0 + (p.off_sign > 0 ? ta : p.kh - 1 - ta) * p.hw + (p.off_sign > 0 ? tb : p.kw - 1 - tb);
+                    float hi[16], lo[16];
+                    const uint8_t* rp = stage + prow * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(rp + (((4 * half + c) ^ (prow & 7)) << 4));
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xFFFFE000u);
+                            hi[4 * c + e] = h;
+                            lo[4 * c + e] = vv[e] - h;
+                        }
+                    }
+                    if (tap == taps - 1) mbar_arrive(&bar_afree[s]);      // last tap is in registers: stage back to the producer
+                    TCP_ADD(7);
+                    mbar_wait(&bar_tfree[t], pt ^ 1, 5);
+                    TCP_ADD(8);
+                    tcgen05_fence_after();
+                    const uint32_t dst = a_base + ((uint32_t)(qd * 32) << 16) + t * 64 + 16 * half;
+                    tmem_st_32x16(dst, hi);
+                    tmem_st_32x16(dst + 32, lo);
+                    tmem_st_wait();
+                    tcgen05_fence_before();
+                    mbar_arrive(&bar_tready[t]);
+                    TCP_ADD(9);
+                }
+            }
+        }
+    } else if (warp >= 12) {
+        // ---- epilogue: accumulator set -> (+ bias, activation) -> global, while the MMA warp works on the other set
+        const int qd = warp & 3, row = qd * 32 + lane;
+        const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ln = row / (p.bw * p.bh);
+        int tcount = 0;
+#ifdef NI_TC_PROFILE
+        long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 384;
+#endif
+        for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tcount) {
+            const int aset = tcount % NSETS, use = tcount / NSETS;
+            int x0, y0, n0, nt;
+            tile_origin(tile, x0, y0, n0, nt);
+            const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;
+            const bool valid = on < p.n && oy < p.oh && ox < p.ow;
+            TCP_START();
+            mbar_wait(&bar_accfull[aset], use & 1, 4);
+            TCP_ADD(10);
+            tcgen05_fence_after();
+            const uint32_t dbase = tmem + (uint32_t)aset * set_cols + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BNT / 32; ++c) {
+                float v[32], v2[32];
+                tmem_ld_32x32(dbase + (uint32_t)(c * 32), v);
+                for (int a2 = 1; a2 < nsum; ++a2) {
+                    tmem_ld_32x32(dbase + (uint32_t)(a2 * BNT + c * 32), v2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += v2[j];
+                }
+                TCP_ADD(14);
+                if (c == BNT / 32 - 1) {          // every TMEM read of this tile has completed: release the accumulator set
+                    tcgen05_fence_before();
+                    mbar_arrive(&bar_accfree[aset]);
+                }
+                if (!valid) continue;
+                const int co0 = nt * BNT + c * 32;
+                float* o;
+                if (p.out_mode == NI_MODE_PLAIN) {
+                    o = p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff + co0;
+                } else {
+                    const int F = p.ntot >> 2, blk = co0 / F, f0 = co0 - blk * F;
+                    o = p.out + (((long long)on * 2 * p.oh + 2 * oy + (blk >> 1)) * (2 * p.ow) + 2 * ox + (blk & 1)) * p.out_pitch + p.out_coff + f0;
+                }
+                // bias: 8 independent 128-bit loads issued together (a scalar __ldg per element inside the activation switch
+                // serialised 32 L2 round trips per chunk: 12.5 k cycles of the 13 k-cycle epilogue, in-kernel clock64 spans)
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + (p.bias_mod > 0 ? co0 % p.bias_mod : co0));
+                    float4 bv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w; }
+                }
+                switch (p.act) {       // one branch per chunk, straight-line code inside
+                    case NI_ACT_LEAKY_RELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : p.alpha * v[j];
+                        break;
+                    case NI_ACT_RELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        break;
+                    case NI_ACT_NONE: break;
+                    default:
+#pragma unroll 4
+                        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], p.act, p.alpha);
+                        break;
+                }
+                TCP_ADD(15);
+                float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 w4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (p.accumulate) { const float4 old = o4[j]; w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
+                    o4[j] = w4;
+                }
+                TCP_ADD(16);
+            }
+            TCP_ADD(11);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 3) { tcgen05_fence_after(); tmem_dealloc(tmem, TMEM_COLS); }
+}
+
+}  // namespace tcv3
