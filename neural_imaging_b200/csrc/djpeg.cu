@@ -6,9 +6,9 @@
 // >= 25 full-size temporaries). HBM traffic = read x + write y (24 B/pixel) forward; read x, dy + write dx backward
 // (36 B/pixel, X/Q is recomputed instead of saved).
 //
-// Work decomposition: a CTA owns a tile of 64 8x8 pixel blocks (48 KB of interleaved RGB staged in shared
-// memory); one thread owns one (block, Y/Cb/Cr channel) pair and keeps the whole 8x8 coefficient block in
-// registers, so the 2-D DCT / quantisation / IDCT need no inter-thread exchange. The 1-D transforms use the
+// Work decomposition: a CTA owns a tile of 32 8x8 pixel blocks (24.5 KB of interleaved RGB staged in shared
+// memory); one thread owns one (block, Y/Cb/Cr channel) pair (warp = channel, lane = block) and keeps the whole 8x8
+// coefficient block in registers, so the 2-D DCT / quantisation / IDCT need no inter-thread exchange. The 1-D transforms use the
 // even/odd symmetry that the literal rows preserve (36 instead of 64 FMA-class ops per 8-point transform) with
 // the literal coefficients as FFMA immediates. The colour transforms (which mix channels) run in cooperative
 // per-pixel passes over the shared-memory tile.
@@ -89,18 +89,15 @@ __device__ __forceinline__ void dct2d_inv(float (&v)[8][8]) {
 constexpr float kTwoPi = 6.2831855f;  // float32(2*np.pi), as TF casts the python scalar
 constexpr float kPi = 3.1415927f;
 
+// sin(2 pi z) through the period-1 identity: r = z - rint(z) is exact in float32 and lies in [-0.5, 0.5], where the
+// special-function unit is accurate to < 5e-7 (the plain sinf(2 pi z) loses ulp(2 pi z) and takes a ~40-instruction path).
+__device__ __forceinline__ float sin_2pi(float z) { return __sinf(kTwoPi * (z - ni_round_he(z))); }
 template <int MODE>
 __device__ __forceinline__ float quant_fwd(float z) {
     if (MODE == 0) return ni_round_he(z);
-    if (MODE == 1) return z - sinf(kTwoPi * z) / kTwoPi;
-    return z - sinf(kTwoPi * z) / kPi;
+    if (MODE == 1) return z - sin_2pi(z) * (1.f / kTwoPi);
+    return z - sin_2pi(z) * (1.f / kPi);
 }
-template <int MODE>
-__device__ __forceinline__ float quant_grad(float z) {
-    if (MODE == 2) return 1.f - 2.f * cosf(kTwoPi * z);
-    return 1.f - cosf(kTwoPi * z);  // soft: backward of the sin approximation; sin: its own derivative
-}
-
 // Colour constants. Forward rows of _color_F with the 255 input scale and the -127 level shift folded in; inverse
 // rows of _color_I with the +127 shift and the /255 folded in (reference models/jpeg.py:74-75,99-105,154-156).
 __device__ __forceinline__ void color_fwd_coeffs(int c, float& k0, float& kr, float& kg, float& kb) {
@@ -109,36 +106,18 @@ __device__ __forceinline__ void color_fwd_coeffs(int c, float& k0, float& kr, fl
     else { k0 = 128.f - 127.f; kr = 255.f * 0.5f; kg = 255.f * -0.418688f; kb = 255.f * -0.081312f; }
 }
 
-// ypre (before clip) for one pixel from level-shifted Y, Cb, Cr (xi, i.e. without the +127).
-__device__ __forceinline__ void color_inv(float yy, float cb, float cr, float& r, float& g, float& b) {
-    const float Y = yy + 127.f, B = cb + 127.f, R = cr + 127.f;
-    const float s = 1.f / 255.f;
-    r = (fmaf(1.402f, R, Y) + (-1.402f * 128.f)) * s;
-    g = (fmaf(-0.714136f, R, fmaf(-0.344136f, B, Y)) + (1.058272f * 128.f)) * s;
-    b = (fmaf(1.772f, B, Y) + (-1.772f * 128.f)) * s;
-}
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// Float offset of (block g, row 0, col 0) in an (N,H,W,3) tensor; computed once per block per tile.
-__device__ __forceinline__ long long block_base_offset(long long g, int nbw, int nbh, int W) {
-    const int bx = (int)(g % nbw);
-    const long long t = g / nbw;
-    const int by = (int)(t % nbh);
-    const long long n = t / nbh;
-    return (((n * nbh + by) * 8) * (long long)W + bx * 8) * 3;
+// Float offset of (block g, row 0, col 0) in an (N,H,W,3) tensor; computed once per block per tile (32-bit divisions: nblk < 2^31).
+__device__ __forceinline__ long long block_base_offset(int g, int nbw, int nbh, int W) {
+    const int bx = g % nbw, t = g / nbw;
+    const int by = t % nbh, n = t / nbh;
+    return ((((long long)n * nbh + by) * 8) * (long long)W + bx * 8) * 3;
 }
-__device__ __forceinline__ void fill_base_table(long long* base, long long g0, long long nblk, int nbw, int nbh, int W) {
-    if (threadIdx.x < kTileBlocks) {
-        const long long g = g0 + threadIdx.x;
-        base[threadIdx.x] = g < nblk ? block_base_offset(g, nbw, nbh, W) : -1;
-    }
-}
-
 // Stage a tile (block-major [blk][row][24], block stride 196) global -> shared with 16-byte async copies. A thread owns
 // (block, 16-byte column) pairs and walks down the 8 rows with pointer increments (3 instructions per copy instead of
 // ~15 of index arithmetic); consecutive threads still copy consecutive 16-byte chunks of one image row.
@@ -153,15 +132,6 @@ __device__ __forceinline__ void tile_load(float* tile, const float* __restrict__
         for (int row = 0; row < 8; ++row) cp_async16(d + row * 24, g + (long long)row * rowf);
     }
 }
-// global float offset of the 4-pixel unit u (see unit_offset) or -1 for blocks past the end
-__device__ __forceinline__ long long unit_global(int u, const long long* base, int rowf) {
-    const long long b = base[u / kUnitsPerBlock];
-    const int r = u % kUnitsPerBlock;
-    return b < 0 ? -1 : b + (long long)(r >> 1) * rowf + (r & 1) * 12;
-}
-// address of 4-pixel unit u of the per-pixel passes
-__device__ __forceinline__ int unit_offset(int u) { return (u / kUnitsPerBlock) * kBlockFloats + (u % kUnitsPerBlock) * 12; }
-
 // Load this thread's channel of its block (level-shifted YCbCr) from the interleaved RGB tile.
 __device__ __forceinline__ void load_channel(const float* bp, int c, float (&v)[8][8]) {
     float k0, kr, kg, kb;
@@ -178,65 +148,71 @@ __device__ __forceinline__ void load_channel(const float* bp, int c, float (&v)[
         for (int j = 0; j < 8; ++j) v[i][j] = fmaf(kb, f[3 * j + 2], fmaf(kg, f[3 * j + 1], fmaf(kr, f[3 * j], k0)));
     }
 }
-__device__ __forceinline__ void store_channel(float* bp, int c, const float (&v)[8][8]) {
+// ---------------------------------------------------------------------------------------------------- forward, generation 3
+// ncu on generation 2 (profiles/r1_djpeg_v2_ncu.txt): 113 thread-instructions per pixel, issue-active 51 %, 16.6 warps/SM,
+// stalls = short scoreboard (shared-memory loads: 64 table LDS.64 + 48 tile LDS.128 + 64 STS.32 per thread), barrier, MIO
+// throttle; 17 % of the shared wavefronts were bank conflicts (store_channel). Changes:
+//  * warp = channel (Y | Cb | Cr), lane = 8x8 block: the quantisation table is warp-uniform, so Q and 1/Q come from the
+//    kernel-parameter constant bank as immediate operands of the FMULs (no table loads at all);
+//  * the IDCT result goes back to shared memory PLANAR ([block][channel][8][8], 16 conflict-free STS.128 instead of 64
+//    STS.32) and the colour pass reads three LDS.128 per 4 pixels;
+//  * inverse colour transform with the +127 / -k*128 / 1/255 constants folded: 7 FFMA(.SAT) per pixel instead of 16 ops;
+//  * 80 registers -> 8 CTAs (24 warps) per SM instead of 6.
+// Measured and dropped: cp.async.bulk.prefetch.L2 of the tile a later CTA will read (0.117 -> 0.159 ms), packed FFMA2 arithmetic
+// (half issue rate on sm_100a: tools/probes/ffma2_probe.cu).
+template <int MODE, int CC>
+__device__ __forceinline__ void quantise_block(float (&v)[8][8], const DjpegTables& tab) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int k = 0; k < 8; ++k)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bp[i * 24 + 3 * j + c] = v[i][j];
-}
-__device__ __forceinline__ void load_channel_raw(const float* bp, int c, float (&v)[8][8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = bp[i * 24 + 3 * j + c];
+        for (int l = 0; l < 8; ++l) v[k][l] = quant_fwd<MODE>(v[k][l] * tab.rq[CC][k * 8 + l]) * tab.q[CC][k * 8 + l];
 }
 
-__device__ __forceinline__ void load_tables(float2* sq, const DjpegTables& tab) {
-    // layout: sq[idx*2 + cc] = {Q, 1/Q}; adjacent banks for the two tables -> conflict-free mixed-channel reads.
-    for (int i = threadIdx.x; i < 128; i += kThreads) {
-        const int cc = i & 1, idx = i >> 1;
-        sq[i] = make_float2(tab.q[cc][idx], tab.rq[cc][idx]);
+// ypre for 4 pixels of one row from planar level-shifted Y / Cb / Cr, clipped to [0,1] (reference models/jpeg.py:154-157)
+__device__ __forceinline__ void color_inv_clip4(const float4 Y, const float4 B, const float4 R, float (&f)[12]) {
+    constexpr float s = 1.f / 255.f;
+    constexpr float kr = (127.f - 1.402f) * s, kg = (127.f + 1.058272f) * s, kb = (127.f - 1.772f) * s;
+    const float yy[4] = {Y.x, Y.y, Y.z, Y.w}, cb[4] = {B.x, B.y, B.z, B.w}, cr[4] = {R.x, R.y, R.z, R.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[3 * j] = __saturatef(fmaf(cr[j], 1.402f * s, fmaf(yy[j], s, kr)));
+        f[3 * j + 1] = __saturatef(fmaf(cr[j], -0.714136f * s, fmaf(cb[j], -0.344136f * s, fmaf(yy[j], s, kg))));
+        f[3 * j + 2] = __saturatef(fmaf(cb[j], 1.772f * s, fmaf(yy[j], s, kb)));
     }
 }
 
-// ---------------------------------------------------------------------------------------------------- forward
 template <int MODE, bool WRITE_X>
-__global__ void __launch_bounds__(kThreads, 6)
-djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ Xd, int H, int W,
-                 long long nblk, DjpegTables tab) {
+__global__ void __launch_bounds__(kThreads, 8)
+djpeg_fwd3_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ Xd, int H, int W, int nblk,
+                  const __grid_constant__ DjpegTables tab) {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
-    float2* sq = reinterpret_cast<float2*>(smem + kTileFloats);
-    long long* base = reinterpret_cast<long long*>(sq + 128);
+    long long* base = reinterpret_cast<long long*>(smem + kTileFloats);
     const int nbw = W / 8, nbh = H / 8, rowf = W * 3;
-    const long long g0 = (long long)blockIdx.x * kTileBlocks;
+    const int g0 = blockIdx.x * kTileBlocks;
+    const int c = threadIdx.x >> 5, blk = threadIdx.x & 31;
 
-    fill_base_table(base, g0, nblk, nbw, nbh, W);
-    load_tables(sq, tab);
+    if (c == 0) {
+        const int g = g0 + blk;
+        base[blk] = g < nblk ? block_base_offset(g, nbw, nbh, W) : -1;
+    }
     __syncthreads();
     tile_load(tile, x, base, rowf);
     cp_async_wait_all();
     __syncthreads();
 
-    const int blk = threadIdx.x / 3, c = threadIdx.x % 3, cc = c ? 1 : 0;
     float* bp = tile + blk * kBlockFloats;
     float v[8][8];
     load_channel(bp, c, v);
-    __syncthreads();  // all three channel threads of a block have read the RGB data before it is overwritten
+    __syncthreads();  // all three channel warps have read the RGB data before the tile is overwritten
 
     dct2d_fwd(v);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            const float2 qr = sq[(k * 8 + l) * 2 + cc];
-            v[k][l] = quant_fwd<MODE>(v[k][l] * qr.y) * qr.x;
-        }
+    if (c == 0) quantise_block<MODE, 0>(v, tab); else quantise_block<MODE, 1>(v, tab);
     if (WRITE_X) {
         // de-quantised coefficients, reference block order ((n*3+c)*nb + by*nbw + bx, k, l)  (models/jpeg.py:105-114,159)
-        const long long g = g0 + blk;
+        const int g = g0 + blk;
         if (g < nblk) {
-            const long long nb = (long long)nbw * nbh;
+            const int nb = nbw * nbh;
             const long long n = g / nb, r = g % nb;
             float4* o = reinterpret_cast<float4*>(Xd + ((n * 3 + c) * nb + r) * 64);
 #pragma unroll
@@ -247,127 +223,163 @@ djpeg_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __re
         }
     }
     dct2d_inv(v);
-    store_channel(bp, c, v);
+    {   // planar store: [block][channel][row][col]
+        float4* pp = reinterpret_cast<float4*>(bp + c * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            pp[2 * i] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+            pp[2 * i + 1] = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+        }
+    }
     __syncthreads();
 
-    // per-pixel inverse colour transform + /255 + clip, 4 pixels (3 float4 = 48 contiguous bytes) per step, written straight
-    // to global memory (saves a shared-memory round trip and a barrier; L2 merges the partial-sector writes of a warp)
+    // colour pass: unit u = (block u/16, row (u%16)/2, half u%2) = 4 pixels = 48 contiguous output bytes
     for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
-        const long long go = unit_global(u, base, rowf);
-        if (go < 0) continue;
-        const float4* p = reinterpret_cast<const float4*>(tile + unit_offset(u));
-        float4 a = p[0], b = p[1], d = p[2];
-        float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float r, g, bl;
-            color_inv(f[3 * j], f[3 * j + 1], f[3 * j + 2], r, g, bl);
-            f[3 * j] = ni_clamp01(r); f[3 * j + 1] = ni_clamp01(g); f[3 * j + 2] = ni_clamp01(bl);
-        }
-        float4* o = reinterpret_cast<float4*>(y + go);
+        const int b = u >> 4, r = u & 15;
+        const long long bo = base[b];
+        if (bo < 0) continue;
+        const float4* p = reinterpret_cast<const float4*>(tile + b * kBlockFloats + r * 4);
+        float f[12];
+        color_inv_clip4(p[0], p[16], p[32], f);
+        float4* o = reinterpret_cast<float4*>(y + bo + (long long)(r >> 1) * rowf + (r & 1) * 12);
         __stcs(o, make_float4(f[0], f[1], f[2], f[3]));
         __stcs(o + 1, make_float4(f[4], f[5], f[6], f[7]));
         __stcs(o + 2, make_float4(f[8], f[9], f[10], f[11]));
     }
 }
 
-// ---------------------------------------------------------------------------------------------------- backward
+// ---------------------------------------------------------------------------------------------------- backward, generation 3
 // dx = J^T dy with everything recomputed from x. Chain (per block-channel):
 //   r = C_F[1,255x]-127 ; Z = (F r F^T)/Q ; Zq = q(Z) ; xi = F^T (Zq*Q) F ; ypre = (C_I[1,xi+127])/255 ; y = clip(ypre)
 //   g_ypre = dy * 1[0<=ypre<=1] ; g_xi = C_I[:,1:]^T g_ypre / 255 ; G = F g_xi F^T ; g_Z-path: G*Q*q'(Z)/Q = G*q'(Z)
 //   g_r = F^T (G q') F ; dx = 255 * C_F[:,1:]^T g_r
+// Same mapping as djpeg_fwd3_kernel (warp = channel, lane = block, tables from the constant bank, planar exchange through the
+// x tile). q'(Z) uses the period-1 identity cos(2 pi z) = cos(2 pi (z - rint(z))): the reduction is exact in float32, so the
+// special-function unit is accurate (|err| < 5e-7) whatever |z| is, and the ~40-instruction cosf() slow path disappears.
+template <int MODE>
+__device__ __forceinline__ float quant_grad_fast(float z) {
+    const float r = z - ni_round_he(z);                   // exact, in [-0.5, 0.5]
+    const float cs = __cosf(kTwoPi * r);
+    return MODE == 2 ? fmaf(-2.f, cs, 1.f) : 1.f - cs;
+}
+template <int MODE, int CC>
+__device__ __forceinline__ void quantise_block_grad(float (&v)[8][8], float (&qg)[8][8], const DjpegTables& tab) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const float z = v[k][l] * tab.rq[CC][k * 8 + l];
+            qg[k][l] = quant_grad_fast<MODE>(z);
+            v[k][l] = quant_fwd<MODE>(z) * tab.q[CC][k * 8 + l];
+        }
+}
+__device__ __forceinline__ void store_plane(float* plane, const float (&v)[8][8]) {
+    float4* pp = reinterpret_cast<float4*>(plane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pp[2 * i] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        pp[2 * i + 1] = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+    }
+}
+__device__ __forceinline__ void load_plane(const float* plane, float (&v)[8][8]) {
+    const float4* pp = reinterpret_cast<const float4*>(plane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 a = pp[2 * i], b = pp[2 * i + 1];
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
-djpeg_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int H, int W,
-                 long long nblk, DjpegTables tab) {
+djpeg_bwd3_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int nblk,
+                  const __grid_constant__ DjpegTables tab) {
     extern __shared__ __align__(16) float smem[];
-    float* tx = smem;                 // x tile -> xi -> g_r -> dx
-    float* tg = smem + kTileFloats;   // dy tile -> g_xi
-    float2* sq = reinterpret_cast<float2*>(smem + 2 * kTileFloats);
-    long long* base = reinterpret_cast<long long*>(sq + 128);
+    float* tx = smem;                 // x tile (interleaved) -> xi -> g_xi -> g_r (planar)
+    float* tg = smem + kTileFloats;   // dy tile (interleaved)
+    long long* base = reinterpret_cast<long long*>(smem + 2 * kTileFloats);
     const int nbw = W / 8, nbh = H / 8, rowf = W * 3;
-    const long long g0 = (long long)blockIdx.x * kTileBlocks;
+    const int g0 = blockIdx.x * kTileBlocks;
+    const int c = threadIdx.x >> 5, blk = threadIdx.x & 31;
 
-    fill_base_table(base, g0, nblk, nbw, nbh, W);
-    load_tables(sq, tab);
+    if (c == 0) {
+        const int g = g0 + blk;
+        base[blk] = g < nblk ? block_base_offset(g, nbw, nbh, W) : -1;
+    }
     __syncthreads();
     tile_load(tx, x, base, rowf);
     tile_load(tg, dy, base, rowf);
     cp_async_wait_all();
     __syncthreads();
 
-    const int blk = threadIdx.x / 3, c = threadIdx.x % 3, cc = c ? 1 : 0;
-    float* bx_ = tx + blk * kBlockFloats;
-    float* bg_ = tg + blk * kBlockFloats;
+    float* bp = tx + blk * kBlockFloats;
     float v[8][8];
     float qg[8][8];
-    load_channel(bx_, c, v);
+    load_channel(bp, c, v);
     __syncthreads();
     dct2d_fwd(v);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            const float2 qr = sq[(k * 8 + l) * 2 + cc];
-            const float z = v[k][l] * qr.y;
-            qg[k][l] = quant_grad<MODE>(z);
-            v[k][l] = quant_fwd<MODE>(z) * qr.x;
-        }
+    if (c == 0) quantise_block_grad<MODE, 0>(v, qg, tab); else quantise_block_grad<MODE, 1>(v, qg, tab);
     dct2d_inv(v);
-    store_channel(bx_, c, v);
+    store_plane(bp + c * 64, v);
     __syncthreads();
 
-    // pixel pass 1: clip mask from recomputed ypre, g_xi = C_I[:,1:]^T (mask*dy)/255, written over the dy tile
+    // pixel pass 1: clip mask from the recomputed ypre, g_xi = C_I[:,1:]^T (mask * dy) / 255, planar, in place over xi
     for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
-        const float4* px = reinterpret_cast<const float4*>(tx + unit_offset(u));
-        float4* pg = reinterpret_cast<float4*>(tg + unit_offset(u));
-        float4 a = px[0], b = px[1], d = px[2];
-        float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
-        a = pg[0]; b = pg[1]; d = pg[2];
-        float g[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
-        const float s = 1.f / 255.f;
+        const int b = u >> 4, r = u & 15;
+        float4* p = reinterpret_cast<float4*>(tx + b * kBlockFloats + r * 4);
+        const float4* pg = reinterpret_cast<const float4*>(tg + b * kBlockFloats + (r >> 1) * 24 + (r & 1) * 12);
+        const float4 Y = p[0], B = p[16], R = p[32];
+        const float4 ga = pg[0], gb4 = pg[1], gc = pg[2];
+        const float yy[4] = {Y.x, Y.y, Y.z, Y.w}, cb[4] = {B.x, B.y, B.z, B.w}, cr[4] = {R.x, R.y, R.z, R.w};
+        const float g[12] = {ga.x, ga.y, ga.z, ga.w, gb4.x, gb4.y, gb4.z, gb4.w, gc.x, gc.y, gc.z, gc.w};
+        constexpr float s = 1.f / 255.f;
+        constexpr float kr = (127.f - 1.402f) * s, kg = (127.f + 1.058272f) * s, kb = (127.f - 1.772f) * s;
+        float oy[4], ob[4], orr[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float r, gg, bl;
-            color_inv(f[3 * j], f[3 * j + 1], f[3 * j + 2], r, gg, bl);
-            const float gr = (r >= 0.f && r <= 1.f) ? g[3 * j] * s : 0.f;
-            const float ggn = (gg >= 0.f && gg <= 1.f) ? g[3 * j + 1] * s : 0.f;
-            const float gb = (bl >= 0.f && bl <= 1.f) ? g[3 * j + 2] * s : 0.f;
-            g[3 * j] = gr + ggn + gb;                                   // d/dY
-            g[3 * j + 1] = fmaf(-0.344136f, ggn, 1.772f * gb);          // d/dCb
-            g[3 * j + 2] = fmaf(1.402f, gr, -0.714136f * ggn);          // d/dCr
+            const float pr = fmaf(cr[j], 1.402f * s, fmaf(yy[j], s, kr));
+            const float pgn = fmaf(cr[j], -0.714136f * s, fmaf(cb[j], -0.344136f * s, fmaf(yy[j], s, kg)));
+            const float pb = fmaf(cb[j], 1.772f * s, fmaf(yy[j], s, kb));
+            const float gr = (pr >= 0.f && pr <= 1.f) ? g[3 * j] * s : 0.f;
+            const float ggn = (pgn >= 0.f && pgn <= 1.f) ? g[3 * j + 1] * s : 0.f;
+            const float gbl = (pb >= 0.f && pb <= 1.f) ? g[3 * j + 2] * s : 0.f;
+            oy[j] = gr + ggn + gbl;                               // d/dY
+            ob[j] = fmaf(-0.344136f, ggn, 1.772f * gbl);          // d/dCb
+            orr[j] = fmaf(1.402f, gr, -0.714136f * ggn);          // d/dCr
         }
-        pg[0] = make_float4(g[0], g[1], g[2], g[3]);
-        pg[1] = make_float4(g[4], g[5], g[6], g[7]);
-        pg[2] = make_float4(g[8], g[9], g[10], g[11]);
+        p[0] = make_float4(oy[0], oy[1], oy[2], oy[3]);
+        p[16] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        p[32] = make_float4(orr[0], orr[1], orr[2], orr[3]);
     }
     __syncthreads();
 
-    load_channel_raw(bg_, c, v);
+    load_plane(bp + c * 64, v);
     dct2d_fwd(v);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int l = 0; l < 8; ++l) v[k][l] *= qg[k][l];
     dct2d_inv(v);
-    store_channel(bx_, c, v);   // tx is free: xi was consumed by pixel pass 1
+    store_plane(bp + c * 64, v);   // same thread, same addresses as the load above
     __syncthreads();
 
     // pixel pass 2: dx = 255 * C_F[:,1:]^T g_r, written straight to global memory
     for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
-        const long long go = unit_global(u, base, rowf);
-        if (go < 0) continue;
-        const float4* p = reinterpret_cast<const float4*>(tx + unit_offset(u));
-        float4 a = p[0], b = p[1], d = p[2];
-        float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+        const int b = u >> 4, r = u & 15;
+        const long long bo = base[b];
+        if (bo < 0) continue;
+        const float4* p = reinterpret_cast<const float4*>(tx + b * kBlockFloats + r * 4);
+        const float4 Y = p[0], B = p[16], R = p[32];
+        const float gy[4] = {Y.x, Y.y, Y.z, Y.w}, gb[4] = {B.x, B.y, B.z, B.w}, gr[4] = {R.x, R.y, R.z, R.w};
+        float f[12];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float gy = f[3 * j], gb = f[3 * j + 1], gr = f[3 * j + 2];
-            f[3 * j] = fmaf(255.f * 0.299f, gy, fmaf(255.f * -0.168736f, gb, (255.f * 0.5f) * gr));
-            f[3 * j + 1] = fmaf(255.f * 0.587f, gy, fmaf(255.f * -0.331264f, gb, (255.f * -0.418688f) * gr));
-            f[3 * j + 2] = fmaf(255.f * 0.114f, gy, fmaf(255.f * 0.5f, gb, (255.f * -0.081312f) * gr));
+            f[3 * j] = fmaf(255.f * 0.299f, gy[j], fmaf(255.f * -0.168736f, gb[j], (255.f * 0.5f) * gr[j]));
+            f[3 * j + 1] = fmaf(255.f * 0.587f, gy[j], fmaf(255.f * -0.331264f, gb[j], (255.f * -0.418688f) * gr[j]));
+            f[3 * j + 2] = fmaf(255.f * 0.114f, gy[j], fmaf(255.f * 0.5f, gb[j], (255.f * -0.081312f) * gr[j]));
         }
-        float4* o = reinterpret_cast<float4*>(dx + go);
+        float4* o = reinterpret_cast<float4*>(dx + bo + (long long)(r >> 1) * rowf + (r & 1) * 12);
         __stcs(o, make_float4(f[0], f[1], f[2], f[3]));
         __stcs(o + 1, make_float4(f[4], f[5], f[6], f[7]));
         __stcs(o + 2, make_float4(f[8], f[9], f[10], f[11]));
@@ -383,9 +395,8 @@ int fill_tables(DjpegTables& t, const float* q_luma, const float* q_chroma) {
     return 0;
 }
 
-constexpr size_t kFwdSmem = kTileFloats * sizeof(float) + 128 * sizeof(float2) + kTileBlocks * sizeof(long long);
-constexpr size_t kBwdSmem = 2 * kTileFloats * sizeof(float) + 128 * sizeof(float2) + kTileBlocks * sizeof(long long);
-
+constexpr size_t kBwd3Smem = 2 * kTileFloats * sizeof(float) + kTileBlocks * sizeof(long long);
+constexpr size_t kFwd3Smem = kTileFloats * sizeof(float) + kTileBlocks * sizeof(long long);
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     NI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -405,12 +416,13 @@ extern "C" int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h
     DjpegTables tab;
     NI_REQUIRE(fill_tables(tab, q_luma, q_chroma) == 0, "ni_djpeg_fwd: quantisation tables must be positive");
     const long long nblk = (long long)n * (h / 8) * (w / 8);
+    NI_REQUIRE(nblk < (1ll << 31) - 64 * kTileBlocks, "ni_djpeg_fwd: tensor too large (%lld blocks)", nblk);
     const int grid = ni_cdiv(nblk, kTileBlocks);
 #define NI_FWD(MODE, WX)                                                                                      \
     {                                                                                                          \
-        int rc = set_smem(djpeg_fwd_kernel<MODE, WX>, kFwdSmem);                                               \
+        int rc = set_smem(djpeg_fwd3_kernel<MODE, WX>, kFwd3Smem);                                             \
         if (rc) return rc;                                                                                     \
-        djpeg_fwd_kernel<MODE, WX><<<grid, kThreads, kFwdSmem, stream>>>(x, y, x_deq, h, w, nblk, tab);        \
+        djpeg_fwd3_kernel<MODE, WX><<<grid, kThreads, kFwd3Smem, stream>>>(x, y, x_deq, h, w, (int)nblk, tab); \
     }
     if (x_deq) {
         if (mode == 0) NI_FWD(0, true) else if (mode == 1) NI_FWD(1, true) else NI_FWD(2, true)
@@ -434,12 +446,13 @@ extern "C" int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, i
     DjpegTables tab;
     NI_REQUIRE(fill_tables(tab, q_luma, q_chroma) == 0, "ni_djpeg_bwd: quantisation tables must be positive");
     const long long nblk = (long long)n * (h / 8) * (w / 8);
+    NI_REQUIRE(nblk < (1ll << 31) - 64 * kTileBlocks, "ni_djpeg_bwd: tensor too large (%lld blocks)", nblk);
     const int grid = ni_cdiv(nblk, kTileBlocks);
 #define NI_BWD(MODE)                                                                                  \
     {                                                                                                  \
-        int rc = set_smem(djpeg_bwd_kernel<MODE>, kBwdSmem);                                           \
+        int rc = set_smem(djpeg_bwd3_kernel<MODE>, kBwd3Smem);                                         \
         if (rc) return rc;                                                                             \
-        djpeg_bwd_kernel<MODE><<<grid, kThreads, kBwdSmem, stream>>>(x, dy, dx, h, w, nblk, tab);      \
+        djpeg_bwd3_kernel<MODE><<<grid, kThreads, kBwd3Smem, stream>>>(x, dy, dx, h, w, (int)nblk, tab); \
     }
     if (mode == 0) NI_BWD(0) else if (mode == 1) NI_BWD(1) else NI_BWD(2)
 #undef NI_BWD
