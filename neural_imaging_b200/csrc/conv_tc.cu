@@ -333,18 +333,30 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     p.dw = dw;
     const int bnt = pick_bnt(d->cout);
     const int mtiles = (p.atoms + 3) / 4, ntiles = d->cout / bnt;
-    // split-K over pixel ranges: ~4 waves of CTAs, at least 16 steps (512 pixels) per CTA; shorter accumulation chains
-    // also bound the truncation bias of the in-TMEM accumulation (the cross-CTA sum is FP32 round-to-nearest atomics)
-    int splits = (4 * ni_num_sms() + mtiles * ntiles - 1) / (mtiles * ntiles);
-    const int max_splits = (p.steps_total + 15) / 16;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    // split-K over pixel ranges. Cost model (us): waves x steps per CTA x t_iter + per-wave fixed cost + the cross-CTA reduction
+    // (every split adds mtot x cout floats through L2 reductions, ~25 floats/ns measured order of magnitude). The old rule (always
+    // ~4 waves) made the 1x1 transposed-conv layers reduction-bound: 592 CTAs x 16 K atomics for 28 iterations of work each.
+    // Chains are capped at 2048 steps (65 K pixels) to bound the truncation bias of the in-TMEM accumulation.
+    const int tiles = mtiles * ntiles, sms = ni_num_sms() * (bnt == 128 ? 1 : 2);   // resident CTAs (BNT <= 64: two per SM)
+    const int min_splits = (p.steps_total + 2047) / 2048;
+    int max_splits = (p.steps_total + 15) / 16;
+    if (max_splits > 1024) max_splits = 1024;
+    if (max_splits < min_splits) max_splits = min_splits;
+    int splits = min_splits;
+    double best = 1e30;
+    for (int sp = min_splits; sp <= max_splits; ++sp) {
+        const int per = (p.steps_total + sp - 1) / sp;
+        const int eff = (p.steps_total + per - 1) / per;
+        const int waves = (tiles * eff + sms - 1) / sms;
+        const double cost = waves * (per * 0.25 + 6.0) + (double)eff * p.mtot * d->cout / 25e3;
+        if (cost < best) { best = cost; splits = eff; }
+    }
     p.steps_per_split = (p.steps_total + splits - 1) / splits;
     splits = (p.steps_total + p.steps_per_split - 1) / p.steps_per_split;
     dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
 #define NI_TC_WGRAD(B)                                                                                         \
     {                                                                                                          \
-        const size_t smem = (size_t)tcv2::kWgStages * (tcv2::kAraw + 3 * B * 128) + 1024;                      \
+        const size_t smem = (size_t)tcv2::WgCfg<B>::STAGES * (tcv2::kAraw + 3 * B * 128) + 1024;                      \
         rc = set_dyn_smem(tcv2::conv_tc2_wgrad_kernel<B>, smem);                                               \
         if (rc) return rc;                                                                                     \
         tcv2::conv_tc2_wgrad_kernel<B><<<grid, tcv2::kThreadsWg, smem, st>>>(tmX, tmDY, p);                    \

@@ -246,7 +246,11 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
 // [pixel][channel] tile (conflict-free through the swizzle) and writes hi / lo rows straight to TMEM.
 // B (dY^T) has to be K-major in shared memory (kind::tf32 has no MN-major mode): 4 transposer warps turn the pixel-major
 // tile around with scalar stores (also conflict-free).
-constexpr int kWgStages = 2;
+// Pipeline depth per tile width: a stage is 16 KB of raw A + 3 x BNT x 128 B (raw B, B hi, B lo); TMEM holds 2 x BNT accumulator
+// columns + 64 A columns per stage. Measured: the loop is bound by the converter / transposer warps, not by the TMA round trip --
+// BNT <= 64 is faster as two co-resident 2-stage CTAs per SM (7.35 ms) than as one 4-stage CTA (9.02 ms, FAN conv1 wgrad);
+// BNT = 128 only fits one CTA per SM and gains from the third stage (78 -> 109 TFLOP/s).
+template <int BNT> struct WgCfg { static constexpr int STAGES = BNT == 128 ? 3 : 2; };
 constexpr int kThreadsWg = 64 + 128 + 128;
 
 struct WgradParams {
@@ -278,6 +282,7 @@ template <int BNT>
 __global__ void __launch_bounds__(kThreadsWg, 1)
 conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
     constexpr int B_BYTES = BNT * 128;
+    constexpr int kWgStages = WgCfg<BNT>::STAGES;
     constexpr int STAGE_BYTES = kAraw + 3 * B_BYTES;   // raw A (4 atoms), raw B, B hi, B lo
     const uint32_t TMEM_COLS = pow2_cols(2 * BNT + kWgStages * 64);
     extern __shared__ uint8_t smem_raw[];
@@ -394,9 +399,11 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(BNT + c * 32), v2);
             if (!valid) continue;
-            float* o = p.dw + (long long)mm * p.cout + co0 + c * 32;
+            float* o = p.dw + (long long)mm * p.cout + co0 + c * 32;     // 16-byte aligned: cout % 32 == 0
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) atomicAdd(o + jj, v[jj] + v2[jj]);
+            for (int jj = 0; jj < 32; jj += 4)      // 128-bit reductions: a quarter of the L2 atomic operations of scalar atomicAdd
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + jj), "f"(v[jj] + v2[jj]), "f"(v[jj + 1] + v2[jj + 1]),
+                             "f"(v[jj + 2] + v2[jj + 2]), "f"(v[jj + 3] + v2[jj + 3]) : "memory");
         }
         tcgen05_fence_before();
     } else {
