@@ -109,7 +109,13 @@ int ni_conv2d_tc_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_tc(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
 int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
-/* Direct FP32 stencils for the 3/4-input-channel and 3/12-output-channel layers (FAN front end, U-Net first / last conv). */
+/* Direct FP32 stencils for the 3/4-input-channel and 3/12-output-channel layers (FAN front end, U-Net first / last conv):
+ * register-blocked kernels for the hot shapes (FAN 5x5 3->32 and its input gradient, U-Net 4->32 and 32->12), generic
+ * thread-per-pixel stencils ("small") for the other shapes of INet / DNet / ClassicISP / TwitterDCN. */
+int ni_conv2d_direct_supported(const ni_conv_desc* d, int op);
+int ni_conv2d_fprop_direct(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
+int ni_conv2d_dgrad_direct(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
+int ni_conv2d_wgrad_direct(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
 int ni_conv2d_small_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_small(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_small(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);

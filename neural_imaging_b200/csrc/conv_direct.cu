@@ -1,0 +1,447 @@
+// Register-blocked direct FP32 convolutions for the hot non-dense layers of the joint step (FAN front end 5x5 3->32 and its
+// input gradient 32->3, the U-Net input 3x3 4->32 and output 3x3 32->12 + depth_to_space; reference models/forensics.py:62-68,
+// models/pipelines.py:190,215-218). They replace the thread-per-pixel stencils of conv_small.cu for these shapes: those issued
+// one shared-memory load per 3-4 FMAs (measured 12-26 TFLOP/s); here every thread owns 4 pixels x 3..16 channels so that a
+// shared-memory operand feeds 10-16 FMAs.
+//
+//   fewin  (CIN <= 4)   : thread = 4 pixels of a row x COUT/2 output channels; planar input tile, weights broadcast.
+//   manyin (CIN % 4 = 0): thread = 4 pixels of a COLUMN x all COUT (3..12) channels; input tile stored channel-quad-major so
+//                         that neighbouring lanes read neighbouring 16-byte words (conflict-free LDS.128). Also serves as
+//                         dgrad of the few-input layers (flipped, channel-swapped filter).
+//   wgrad               : thread = (filter row, ci, group of COG output channels) with K x COG accumulators, sweeping the
+//                         pixels of 8x32 tiles four at a time; register accumulation across tiles, one atomicAdd per output.
+#include "conv_desc.h"
+#include "ni_common.cuh"
+#include "views.cuh"
+
+namespace {
+
+struct DirectParams {
+    TensorView src, dst;
+    int n, pad_t, pad_l, pad_mode;
+    int act, bias_mod; float alpha; int accumulate;
+};
+
+__device__ __forceinline__ int mirror_idx(int u, int n, int mode) {
+    if (mode == NI_PAD_SYMMETRIC) { if (u < 0) u = -u - 1; if (u >= n) u = 2 * n - 1 - u; }
+    else { if (u < 0) u = -u; if (u >= n) u = 2 * (n - 1) - u; }
+    return u;
+}
+
+__device__ __forceinline__ float act_direct(float v, int act, float alpha) {
+    switch (act) {
+        case NI_ACT_LEAKY_RELU: return v > 0.f ? v : alpha * v;
+        case NI_ACT_RELU: return fmaxf(v, 0.f);
+        case NI_ACT_TANH: return tanhf(v);
+        case NI_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case NI_ACT_CLIP01: return ni_clamp01(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ bool view_vec4(const TensorView& v) { return v.mode == NI_MODE_PLAIN && !(v.pitch & 3) && !(v.coff & 3); }
+
+// ------------------------------------------------------------------------------------------------ few input channels
+constexpr int FW = 64, FH = 8;     // output tile, 256 threads = 128 pixel groups x 2 channel halves
+constexpr int FXS = FW + 4;        // input tile row stride (floats): room for the 8-wide window of the last pixel group
+
+template <int CIN, int COUT, int K>
+__global__ void __launch_bounds__(256, 2)
+conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y) {
+    static_assert(K <= 5 && COUT % 8 == 0, "window of 4 + K - 1 <= 8 input columns; two channel halves of whole float4s");
+    constexpr int COG = COUT / 2, IH = FH + K - 1;
+    extern __shared__ __align__(16) float smem[];
+    float* sw = smem;                              // [K*K][CIN][COUT]
+    float* sx = smem + K * K * CIN * COUT;         // [CIN][IH][FXS]
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.dst.W + FW - 1) / FW, tiles_y = (p.dst.H + FH - 1) / FH;
+    const int tx0 = (blockIdx.x % tiles_x) * FW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * FH, n = blockIdx.x / (tiles_x * tiles_y);
+
+    for (int i = tid; i < K * K * CIN * COUT; i += 256) sw[i] = __ldg(w + i);      // w is a slice of the flat parameter buffer: not necessarily 16-byte aligned
+    for (int i = tid; i < IH * FXS; i += 256) {
+        const int px = i % FXS, py = i / FXS;
+        int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+        if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
+        const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) sx[(c * IH + py) * FXS + px] = in ? __ldg(x + view_addr(p.src, n, sy, sxx, c)) : 0.f;
+    }
+    __syncthreads();
+
+    const int pg = tid & 127, cog = tid >> 7;      // warp-uniform channel half: weight loads are pure broadcasts
+    const int gx = pg & 15, gy = pg >> 4;
+    float acc[4][COG];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < COG; ++j) acc[q][j] = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float4* xp = reinterpret_cast<const float4*>(sx + (ci * IH + gy + a) * FXS + gx * 4);
+            const float4 x0 = xp[0], x1 = xp[1];
+            const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((a * K + b) * CIN + ci) * COUT + cog * COG);
+#pragma unroll
+                for (int j4 = 0; j4 < COG / 4; ++j4) {
+                    const float4 wv = wp[j4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[q][4 * j4] = fmaf(xr[q + b], wv.x, acc[q][4 * j4]);
+                        acc[q][4 * j4 + 1] = fmaf(xr[q + b], wv.y, acc[q][4 * j4 + 1]);
+                        acc[q][4 * j4 + 2] = fmaf(xr[q + b], wv.z, acc[q][4 * j4 + 2]);
+                        acc[q][4 * j4 + 3] = fmaf(xr[q + b], wv.w, acc[q][4 * j4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+    const int oy = ty0 + gy;
+    if (oy >= p.dst.H) return;
+    float bv[COG];
+#pragma unroll
+    for (int j = 0; j < COG; ++j) {
+        const int co = cog * COG + j;
+        bv[j] = bias ? __ldg(bias + (p.bias_mod > 0 ? co % p.bias_mod : co)) : 0.f;
+    }
+    const bool vec = view_vec4(p.dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ox = tx0 + gx * 4 + q;
+        if (ox >= p.dst.W) continue;
+#pragma unroll
+        for (int j = 0; j < COG; ++j) acc[q][j] = act_direct(acc[q][j] + bv[j], p.act, p.alpha);
+        if (vec) {
+            float4* o = reinterpret_cast<float4*>(y + view_addr(p.dst, n, oy, ox, cog * COG));
+#pragma unroll
+            for (int j4 = 0; j4 < COG / 4; ++j4) {
+                float4 r = make_float4(acc[q][4 * j4], acc[q][4 * j4 + 1], acc[q][4 * j4 + 2], acc[q][4 * j4 + 3]);
+                if (p.accumulate) { const float4 old = o[j4]; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+                o[j4] = r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < COG; ++j) {
+                float* o = y + view_addr(p.dst, n, oy, ox, cog * COG + j);
+                *o = p.accumulate ? *o + acc[q][j] : acc[q][j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ many input channels
+constexpr int MW = 32, MH = 16;    // output tile, 128 threads: lane = column, warp = group of 4 rows
+
+// weights re-ordered for the column-blocked kernel: [b][c4][a][ci % 4][co]  (one contiguous run per (b, c4))
+__global__ void reorder_manyin_weights_kernel(const float* __restrict__ w, float* __restrict__ wr, int k, int cin, int cout, int flip) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= k * k * cin * cout) return;
+    const int co = i % cout, e = (i / cout) % 4, a = (i / (cout * 4)) % k, c4 = (i / (cout * 4 * k)) % (cin / 4), b = i / (cout * 4 * k * (cin / 4));
+    const int ci = c4 * 4 + e;
+    // flip: dgrad = forward conv of dy with the spatially flipped filter and swapped channel axes (w is (k,k,cout_fwd=cin... see caller)
+    wr[i] = flip ? w[(((k - 1 - a) * k + (k - 1 - b)) * cout + co) * cin + ci] : w[((a * k + b) * cin + ci) * cout + co];
+}
+
+template <int CIN, int COUT, int K>
+__global__ void __launch_bounds__(128, 2)
+conv_manyin_kernel(DirectParams p, const float* __restrict__ x, const float* __restrict__ wr, const float* __restrict__ bias, float* __restrict__ y) {
+    static_assert(CIN % 4 == 0, "channel quads");
+    constexpr int C4 = CIN / 4, IH = MH + K - 1, IW = MW + K - 1, R = 4 + K - 1;
+    constexpr int PLANE = IH * IW * 4 + 4;         // +16 bytes: the 8 quads of a pixel land in 8 different bank groups
+    extern __shared__ __align__(16) float smem[];
+    float* sw = smem;                              // [K][C4][K][4][COUT]
+    float* sx = smem + K * K * CIN * COUT;         // [C4][IH][IW][4]
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.dst.W + MW - 1) / MW, tiles_y = (p.dst.H + MH - 1) / MH;
+    const int tx0 = (blockIdx.x % tiles_x) * MW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * MH, n = blockIdx.x / (tiles_x * tiles_y);
+
+    for (int i = tid; i < K * K * CIN * COUT / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wr) + i);
+    const bool vec_in = view_vec4(p.src);
+    for (int i = tid; i < IH * IW * C4; i += 128) {
+        const int c4 = i % C4, pxl = i / C4, px = pxl % IW, py = pxl / IW;
+        int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+        if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W) {
+            if (vec_in) v = __ldg(reinterpret_cast<const float4*>(x + view_addr(p.src, n, sy, sxx, c4 * 4)));
+            else {
+                v.x = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4)); v.y = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 1));
+                v.z = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 2)); v.w = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 3));
+            }
+        }
+        *reinterpret_cast<float4*>(sx + c4 * PLANE + pxl * 4) = v;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, rg = tid >> 5;
+    float acc[4][COUT];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[q][j] = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < K; ++b) {
+#pragma unroll 1
+        for (int c4 = 0; c4 < C4; ++c4) {
+            float4 xv[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(sx + c4 * PLANE + ((rg * 4 + r) * IW + lane + b) * 4);
+            const float* wp = sw + (b * C4 + c4) * (K * 4 * COUT);
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                float wv[4 * COUT];
+#pragma unroll
+                for (int t = 0; t < COUT; ++t) {      // 4 * COUT floats = COUT float4
+                    const float4 f = *reinterpret_cast<const float4*>(wp + a * 4 * COUT + t * 4);
+                    wv[4 * t] = f.x; wv[4 * t + 1] = f.y; wv[4 * t + 2] = f.z; wv[4 * t + 3] = f.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xe[4] = {xv[q + a].x, xv[q + a].y, xv[q + a].z, xv[q + a].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int j = 0; j < COUT; ++j) acc[q][j] = fmaf(xe[e], wv[e * COUT + j], acc[q][j]);
+                }
+            }
+        }
+    }
+    const int ox = tx0 + lane;
+    if (ox >= p.dst.W) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int oy = ty0 + rg * 4 + q;
+        if (oy >= p.dst.H) continue;
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+            float t = acc[q][j];
+            if (bias) t += __ldg(bias + (p.bias_mod > 0 ? j % p.bias_mod : j));
+            t = act_direct(t, p.act, p.alpha);
+            float* o = y + view_addr(p.dst, n, oy, ox, j);
+            *o = p.accumulate ? *o + t : t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+constexpr int WH = 8, WW = 32, WXS = 36;   // pixel tile; input tile row stride (8-wide windows starting at multiples of 4)
+
+struct DirectWgradParams {
+    TensorView xin, dyv;
+    int n, pad_t, pad_l, pad_mode;
+    int tiles_x, tiles_y, tiles_total;
+};
+
+template <int CIN, int COUT, int K, int COG>
+__global__ void __launch_bounds__(256)
+conv_direct_wgrad_kernel(DirectWgradParams p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw) {
+    static_assert(K <= 5 && COUT % COG == 0, "window of 4 + K - 1 <= 8 input columns");
+    constexpr int XH = WH + K - 1;
+    constexpr int TPS = K * CIN * (COUT / COG);                 // threads per pixel split
+    constexpr int S = (256 / TPS) < WH ? (256 / TPS) : WH;      // splits: each takes rows s, s + S, ...
+    static_assert(S >= 1, "too many (row, ci, co-group) combinations for one CTA");
+    extern __shared__ __align__(16) float smem[];
+    float* sx = smem;                                  // [CIN][XH][WXS]
+    float* sd = smem + CIN * XH * WXS;                 // [WH][WW][COUT]
+    const int tid = threadIdx.x;
+    const int s = tid / TPS, r = tid - s * TPS;
+    const bool active = s < S;
+    const int cog = r % (COUT / COG), ci = (r / (COUT / COG)) % CIN, a = r / ((COUT / COG) * CIN);
+    float acc[K][COG];
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+        for (int j = 0; j < COG; ++j) acc[b][j] = 0.f;
+
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const int tx0 = (tile % p.tiles_x) * WW, ty0 = ((tile / p.tiles_x) % p.tiles_y) * WH, n = tile / (p.tiles_x * p.tiles_y);
+        __syncthreads();
+        for (int i = tid; i < XH * WXS; i += 256) {
+            const int px = i % WXS, py = i / WXS;
+            int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+            if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.xin.H, p.pad_mode); sxx = mirror_idx(sxx, p.xin.W, p.pad_mode); }
+            const bool in = px < WW + K - 1 && sy >= 0 && sy < p.xin.H && sxx >= 0 && sxx < p.xin.W;
+            if (CIN % 4 == 0 && view_vec4(p.xin)) {
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const float4 v = in ? __ldg(reinterpret_cast<const float4*>(x + view_addr(p.xin, n, sy, sxx, c4 * 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sx[((c4 * 4) * XH + py) * WXS + px] = v.x; sx[((c4 * 4 + 1) * XH + py) * WXS + px] = v.y;
+                    sx[((c4 * 4 + 2) * XH + py) * WXS + px] = v.z; sx[((c4 * 4 + 3) * XH + py) * WXS + px] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) sx[(c * XH + py) * WXS + px] = in ? __ldg(x + view_addr(p.xin, n, sy, sxx, c)) : 0.f;
+            }
+        }
+        if (COUT % 4 == 0 && view_vec4(p.dyv)) {
+            for (int i = tid; i < WH * WW * (COUT / 4); i += 256) {
+                const int c4 = i % (COUT / 4), px = (i / (COUT / 4)) % WW, py = i / ((COUT / 4) * WW);
+                const int oy = ty0 + py, ox = tx0 + px;
+                reinterpret_cast<float4*>(sd)[i] = (oy < p.dyv.H && ox < p.dyv.W) ? __ldg(reinterpret_cast<const float4*>(dy + view_addr(p.dyv, n, oy, ox, c4 * 4)))
+                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int i = tid; i < WH * WW * COUT; i += 256) {
+                const int c = i % COUT, px = (i / COUT) % WW, py = i / (COUT * WW);
+                const int oy = ty0 + py, ox = tx0 + px;
+                sd[i] = (oy < p.dyv.H && ox < p.dyv.W) ? __ldg(dy + view_addr(p.dyv, n, oy, ox, c)) : 0.f;
+            }
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 1
+        for (int yy = s; yy < WH; yy += S) {
+            const float* xr = sx + (ci * XH + yy + a) * WXS;
+            const float* dr = sd + (yy * WW) * COUT + cog * COG;
+#pragma unroll 2
+            for (int xq = 0; xq < WW; xq += 4) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xr + xq), x1 = *reinterpret_cast<const float4*>(xr + xq + 4);
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float g[COG];
+                    if (COG % 4 == 0 && COUT % 4 == 0) {
+#pragma unroll
+                        for (int j4 = 0; j4 < COG / 4; ++j4) {
+                            const float4 f = *reinterpret_cast<const float4*>(dr + (xq + e) * COUT + j4 * 4);
+                            g[4 * j4] = f.x; g[4 * j4 + 1] = f.y; g[4 * j4 + 2] = f.z; g[4 * j4 + 3] = f.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < COG; ++j) g[j] = dr[(xq + e) * COUT + j];
+                    }
+#pragma unroll
+                    for (int b = 0; b < K; ++b)
+#pragma unroll
+                        for (int j = 0; j < COG; ++j) acc[b][j] = fmaf(xv[e + b], g[j], acc[b][j]);
+                }
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+        for (int j = 0; j < COG; ++j) atomicAdd(dw + (((a * K + b) * CIN) + ci) * COUT + cog * COG + j, acc[b][j]);
+}
+
+template <int CIN, int COUT, int K>
+int launch_fewin(const DirectParams& p, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (K * K * CIN * COUT + CIN * (FH + K - 1) * FXS);
+    NI_CUDA(cudaFuncSetAttribute(conv_fewin_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = ((p.dst.W + FW - 1) / FW) * ((p.dst.H + FH - 1) / FH) * p.n;
+    conv_fewin_kernel<CIN, COUT, K><<<tiles, 256, smem, st>>>(p, x, w, bias, y);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+template <int CIN, int COUT, int K>
+int launch_manyin(const DirectParams& p, const float* x, const float* wr, const float* bias, float* y, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (K * K * CIN * COUT + (CIN / 4) * ((MH + K - 1) * (MW + K - 1) * 4 + 4));
+    NI_CUDA(cudaFuncSetAttribute(conv_manyin_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = ((p.dst.W + MW - 1) / MW) * ((p.dst.H + MH - 1) / MH) * p.n;
+    conv_manyin_kernel<CIN, COUT, K><<<tiles, 128, smem, st>>>(p, x, wr, bias, y);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+template <int CIN, int COUT, int K, int COG>
+int launch_wgrad(DirectWgradParams p, const float* x, const float* dy, float* dw, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (CIN * (WH + K - 1) * WXS + WH * WW * COUT);
+    NI_CUDA(cudaFuncSetAttribute(conv_direct_wgrad_kernel<CIN, COUT, K, COG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.tiles_x = (p.dyv.W + WW - 1) / WW; p.tiles_y = (p.dyv.H + WH - 1) / WH; p.tiles_total = p.tiles_x * p.tiles_y * p.n;
+    int per_sm = (int)((200u << 10) / (smem + 1024));
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = p.tiles_total < per_sm * ni_num_sms() ? p.tiles_total : per_sm * ni_num_sms();
+    conv_direct_wgrad_kernel<CIN, COUT, K, COG><<<grid, 256, smem, st>>>(p, x, dy, dw);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// (cin, cout, k) of the logical FORWARD convolution each kernel family is instantiated for
+#define NI_FEWIN_SHAPES(X) X(3, 32, 5) X(4, 32, 3)
+#define NI_MANYIN_SHAPES(X) X(32, 3, 5) X(32, 12, 3) X(32, 4, 3)
+#define NI_DWGRAD_SHAPES(X) X(3, 32, 5, 8) X(4, 32, 3, 8) X(32, 12, 3, 12) X(3, 3, 5, 3)
+
+}  // namespace
+
+int ni_get_scratch2(size_t bytes, float** out);
+
+// op: 0 fprop, 1 dgrad, 2 wgrad. Only stride 1, square filters, plain input addressing.
+extern "C" int ni_conv2d_direct_supported(const ni_conv_desc* d, int op) {
+    if (!d || d->n <= 0 || d->stride != 1 || d->kh != d->kw || d->in_mode != NI_MODE_PLAIN) return 0;
+#define X(a, b, c) if (op == 0 && d->cin == a && d->cout == b && d->kh == c) return 1;
+    NI_FEWIN_SHAPES(X) NI_MANYIN_SHAPES(X)
+#undef X
+#define X(a, b, c) if (op == 1 && d->pad_mode == NI_PAD_ZERO && d->cout == a && d->cin == b && d->kh == c) return 1;   /* dgrad: roles swapped */
+    NI_MANYIN_SHAPES(X)
+#undef X
+#define X(a, b, c, g) if (op == 2 && d->cin == a && d->cout == b && d->kh == c) return 1;
+    NI_DWGRAD_SHAPES(X)
+#undef X
+    return 0;
+}
+
+static int reorder_weights(const float* w, int k, int cin, int cout, int flip, float** out, cudaStream_t st) {
+    const int total = k * k * cin * cout;
+    int rc = ni_get_scratch2(sizeof(float) * (size_t)total, out);
+    if (rc) return rc;
+    reorder_manyin_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, *out, k, cin, cout, flip);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_conv2d_fprop_direct(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    NI_REQUIRE(ni_conv2d_direct_supported(d, 0) && x && w && y, "ni_conv2d_fprop_direct: unsupported problem or null pointer");
+    DirectParams p;
+    p.src = TensorView{d->h, d->w, d->cin, d->in_pitch, d->in_coff, d->in_mode};
+    p.dst = TensorView{d->oh, d->ow, d->cout, d->out_pitch, d->out_coff, d->out_mode};
+    p.n = d->n; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
+    p.act = d->act; p.bias_mod = d->bias_mod; p.alpha = d->act_alpha; p.accumulate = d->accumulate;
+#define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return launch_fewin<a, b, c>(p, x, w, bias, y, st);
+    NI_FEWIN_SHAPES(X)
+#undef X
+    float* wr = nullptr;
+    int rc = reorder_weights(w, d->kh, d->cin, d->cout, 0, &wr, st);
+    if (rc) return rc;
+#define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return launch_manyin<a, b, c>(p, x, wr, bias, y, st);
+    NI_MANYIN_SHAPES(X)
+#undef X
+    return NI_ERR_UNSUPPORTED;
+}
+
+// dx = forward conv of dy (cout channels) with the flipped / channel-swapped filter (stride 1, zero padding K-1-pad).
+extern "C" int ni_conv2d_dgrad_direct(const ni_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st) {
+    NI_REQUIRE(ni_conv2d_direct_supported(d, 1) && dy && w && dx, "ni_conv2d_dgrad_direct: unsupported problem or null pointer");
+    const int k = d->kh;
+    float* wr = nullptr;
+    // w is (k, k, cin, cout); the "forward" conv of dgrad has cin' = cout, cout' = cin
+    int rc = reorder_weights(w, k, d->cout, d->cin, 1, &wr, st);
+    if (rc) return rc;
+    DirectParams p;
+    p.src = TensorView{d->oh, d->ow, d->cout, d->out_pitch, d->out_coff, d->out_mode};
+    p.dst = TensorView{d->h, d->w, d->cin, d->in_pitch, d->in_coff, d->in_mode};
+    p.n = d->n; p.pad_t = k - 1 - d->pad_t; p.pad_l = k - 1 - d->pad_l; p.pad_mode = NI_PAD_ZERO;
+    p.act = NI_ACT_NONE; p.bias_mod = 0; p.alpha = 0.f; p.accumulate = d->accumulate;
+#define X(a, b, c) if (d->cout == a && d->cin == b && d->kh == c) return launch_manyin<a, b, c>(p, dy, wr, nullptr, dx, st);
+    NI_MANYIN_SHAPES(X)
+#undef X
+    return NI_ERR_UNSUPPORTED;
+}
+
+extern "C" int ni_conv2d_wgrad_direct(const ni_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
+    NI_REQUIRE(ni_conv2d_direct_supported(d, 2) && x && dy && dw, "ni_conv2d_wgrad_direct: unsupported problem or null pointer");
+    if (!d->accumulate) NI_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->kh * d->kw * d->cin * d->cout, st));
+    DirectWgradParams p;
+    p.xin = TensorView{d->h, d->w, d->cin, d->in_pitch, d->in_coff, d->in_mode};
+    p.dyv = TensorView{d->oh, d->ow, d->cout, d->out_pitch, d->out_coff, d->out_mode};
+    p.n = d->n; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
+#define X(a, b, c, g) if (d->cin == a && d->cout == b && d->kh == c) return launch_wgrad<a, b, c, g>(p, x, dy, dw, st);
+    NI_DWGRAD_SHAPES(X)
+#undef X
+    return NI_ERR_UNSUPPORTED;
+}

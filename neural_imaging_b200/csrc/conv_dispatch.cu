@@ -18,6 +18,10 @@ extern "C" int ni_conv2d_small_supported(const ni_conv_desc*, int);
 extern "C" int ni_conv2d_fprop_small(const ni_conv_desc*, const float*, const float*, const float*, float*, cudaStream_t);
 extern "C" int ni_conv2d_dgrad_small(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
 extern "C" int ni_conv2d_wgrad_small(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_direct_supported(const ni_conv_desc*, int);
+extern "C" int ni_conv2d_fprop_direct(const ni_conv_desc*, const float*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_dgrad_direct(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
+extern "C" int ni_conv2d_wgrad_direct(const ni_conv_desc*, const float*, const float*, float*, cudaStream_t);
 int ni_get_scratch2(size_t bytes, float** out);
 
 static bool force_simt() {
@@ -36,6 +40,7 @@ extern "C" void ni_conv2d_set_force_simt(int on) { g_force_simt_override = on; }
 static bool use_simt() { return g_force_simt_override >= 0 ? g_force_simt_override == 1 : force_simt(); }
 
 extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    if (!use_simt() && ni_conv2d_direct_supported(d, 0)) return ni_conv2d_fprop_direct(d, x, w, bias, y, st);
     if (!use_simt() && ni_conv2d_small_supported(d, 0)) return ni_conv2d_fprop_small(d, x, w, bias, y, st);
     if (!use_simt() && ni_conv2d_tc_supported(d, 0) && aligned16(x) && aligned16(y)) return ni_conv2d_fprop_tc(d, x, w, bias, y, st);
     return ni_conv2d_fprop_simt(d, x, w, bias, y, st);
@@ -44,6 +49,7 @@ extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const floa
 // w: the layer's HWIO weights (kh, kw, cin, cout).
 extern "C" int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st) {
     NI_REQUIRE(d && w, "ni_conv2d_dgrad: null pointer");
+    if (!use_simt() && ni_conv2d_direct_supported(d, 1)) return ni_conv2d_dgrad_direct(d, dy, w, dx, st);
     if (!use_simt() && ni_conv2d_small_supported(d, 1)) return ni_conv2d_dgrad_small(d, dy, w, dx, st);
     if (!use_simt() && ni_conv2d_tc_supported(d, 1) && aligned16(dy) && aligned16(dx)) return ni_conv2d_dgrad_tc(d, dy, w, dx, st);
     float* wt = nullptr;
@@ -56,6 +62,7 @@ extern "C" int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const flo
 }
 
 extern "C" int ni_conv2d_wgrad(const ni_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
+    if (!use_simt() && ni_conv2d_direct_supported(d, 2)) return ni_conv2d_wgrad_direct(d, x, dy, dw, st);
     if (!use_simt() && ni_conv2d_small_supported(d, 2)) return ni_conv2d_wgrad_small(d, x, dy, dw, st);
     if (!use_simt() && ni_conv2d_tc_supported(d, 2) && aligned16(x) && aligned16(dy)) return ni_conv2d_wgrad_tc(d, x, dy, dw, st);
     return ni_conv2d_wgrad_simt(d, x, dy, dw, st);

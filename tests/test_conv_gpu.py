@@ -34,6 +34,12 @@ CASES = [
     (2, 32, 32, 64, 128, 5, 1, 'SAME', 'leaky_relu'),
     (2, 16, 16, 128, 256, 5, 1, 'SAME', 'leaky_relu'),
     (1, 256, 256, 32, 32, 3, 1, 'SAME', 'relu'),
+    # register-blocked direct kernels (csrc/conv_direct.cu): several tiles, ragged right / bottom edges
+    (2, 40, 72, 3, 32, 5, 1, 'SAME', 'leaky_relu'),
+    (1, 24, 40, 4, 32, 3, 1, 'SAME', 'leaky_relu'),
+    (2, 20, 36, 32, 12, 3, 1, 'SAME', None),
+    (2, 40, 40, 3, 3, 5, 1, 'SAME', None),
+    (1, 128, 128, 3, 32, 5, 1, 'SAME', 'leaky_relu'),
 ]
 
 
