@@ -159,6 +159,8 @@ def run_ours(args, rank, world, local_rank):
     bl = gb // world
     flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=RAW, seed=1234)
     sync = GradSync() if world > 1 else None
+    if not args.no_graph:
+        flow.enable_cuda_graph()       # static step (augment=False, fixed quality): two captured graphs instead of ~220 launches
     if world > 1:
         broadcast_parameters(flow._stores)
     xh, yh = make_inputs(gb, 1234)
@@ -174,13 +176,17 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        host_ms[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE a step (no sync inside)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
         if world > 1:
@@ -196,6 +202,8 @@ def run_ours(args, rank, world, local_rank):
     L.ni_reset_launch_count()
     ms = timed(step_resident, args.steps)
     launches = int(L.ni_launch_count())
+    if flow.graph_launches_per_step:        # graph replays do not pass through the host-side launch counter
+        launches = flow.graph_launches_per_step * args.steps
     clk = clocks.stop() if rank == 0 else None
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, through the public training_step()
@@ -214,6 +222,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-kernel roofline: same steps again with every C-ABI call bracketed by CUDA events (own pass so that the
     # event records do not perturb `value`)
+    flow.enable_cuda_graph(False)
     prof = EventProfiler()
     _lib.PROFILER = prof
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -262,7 +271,8 @@ def run_ours(args, rank, world, local_rank):
                    'l2': 'working set (multi-GB activations per step) >> 126 MB L2; no explicit flush needed'},
         'e2e': {'value': gb / (ms_e2e * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(xp.numel() * 4 + yp.numel() * 4) * world, 'd2h_bytes_per_step': 4 * world},
-        'gpu_launches': launches, 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:12],
+        'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'cuda_graph': not args.no_graph,
+        'host_enqueue_ms_per_step': host_ms.get('step_resident'), 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:12],
         'images_per_sec_codec_fan': 5 * gb / (ms * 1e-3), 'loss': float(loss.numpy()),
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -343,6 +353,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4)
     ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying the captured CUDA graphs')
     ap.add_argument('--layer-report', default=None, help='write a per-layer (per conv shape) timing table to this JSON file')
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))

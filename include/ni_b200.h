@@ -161,6 +161,10 @@ int ni_pad_fold(const float* dpad, float* dx, int n, int h, int w, int c, int pa
  * also replaces the host-side NaN scan (:281): *nonfinite_flag |= 1 if any gradient is NaN/Inf. */
 int ni_adam_keras(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   long long step, float gscale, int* nonfinite_flag, ni_stream_t stream);
+/* Same update with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from DEVICE memory, so that a captured CUDA graph of the
+ * training step can be replayed with a new step count / learning rate (optimizer.lr.assign, :279). */
+int ni_adam_keras_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr_t_dev, float beta1, float beta2,
+                      float eps, float gscale, int* nonfinite_flag, ni_stream_t stream);
 /* DiscreteLatent + Quantization('soft-codebook') + tf_helpers.entropy histogram (models/layers.py:139-170,195-203,
  * helpers/tf_helpers.py:290-333), float64 inside like the reference. hist_acc: ncodes doubles zeroed by the caller (sum of the
  * normalised weights per bin, evaluated at the QUANTISED values like the reference); q: the forward's output;

@@ -39,9 +39,27 @@ __device__ __forceinline__ float act_direct(float v, int act, float alpha) {
     }
 }
 
+// Asynchronous global -> shared copies with zero fill (src-size 0) for out-of-range taps: a whole tile is in flight at once,
+// whereas a load -> store loop serialises one memory round trip per iteration (measured: 31 us of loads for 5 us of math per tile).
+__device__ __forceinline__ void cp_async4_zfill(float* smem, const float* gmem, bool valid) {
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16_zfill(float* smem, const float* gmem, bool valid) {
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 __device__ __forceinline__ bool view_vec4(const TensorView& v) { return v.mode == NI_MODE_PLAIN && !(v.pitch & 3) && !(v.coff & 3); }
 
 // ------------------------------------------------------------------------------------------------ few input channels
+// Note on the operand path: shared-memory operands cost register write-back bandwidth (128 B/clk/SM = 1 byte per FMA per thread
+// at full FMA rate) whether they are broadcasts or not; these kernels move 0.5 - 1.5 B per FMA and sit at 30 - 34 TFLOP/s.
+// Measured alternative: weights in __constant__ memory indexed by the (rolled) filter-row loop compile to per-thread LDC
+// loads, which were no faster (3.06 vs 2.99 ms for the FAN 3->32 fprop) and add a global staging buffer -- not kept.
 constexpr int FW = 64, FH = 8;     // output tile, 256 threads = 128 pixel groups x 2 channel halves
 constexpr int FXS = FW + 4;        // input tile row stride (floats): room for the 8-wide window of the last pixel group
 
@@ -57,15 +75,15 @@ conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __re
     const int tiles_x = (p.dst.W + FW - 1) / FW, tiles_y = (p.dst.H + FH - 1) / FH;
     const int tx0 = (blockIdx.x % tiles_x) * FW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * FH, n = blockIdx.x / (tiles_x * tiles_y);
 
-    for (int i = tid; i < K * K * CIN * COUT; i += 256) sw[i] = __ldg(w + i);      // w is a slice of the flat parameter buffer: not necessarily 16-byte aligned
-    for (int i = tid; i < IH * FXS; i += 256) {
-        const int px = i % FXS, py = i / FXS;
+    for (int i = tid; i < K * K * CIN * COUT; i += 256) cp_async4_zfill(sw + i, w + i, true);   // w: slice of the flat parameter buffer (4-byte aligned)
+    for (int i = tid; i < IH * FXS * CIN; i += 256) {
+        const int c = i % CIN, px = (i / CIN) % FXS, py = i / (CIN * FXS);
         int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
         if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
         const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
-#pragma unroll
-        for (int c = 0; c < CIN; ++c) sx[(c * IH + py) * FXS + px] = in ? __ldg(x + view_addr(p.src, n, sy, sxx, c)) : 0.f;
+        cp_async4_zfill(sx + (c * IH + py) * FXS + px, in ? x + view_addr(p.src, n, sy, sxx, c) : x, in);
     }
+    cp_async_wait();
     __syncthreads();
 
     const int pg = tid & 127, cog = tid >> 7;      // warp-uniform channel half: weight loads are pure broadcasts
@@ -158,22 +176,21 @@ conv_manyin_kernel(DirectParams p, const float* __restrict__ x, const float* __r
     const int tiles_x = (p.dst.W + MW - 1) / MW, tiles_y = (p.dst.H + MH - 1) / MH;
     const int tx0 = (blockIdx.x % tiles_x) * MW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * MH, n = blockIdx.x / (tiles_x * tiles_y);
 
-    for (int i = tid; i < K * K * CIN * COUT / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wr) + i);
+    for (int i = tid; i < K * K * CIN * COUT / 4; i += 128) cp_async16_zfill(sw + 4 * i, wr + 4 * i, true);
     const bool vec_in = view_vec4(p.src);
     for (int i = tid; i < IH * IW * C4; i += 128) {
         const int c4 = i % C4, pxl = i / C4, px = pxl % IW, py = pxl / IW;
         int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
         if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W) {
-            if (vec_in) v = __ldg(reinterpret_cast<const float4*>(x + view_addr(p.src, n, sy, sxx, c4 * 4)));
-            else {
-                v.x = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4)); v.y = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 1));
-                v.z = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 2)); v.w = __ldg(x + view_addr(p.src, n, sy, sxx, c4 * 4 + 3));
-            }
+        const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
+        float* dst = sx + c4 * PLANE + pxl * 4;
+        if (vec_in) cp_async16_zfill(dst, in ? x + view_addr(p.src, n, sy, sxx, c4 * 4) : x, in);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cp_async4_zfill(dst + e, in ? x + view_addr(p.src, n, sy, sxx, c4 * 4 + e) : x, in);
         }
-        *reinterpret_cast<float4*>(sx + c4 * PLANE + pxl * 4) = v;
     }
+    cp_async_wait();
     __syncthreads();
 
     const int lane = tid & 31, rg = tid >> 5;
@@ -189,24 +206,17 @@ conv_manyin_kernel(DirectParams p, const float* __restrict__ x, const float* __r
             float4 xv[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(sx + c4 * PLANE + ((rg * 4 + r) * IW + lane + b) * 4);
-            const float* wp = sw + (b * C4 + c4) * (K * 4 * COUT);
+            const float* wp = sw + (b * C4 + c4) * (K * 4 * COUT);             // broadcast loads
 #pragma unroll
-            for (int a = 0; a < K; ++a) {
-                float wv[4 * COUT];
-#pragma unroll
-                for (int t = 0; t < COUT; ++t) {      // 4 * COUT floats = COUT float4
-                    const float4 f = *reinterpret_cast<const float4*>(wp + a * 4 * COUT + t * 4);
-                    wv[4 * t] = f.x; wv[4 * t + 1] = f.y; wv[4 * t + 2] = f.z; wv[4 * t + 3] = f.w;
-                }
+            for (int a = 0; a < K; ++a)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float xe[4] = {xv[q + a].x, xv[q + a].y, xv[q + a].z, xv[q + a].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
 #pragma unroll
-                        for (int j = 0; j < COUT; ++j) acc[q][j] = fmaf(xe[e], wv[e * COUT + j], acc[q][j]);
+                        for (int j = 0; j < COUT; ++j) acc[q][j] = fmaf(xe[e], wp[(a * 4 + e) * COUT + j], acc[q][j]);
                 }
-            }
         }
     }
     const int ox = tx0 + lane;
@@ -244,8 +254,9 @@ conv_direct_wgrad_kernel(DirectWgradParams p, const float* __restrict__ x, const
     constexpr int S = (256 / TPS) < WH ? (256 / TPS) : WH;      // splits: each takes rows s, s + S, ...
     static_assert(S >= 1, "too many (row, ci, co-group) combinations for one CTA");
     extern __shared__ __align__(16) float smem[];
+    constexpr int XPL = XH * WXS + 4;                  // channel-plane stride (+4 floats: neighbouring channels on different banks)
     float* sx = smem;                                  // [CIN][XH][WXS]
-    float* sd = smem + CIN * XH * WXS;                 // [WH][WW][COUT]
+    float* sd = smem + CIN * XPL;                      // [WH][WW][COUT]
     const int tid = threadIdx.x;
     const int s = tid / TPS, r = tid - s * TPS;
     const bool active = s < S;
@@ -259,42 +270,55 @@ conv_direct_wgrad_kernel(DirectWgradParams p, const float* __restrict__ x, const
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
         const int tx0 = (tile % p.tiles_x) * WW, ty0 = ((tile / p.tiles_x) % p.tiles_y) * WH, n = tile / (p.tiles_x * p.tiles_y);
         __syncthreads();
-        for (int i = tid; i < XH * WXS; i += 256) {
-            const int px = i % WXS, py = i / WXS;
+        if constexpr (CIN % 4 == 0) if (view_vec4(p.xin)) {
+            // many channels: 128-bit loads (8 in flight per thread), scattered to the channel planes (4-byte async copies of
+            // 32 channels per pixel were slower: 1.58 vs 1.09 ms for the U-Net 32->12 wgrad)
+            for (int i = tid; i < XH * WXS; i += 256) {
+                const int px = i % WXS, py = i / WXS;
+                int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+                if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.xin.H, p.pad_mode); sxx = mirror_idx(sxx, p.xin.W, p.pad_mode); }
+                const bool in = px < WW + K - 1 && sy >= 0 && sy < p.xin.H && sxx >= 0 && sxx < p.xin.W;
+                float4 v[CIN / 4 > 0 ? CIN / 4 : 1];
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4)
+                    v[c4] = in ? __ldg(reinterpret_cast<const float4*>(x + view_addr(p.xin, n, sy, sxx, c4 * 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    float* d = sx + (c4 * 4) * XPL + py * WXS + px;
+                    d[0] = v[c4].x; d[XPL] = v[c4].y; d[2 * XPL] = v[c4].z; d[3 * XPL] = v[c4].w;
+                }
+            }
+        }
+        if (!(CIN % 4 == 0 && view_vec4(p.xin)))
+        for (int i = tid; i < XH * WXS * CIN; i += 256) {        // lanes = channels: coalesced reads of the NHWC rows
+            const int c = i % CIN, px = (i / CIN) % WXS, py = i / (CIN * WXS);
             int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
             if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.xin.H, p.pad_mode); sxx = mirror_idx(sxx, p.xin.W, p.pad_mode); }
             const bool in = px < WW + K - 1 && sy >= 0 && sy < p.xin.H && sxx >= 0 && sxx < p.xin.W;
-            if (CIN % 4 == 0 && view_vec4(p.xin)) {
-#pragma unroll
-                for (int c4 = 0; c4 < CIN / 4; ++c4) {
-                    const float4 v = in ? __ldg(reinterpret_cast<const float4*>(x + view_addr(p.xin, n, sy, sxx, c4 * 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sx[((c4 * 4) * XH + py) * WXS + px] = v.x; sx[((c4 * 4 + 1) * XH + py) * WXS + px] = v.y;
-                    sx[((c4 * 4 + 2) * XH + py) * WXS + px] = v.z; sx[((c4 * 4 + 3) * XH + py) * WXS + px] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < CIN; ++c) sx[(c * XH + py) * WXS + px] = in ? __ldg(x + view_addr(p.xin, n, sy, sxx, c)) : 0.f;
-            }
+            cp_async4_zfill(sx + c * XPL + py * WXS + px, in ? x + view_addr(p.xin, n, sy, sxx, c) : x, in);
         }
+        constexpr int CO4 = COUT / 4 > 0 ? COUT / 4 : 1;
         if (COUT % 4 == 0 && view_vec4(p.dyv)) {
-            for (int i = tid; i < WH * WW * (COUT / 4); i += 256) {
-                const int c4 = i % (COUT / 4), px = (i / (COUT / 4)) % WW, py = i / ((COUT / 4) * WW);
+            for (int i = tid; i < WH * WW * CO4; i += 256) {
+                const int c4 = i % CO4, px = (i / CO4) % WW, py = i / (CO4 * WW);
                 const int oy = ty0 + py, ox = tx0 + px;
-                reinterpret_cast<float4*>(sd)[i] = (oy < p.dyv.H && ox < p.dyv.W) ? __ldg(reinterpret_cast<const float4*>(dy + view_addr(p.dyv, n, oy, ox, c4 * 4)))
-                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool in = oy < p.dyv.H && ox < p.dyv.W;
+                cp_async16_zfill(sd + 4 * i, in ? dy + view_addr(p.dyv, n, oy, ox, c4 * 4) : dy, in);
             }
         } else {
             for (int i = tid; i < WH * WW * COUT; i += 256) {
                 const int c = i % COUT, px = (i / COUT) % WW, py = i / (COUT * WW);
                 const int oy = ty0 + py, ox = tx0 + px;
-                sd[i] = (oy < p.dyv.H && ox < p.dyv.W) ? __ldg(dy + view_addr(p.dyv, n, oy, ox, c)) : 0.f;
+                const bool in = oy < p.dyv.H && ox < p.dyv.W;
+                cp_async4_zfill(sd + i, in ? dy + view_addr(p.dyv, n, oy, ox, c) : dy, in);
             }
         }
+        cp_async_wait();
         __syncthreads();
         if (!active) continue;
 #pragma unroll 1
         for (int yy = s; yy < WH; yy += S) {
-            const float* xr = sx + (ci * XH + yy + a) * WXS;
+            const float* xr = sx + ci * XPL + (yy + a) * WXS;
             const float* dr = sd + (yy * WW) * COUT + cog * COG;
 #pragma unroll 2
             for (int xq = 0; xq < WW; xq += 4) {
@@ -350,7 +374,7 @@ int launch_manyin(const DirectParams& p, const float* x, const float* wr, const 
 
 template <int CIN, int COUT, int K, int COG>
 int launch_wgrad(DirectWgradParams p, const float* x, const float* dy, float* dw, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (CIN * (WH + K - 1) * WXS + WH * WW * COUT);
+    const size_t smem = sizeof(float) * (CIN * ((WH + K - 1) * WXS + 4) + WH * WW * COUT);
     NI_CUDA(cudaFuncSetAttribute(conv_direct_wgrad_kernel<CIN, COUT, K, COG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.tiles_x = (p.dyv.W + WW - 1) / WW; p.tiles_y = (p.dyv.H + WH - 1) / WH; p.tiles_total = p.tiles_x * p.tiles_y * p.n;
     int per_sm = (int)((200u << 10) / (smem + 1024));

@@ -396,10 +396,14 @@ __global__ void pad_fold_kernel(const float* __restrict__ dpad, float* __restric
 // m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= lr_t * m / (sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) (host-computed).
 // gscale multiplies the gradient first (1/world_size after the sum all-reduce). Non-finite gradients raise *flag and
 // leave the parameter untouched (the reference raises on NaN gradients, workflows/manipulation_classification.py:281).
+// lr_dev != nullptr: the bias-corrected step size is read from device memory (CUDA-graph replays: the host refreshes it through
+// a captured pinned-memory copy instead of a baked-in kernel argument).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr_t, float b1, float b2, float eps, float gscale, int* __restrict__ flag) {
+                            long long n, float lr_t, const float* __restrict__ lr_dev, float b1, float b2, float eps, float gscale,
+                            int* __restrict__ flag) {
     const long long i = (long long)blockIdx.x * kT + threadIdx.x;
     if (i >= n) return;
+    if (lr_dev) lr_t = __ldg(lr_dev);
     const float gi = g[i] * gscale;
     if (!isfinite(gi)) { if (flag) atomicOr(flag, 1); return; }
     const float mi = m[i] + (gi - m[i]) * (1.f - b1);
@@ -574,7 +578,17 @@ extern "C" int ni_adam_keras(float* p, const float* g, float* m, float* v, long 
     NI_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "ni_adam_keras: invalid arguments");
     if (n == 0) return NI_OK;
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
-    adam_kernel<<<grid_for(n), kT, 0, st>>>(p, g, m, v, n, (float)lr_t, beta1, beta2, eps, gscale, nonfinite_flag);
+    adam_kernel<<<grid_for(n), kT, 0, st>>>(p, g, m, v, n, (float)lr_t, nullptr, beta1, beta2, eps, gscale, nonfinite_flag);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// Same update with the bias-corrected step size lr * sqrt(1 - beta2^t) / (1 - beta1^t) supplied in device memory.
+extern "C" int ni_adam_keras_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr_t_dev, float beta1,
+                                 float beta2, float eps, float gscale, int* nonfinite_flag, cudaStream_t st) {
+    NI_REQUIRE(p && g && m && v && lr_t_dev && n >= 0, "ni_adam_keras_dev: invalid arguments");
+    if (n == 0) return NI_OK;
+    adam_kernel<<<grid_for(n), kT, 0, st>>>(p, g, m, v, n, 0.f, lr_t_dev, beta1, beta2, eps, gscale, nonfinite_flag);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }

@@ -230,9 +230,17 @@ class AdamKeras:
         self._state = {}
         self._flag = None
 
-    def apply(self, stores, gscale=1.0, check_finite=True):
+    def step_size(self, iterations=None):
+        """Bias-corrected step size of iteration t (Keras: lr * sqrt(1 - beta2^t) / (1 - beta1^t))."""
+        t = self.iterations if iterations is None else iterations
+        return self.lr * np.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+
+    def apply(self, stores, gscale=1.0, check_finite=True, lr_t_dev=None):
+        """One update of every flat buffer. lr_t_dev: device scalar holding step_size() (CUDA-graph capture; the caller
+        advances `iterations` and refreshes the scalar before each replay), else the step size is a kernel argument."""
         L = _lib.lib()
-        self.iterations += 1
+        if lr_t_dev is None:
+            self.iterations += 1
         if self._flag is None:
             self._flag = zeros((1,), torch.int32)
         for s in stores:
@@ -240,8 +248,12 @@ class AdamKeras:
             if key not in self._state:
                 self._state[key] = (torch.zeros_like(s.flat), torch.zeros_like(s.flat))
             m, v = self._state[key]
-            L.ni_adam_keras(ptr(s.flat), ptr(s.gflat), ptr(m), ptr(v), s.flat.numel(), self.lr, self.beta1, self.beta2, self.eps,
-                            self.iterations, gscale, ptr(self._flag), stream())
+            if lr_t_dev is None:
+                L.ni_adam_keras(ptr(s.flat), ptr(s.gflat), ptr(m), ptr(v), s.flat.numel(), self.lr, self.beta1, self.beta2, self.eps,
+                                self.iterations, gscale, ptr(self._flag), stream())
+            else:
+                L.ni_adam_keras_dev(ptr(s.flat), ptr(s.gflat), ptr(m), ptr(v), s.flat.numel(), ptr(lr_t_dev), self.beta1, self.beta2,
+                                    self.eps, gscale, ptr(self._flag), stream())
         return self._flag
 
     def nonfinite(self):

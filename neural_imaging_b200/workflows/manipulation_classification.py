@@ -103,6 +103,8 @@ class ManipulationClassification(object):
         self._optimizer = nn.AdamKeras()
         self._ws = Workspace()
         self._labels = {}
+        self._use_graph = False
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------ properties
     @property
@@ -220,22 +222,102 @@ class ManipulationClassification(object):
             raise RuntimeError('∇ NaNs: non-finite gradients detected by the fused Adam kernel')
         return loss, parts
 
+    def enable_cuda_graph(self, enabled=True):
+        """Replay the step as two captured CUDA graphs (forward + backward | Adam + loss scalars) instead of ~1100 separate
+        launches. Used when the step is static: augment=False and a fixed codec quality; the first call of a given
+        (shapes, lambdas) combination runs eagerly (it sizes the workspaces), the second captures, later calls replay."""
+        self._use_graph = bool(enabled)
+        if not enabled:
+            self._graphs.clear()
+
     def training_step_device(self, batch_x, batch_y, lambda_nip=0, lambda_dcn=0, augment=False, learning_rate=1e-4,
                              grad_sync=None):
         """The step without the host-side NaN check (no device->host sync). grad_sync(stores) is called between
         backward and Adam (data-parallel all-reduce hook)."""
-        L, ws, s = _lib.lib(), self._ws, stream()
+        world = getattr(grad_sync, 'world', 1)
+        if self._use_graph and self._graphable(augment):
+            return self._graph_step(batch_x, batch_y, lambda_nip, lambda_dcn, learning_rate, grad_sync)
         x = as_device(batch_x)
         if x.dim() == 3:
             x = x.unsqueeze(0)
-        t = as_device(batch_y)
+        ctx = self._forward_backward(x, as_device(batch_y), lambda_nip, lambda_dcn, augment, world)
+        if grad_sync is not None:
+            grad_sync(self._stores)
+        self._optimizer.lr = float(learning_rate)
+        return self._update(ctx, getattr(grad_sync, 'gscale', 1.0))
+
+    # ------------------------------------------------------------------------------------------------ CUDA-graph replay
+    def _graphable(self, augment):
+        if augment:
+            return False            # manipulation strengths are drawn on the host every step
+        if self._distribution['compression'] == 'jpeg' and not jpeg.is_number(self.codec.quality):
+            return False            # random codec quality per step
+        return True
+
+    def _graph_step(self, batch_x, batch_y, lambda_nip, lambda_dcn, learning_rate, grad_sync):
+        xin = batch_x if isinstance(batch_x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(batch_x, dtype=np.float32))
+        tin = batch_y if isinstance(batch_y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(batch_y, dtype=np.float32))
+        if xin.dim() == 3:
+            xin = xin.unsqueeze(0)
+        world = getattr(grad_sync, 'world', 1)
+        gscale = getattr(grad_sync, 'gscale', 1.0)
+        key = (tuple(xin.shape), tuple(tin.shape), float(lambda_nip), float(lambda_dcn), world, float(gscale))
+        st = self._graphs.get(key)
+        if st is None:              # first sight of this configuration: eager step (allocates workspaces / scratch / Adam state)
+            self._graphs[key] = 'warm'
+            ctx = self._forward_backward(as_device(xin), as_device(tin), lambda_nip, lambda_dcn, False, world)
+            if grad_sync is not None:
+                grad_sync(self._stores)
+            self._optimizer.lr = float(learning_rate)
+            return self._update(ctx, gscale)
+        if st == 'warm':
+            st = self._capture(xin.shape, tin.shape, lambda_nip, lambda_dcn, world, gscale)
+            self._graphs[key] = st
+        st['x'].copy_(xin, non_blocking=True)
+        st['t'].copy_(tin, non_blocking=True)
+        opt = self._optimizer
+        opt.lr = float(learning_rate)
+        opt.iterations += 1
+        st['lr_host'][0] = float(opt.step_size())
+        st['fwd_bwd'].replay()
+        if grad_sync is not None:
+            grad_sync(self._stores)
+        st['update'].replay()
+        loss, parts = st['out']
+        return wrap(loss.clone()), {k: (wrap(v.clone()) if isinstance(v, torch.Tensor) else v) for k, v in parts.items()}
+
+    def _capture(self, x_shape, t_shape, lambda_nip, lambda_dcn, world, gscale):
+        L = _lib.lib()
+        st = {'x': empty(tuple(x_shape)), 't': empty(tuple(t_shape)), 'lr_dev': zeros((1,)),
+              'lr_host': torch.zeros(1, dtype=torch.float32).pin_memory()}
+        torch.cuda.synchronize()
+        n0 = int(L.ni_launch_count())
+        st['fwd_bwd'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st['fwd_bwd'], capture_error_mode='thread_local'):
+            ctx = self._forward_backward(st['x'], st['t'], lambda_nip, lambda_dcn, False, world)
+        st['update'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st['update'], pool=st['fwd_bwd'].pool(), capture_error_mode='thread_local'):
+            st['lr_dev'].copy_(st['lr_host'], non_blocking=True)     # pinned -> device copy node: re-read at every replay
+            st['out'] = self._update(ctx, gscale, lr_t_dev=st['lr_dev'])
+        st['launches'] = int(L.ni_launch_count()) - n0
+        st['ctx'] = ctx
+        return st
+
+    @property
+    def graph_launches_per_step(self):
+        """Kernels of this library inside one replay of the captured step (0 when nothing has been captured)."""
+        return max([g['launches'] for g in self._graphs.values() if isinstance(g, dict)] or [0])
+
+    # ------------------------------------------------------------------------------------------------ the step proper
+    def _forward_backward(self, x, t, lambda_nip, lambda_dcn, augment, world):
+        """Forward + backward of the joint graph; leaves the gradients in the flat buffers of self._stores."""
+        L, ws, s = _lib.lib(), self._ws, stream()
         B = int(x.shape[0])
         train_nip = 'nip' in self._trainable and bool(self.nip._store.trainable)
         train_dcn = 'dcn' in self._trainable
         comp = self._distribution['compression']
         # sum-type loss terms (the codec's l2_loss and its global-histogram entropy) are scaled by the world size so that the
         # 1/world average applied to the all-reduced gradients leaves them as the reference's single-process sums
-        world = getattr(grad_sync, 'world', 1)
         lam_dcn = float(lambda_dcn) * world if train_dcn else 0.0
 
         # ---- forward
@@ -246,6 +328,7 @@ class ManipulationClassification(object):
         self._manipulate(Y, strengths, m, training=train_nip)
         c = self._downsample(m, out=ws.get('c', (M, -(-Y.shape[1] // self.downsampling_factor), -(-Y.shape[2] // self.downsampling_factor), 3))
                              if self._distribution['downsampling'].startswith('pool') else None)
+        entropy = acc_dcn = None
         if comp == 'jpeg':
             C = ws.get('C', c.shape)
             quality = self.codec._draw_quality(None)
@@ -291,18 +374,20 @@ class ManipulationClassification(object):
                 if op.has_grad:
                     op.backward(Y, dm[(i + 1) * B:(i + 2) * B], dY, strengths[name])
             self.nip._backward(dY)
-        if grad_sync is not None:
-            grad_sync(self._stores)
-        self._optimizer.lr = float(learning_rate)
-        self._optimizer.apply(self._stores, gscale=getattr(grad_sync, 'gscale', 1.0))
+        return {'M': M, 'Y_numel': Y.numel(), 'loss_ce': loss_ce, 'acc': acc, 'acc_dcn': acc_dcn, 'entropy': entropy,
+                'comp': comp, 'train_dcn': train_dcn, 'lambda_nip': float(lambda_nip), 'lambda_dcn': float(lambda_dcn)}
 
-        loss_ce_v = loss_ce / float(M)
-        loss_nip_v = acc / float(Y.numel())
-        loss = loss_ce_v + (float(lambda_nip) * loss_nip_v if 'nip' in self._trainable else 0.0)
+    def _update(self, ctx, gscale=1.0, lr_t_dev=None):
+        """Fused Adam over the flat buffers + the step's loss scalars (device tensors)."""
+        self._optimizer.apply(self._stores, gscale=gscale, lr_t_dev=lr_t_dev)
+        comp = ctx['comp']
+        loss_ce_v = ctx['loss_ce'] / float(ctx['M'])
+        loss_nip_v = ctx['acc'] / float(ctx['Y_numel'])
+        loss = loss_ce_v + (ctx['lambda_nip'] * loss_nip_v if 'nip' in self._trainable else 0.0)
         if comp == 'dcn':
-            loss_dcn = acc_dcn / (2.0 * 255.0 * 255.0) + float(self.codec._h.entropy_weight) * entropy
-            if train_dcn:
-                loss = loss + float(lambda_dcn) * loss_dcn
+            loss_dcn = ctx['acc_dcn'] / (2.0 * 255.0 * 255.0) + float(self.codec._h.entropy_weight) * ctx['entropy']
+            if ctx['train_dcn']:
+                loss = loss + ctx['lambda_dcn'] * loss_dcn
             loss_dcn = wrap(loss_dcn.reshape(()))
         else:
             loss_dcn = float('nan') if comp == 'jpeg' else 0.0    # Keras MSE with sample_weight = NaN entropy (SURVEY a12)
