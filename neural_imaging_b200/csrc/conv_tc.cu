@@ -106,6 +106,17 @@ int encode_act_map(CUtensorMap* tm, const float* base, int n, int h, int w, int 
     return encode_map(tm, base, 4, dims, str, box);
 }
 
+// Logical (n, h, w, 4F) view of a physical (n, 2h, 2w, F [pitch]) buffer through TensorFlow's block-major depth_to_space(2):
+// logical channel blk * F + f of pixel (y, x) = physical channel f of pixel (2y + blk / 2, 2x + blk % 2). 5-D map
+// (F, dx:2, w, dy:2, h*n) with box (32, 1, bw, 1, bh*bn); rows of consecutive images are contiguous in the merged last
+// dimension, which is all a 1x1 filter needs (no halo, no zero fill).
+int encode_block2_map(CUtensorMap* tm, const float* base, int n, int h, int w, int f, int pitch, int bw, int bh, int bn) {
+    cuuint64_t dims[5] = {(cuuint64_t)f, 2, (cuuint64_t)w, 2, (cuuint64_t)h * n};
+    cuuint64_t str[4] = {(cuuint64_t)pitch * 4, (cuuint64_t)2 * pitch * 4, (cuuint64_t)2 * w * pitch * 4, (cuuint64_t)4 * w * pitch * 4};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, 1, (cuuint32_t)(bh * bn)};
+    return encode_map(tm, base, 5, dims, str, box);
+}
+
 // gemm tiles: 16 x 8 pixels where the image allows it (smallest halo), else the row-major rule of pick_tile
 bool pick_tile(int h, int w, int pixels, int& bw, int& bh, int& bn);
 bool pick_tile_gemm(int h, int w, int& bw, int& bh, int& bn) {
@@ -160,6 +171,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     const int spitch = dgrad ? d->out_pitch : d->in_pitch, scoff = dgrad ? d->out_coff : d->in_coff;
     const int dpitch = dgrad ? d->in_pitch : d->out_pitch, dcoff = dgrad ? d->in_coff : d->out_coff;
     const int dmode = dgrad ? d->in_mode : d->out_mode;
+    const int smode = dgrad ? d->out_mode : d->in_mode;
     const int taps = d->kh * d->kw;
     tcv2::GemmParams p;
     if (!gemm_geometry(th, tw, d->kh, d->kw, p.bw, p.bh, p.bn, p.hw, p.hh, p.a_stage)) {
@@ -176,7 +188,9 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1, bnt);
     NI_LAUNCH_CHECK();
     CUtensorMap tmA;
-    rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.hw, p.hh, p.bn);
+    p.src_block2_f = smode == NI_MODE_BLOCK2 ? K / 4 : 0;
+    if (p.src_block2_f > 0) rc = encode_block2_map(&tmA, src + scoff, d->n, sh, sw, K / 4, spitch, p.hw, p.hh, p.bn);
+    else rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.hw, p.hh, p.bn);
     if (rc) return rc;
     p.n = d->n; p.oh = th; p.ow = tw;
     p.tiles_w = tw / p.bw; p.tiles_h = th / p.bh;
@@ -291,11 +305,13 @@ extern "C" int ni_conv2d_tc_supported(const ni_conv_desc* d, int op) {
         return gemm_geometry(d->oh, d->ow, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
     if (op == 1) {
-        if (d->out_mode != NI_MODE_PLAIN) return 0;                    // dy is the TMA source
+        // dy is the TMA source: depth_to_space addressing only for 1x1 filters (the transposed convolutions) on whole 32-channel chunks
+        if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && getenv("NI_TC_NO_BLOCK2") == nullptr)) return 0;
         if (d->in_mode == NI_MODE_BLOCK2 && ((d->cin / 4) % 32)) return 0;
         return gemm_geometry(d->h, d->w, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
-    if (d->in_mode != NI_MODE_PLAIN || d->out_mode != NI_MODE_PLAIN) return 0;
+    if (d->in_mode != NI_MODE_PLAIN) return 0;
+    if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && getenv("NI_TC_NO_BLOCK2") == nullptr)) return 0;
     if (!pick_tile(d->oh, d->ow, 32, bw, bh, bn)) return 0;
     return (d->n % bn) == 0 ? 1 : 0;
 }
@@ -323,7 +339,9 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     CUtensorMap tmX, tmDY;
     int rc = encode_act_map(&tmX, x + d->in_coff, d->n, d->h, d->w, d->cin, d->in_pitch, p.bw, p.bh, p.bn);
     if (rc) return rc;
-    rc = encode_act_map(&tmDY, dy + d->out_coff, d->n, d->oh, d->ow, d->cout, d->out_pitch, p.bw, p.bh, p.bn);
+    p.dy_block2_f = d->out_mode == NI_MODE_BLOCK2 ? d->cout / 4 : 0;
+    if (p.dy_block2_f > 0) rc = encode_block2_map(&tmDY, dy + d->out_coff, d->n, d->oh, d->ow, d->cout / 4, d->out_pitch, p.bw, p.bh, p.bn);
+    else rc = encode_act_map(&tmDY, dy + d->out_coff, d->n, d->oh, d->ow, d->cout, d->out_pitch, p.bw, p.bh, p.bn);
     if (rc) return rc;
     p.n = d->n; p.oh = d->oh; p.ow = d->ow;
     p.tiles_w = d->ow / p.bw; p.tiles_h = d->oh / p.bh;
@@ -334,7 +352,8 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     const int bnt = pick_bnt(d->cout);
     const int mtiles = (p.atoms + 3) / 4, ntiles = d->cout / bnt;
     // split-K over pixel ranges. Cost model (us): waves x steps per CTA x t_iter + per-wave fixed cost + the cross-CTA reduction
-    // (every split adds mtot x cout floats through L2 reductions, ~25 floats/ns measured order of magnitude). The old rule (always
+    // (every split adds mtot x cout floats through L2 reductions). t_iter = 1.5 us: the loop is bound by L2 -> SM operand traffic
+    // (16 KB of A + BNT x 128 B of B per 32 pixels ~ 3.5 TB/s over 148 SMs), measured 1.4 - 1.8 us for every tile width. The old rule (always
     // ~4 waves) made the 1x1 transposed-conv layers reduction-bound: 592 CTAs x 16 K atomics for 28 iterations of work each.
     // Chains are capped at 2048 steps (65 K pixels) to bound the truncation bias of the in-TMEM accumulation.
     const int tiles = mtiles * ntiles, sms = ni_num_sms() * (bnt == 128 ? 1 : 2);   // resident CTAs (BNT <= 64: two per SM)
@@ -348,7 +367,7 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
         const int per = (p.steps_total + sp - 1) / sp;
         const int eff = (p.steps_total + per - 1) / per;
         const int waves = (tiles * eff + sms - 1) / sms;
-        const double cost = waves * (per * 0.25 + 6.0) + (double)eff * p.mtot * d->cout / 25e3;
+        const double cost = waves * (per * 1.5 + 6.0) + (double)eff * p.mtot * d->cout / 50e3;
         if (cost < best) { best = cost; splits = eff; }
     }
     p.steps_per_split = (p.steps_total + splits - 1) / splits;

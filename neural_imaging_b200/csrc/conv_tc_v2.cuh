@@ -37,6 +37,8 @@ struct GemmParams {
     float alpha;
     const float* bias;
     float* out;
+    int src_block2_f;              // > 0: the source is read through depth_to_space(2) of an (n, 2h, 2w, F) buffer (5-D tensor map
+                                   // (F, 2, w, 2, h*n); only for 1x1 filters = the transposed convolutions), F = src_block2_f
 };
 
 __device__ __forceinline__ float act_apply(float v, int act, float alpha) {
@@ -261,6 +263,7 @@ struct WgradParams {
     int cin_chunks, atoms, mtot, cout;
     int steps_total, steps_per_split;
     float* dw;
+    int dy_block2_f;               // > 0: dy is read through depth_to_space(2) (5-D map, see GemmParams::src_block2_f)
 };
 
 __device__ __forceinline__ void transpose_split_chunk(const uint8_t* raw, uint8_t* hi, uint8_t* lo, int row0, int r) {
@@ -332,7 +335,15 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     const int a = tap / p.kw, b = tap - a * p.kw;
                     tma_load_4d(raw_a(s) + j * 4096, &tmX, &bar_full[s], cc * 32, x0 + b - p.pad_l, y0 + a - p.pad_t, n0);
                 }
-                for (int j = 0; j < BNT / 32; ++j) tma_load_4d(raw_b(s) + j * 4096, &tmDY, &bar_full[s], co0 + j * 32, x0, y0, n0);
+                for (int j = 0; j < BNT / 32; ++j) {
+                    const int co = co0 + j * 32;
+                    if (p.dy_block2_f > 0) {
+                        const int blk = co / p.dy_block2_f, f0 = co - blk * p.dy_block2_f;
+                        tma_load_5d(raw_b(s) + j * 4096, &tmDY, &bar_full[s], f0, blk & 1, x0, blk >> 1, n0 * p.oh + y0);
+                    } else {
+                        tma_load_4d(raw_b(s) + j * 4096, &tmDY, &bar_full[s], co, x0, y0, n0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {

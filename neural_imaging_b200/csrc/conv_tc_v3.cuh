@@ -116,7 +116,12 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     mbar_wait(&bar_afree[s], ph ^ 1, 0);
                     TCP_ADD(12);
                     mbar_expect_tx(&bar_afull[s], bytes);
-                    tma_load_4d(a_halo(s), &tmA, &bar_afull[s], kc * 32, bx, by, n0);
+                    if (p.src_block2_f > 0) {          // 1x1 filter: halo == tile; channel chunk kc*32 lives in sub-pixel blk of the 2x2 block
+                        const int co = kc * 32, blk = co / p.src_block2_f, f0 = co - blk * p.src_block2_f;
+                        tma_load_5d(a_halo(s), &tmA, &bar_afull[s], f0, blk & 1, bx, blk >> 1, n0 * p.oh + by);
+                    } else {
+                        tma_load_4d(a_halo(s), &tmA, &bar_afull[s], kc * 32, bx, by, n0);
+                    }
                 }
             }
         }
