@@ -68,7 +68,8 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         bar_accfull[NSETS], bar_accfree[NSETS];
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // lane-0 broadcasts: tell the compiler that the warp index and the TMEM base are warp-uniform (uniform registers, no waterfalls)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int taps = p.kh * p.kw;
     const int iters = taps * p.kchunks;
     const int ntiles_n = p.ntot / BNT;
@@ -87,7 +88,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t a_base = tmem + acc_cols;
 
     auto a_halo = [&](int s) { return smem + s * p.a_stage; };
@@ -145,7 +146,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         }
     } else if (warp == 1 || warp == 3) {
         const int iss = warp == 1 ? 0 : 1;
-        if (lane == 0 && iss < n_iss) {   // ---- MMA issuer(s)
+        if (iss < n_iss) {   // ---- MMA issuer(s): the whole warp walks the loop (uniform control flow), one elected lane issues
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
             int gbase = 0, tcount = 0;
             TCP_DECL
@@ -176,19 +177,24 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                         d1 = dbase + (uint32_t)(it % p.nacc) * BNT; d2 = dbase + (uint32_t)p.nacc * BNT;
                         first1 = it < p.nacc ? 1u : 0u; first2 = it == 0 ? 1u : 0u;
                     }
+                    const uint64_t dbh0 = make_smem_desc_sw128(bh, 16, 1024), dbl0 = make_smem_desc_sw128(bl, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t dbh = make_smem_desc_sw128(bh + ks * 32, 16, 1024), dbl = make_smem_desc_sw128(bl + ks * 32, 16, 1024);
-                        umma_tf32_ts(d2, alo + ks * 8, dbh, idesc, (first2 && ks == 0) ? 0u : 1u);
-                        umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
-                        umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (first1 && ks == 0) ? 0u : 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t dbh = dbh0 + (uint64_t)(ks * 2), dbl = dbl0 + (uint64_t)(ks * 2);   // +32 bytes (start address is in 16-byte units)
+                            umma_tf32_ts(d2, alo + ks * 8, dbh, idesc, (first2 && ks == 0) ? 0u : 1u);
+                            umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
+                            umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (first1 && ks == 0) ? 0u : 1u);
+                        }
+                        TCP_ADD(17);
+                        umma_commit(&bar_bfree[s]);
+                        umma_commit(&bar_tfree[t]);
+                        TCP_ADD(4);
                     }
-                    TCP_ADD(17);
-                    umma_commit(&bar_bfree[s]);
-                    umma_commit(&bar_tfree[t]);
-                    TCP_ADD(4);
+                    __syncwarp();
                 }
-                umma_commit(&bar_accfull[aset]);
+                if (elect_one()) umma_commit(&bar_accfull[aset]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 4 + kNCW) {

@@ -124,7 +124,27 @@ act_bwd_bias_vec_kernel(const float* __restrict__ y, float* __restrict__ dy, flo
     const bool need_act = act != NI_ACT_NONE && act != NI_ACT_CLIP01;
     for (int c4 = blockIdx.x * nx + tx; c4 * 4 < c; c4 += gridDim.x * nx) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long p = p0 + ty; p < p1; p += ny) {
+        // four pixels per trip with all eight loads issued before the first store: the in-place update otherwise serialises one
+        // memory round trip per pixel (the stores may alias the next loads as far as the compiler knows)
+        long long p = p0 + ty;
+        for (; p + 3LL * ny < p1; p += 4LL * ny) {
+            float4 g[4], yv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = *reinterpret_cast<const float4*>(dy + (p + (long long)u * ny) * dp + dof + c4 * 4);
+            if (need_act) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) yv[u] = __ldg(reinterpret_cast<const float4*>(y + (p + (long long)u * ny) * yp + yo + c4 * 4));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u].x *= act_grad_from_out(yv[u].x, act, alpha); g[u].y *= act_grad_from_out(yv[u].y, act, alpha);
+                    g[u].z *= act_grad_from_out(yv[u].z, act, alpha); g[u].w *= act_grad_from_out(yv[u].w, act, alpha);
+                    *reinterpret_cast<float4*>(dy + (p + (long long)u * ny) * dp + dof + c4 * 4) = g[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s.x += g[u].x; s.y += g[u].y; s.z += g[u].z; s.w += g[u].w; }
+        }
+        for (; p < p1; p += ny) {
             float4* gp = reinterpret_cast<float4*>(dy + p * dp + dof + c4 * 4);
             float4 g = *gp;
             if (need_act) {

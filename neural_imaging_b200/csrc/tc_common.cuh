@@ -79,6 +79,16 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// One elected lane of a CONVERGED warp. Running the surrounding loop on the whole warp and electing only around the tcgen05.mma
+// / commit instructions keeps the loop's control flow and address arithmetic warp-uniform, so ptxas feeds UTCHMMA from uniform
+// registers directly; under `if (lane == 0)` every operand went through an ELECT + 4 x R2UR.BROADCAST + BRA.U.ANY waterfall
+// (~12 instructions, ~74 cycles per MMA measured with clock64).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMEM
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared memory).
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
