@@ -293,7 +293,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     __shared__ uint64_t bar_full[kWgStages], bar_aready[kWgStages], bar_bready[kWgStages], bar_free[kWgStages], bar_accum;
     __shared__ uint32_t tmem_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int atom0 = blockIdx.x * 4;
     const int valid_atoms = min(4, p.atoms - atom0);
     const int co0 = blockIdx.y * BNT;
@@ -313,7 +313,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t a_base = tmem + 2 * BNT;
 
     auto raw_a = [&](int s) { return smem + s * STAGE_BYTES; };
@@ -347,7 +347,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // ---- MMA issuer: the whole warp walks the loop (uniform operands), one elected lane issues (see tc::elect_one)
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kWgStages, ph = (it / kWgStages) & 1;
@@ -356,17 +356,22 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 tcgen05_fence_after();
                 const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
                 const uint32_t ahi = a_base + s * 64, alo = ahi + 32;
+                const uint64_t dbh0 = make_smem_desc_sw128(bh, 16, 1024), dbl0 = make_smem_desc_sw128(bl, 16, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t dbh = make_smem_desc_sw128(bh + ks * 32, 16, 1024), dbl = make_smem_desc_sw128(bl + ks * 32, 16, 1024);
-                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-                    umma_tf32_ts(tmem + BNT, alo + ks * 8, dbh, idesc, acc);
-                    umma_tf32_ts(tmem + BNT, ahi + ks * 8, dbl, idesc, 1u);
-                    umma_tf32_ts(tmem, ahi + ks * 8, dbh, idesc, acc);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dbh = dbh0 + (uint64_t)(ks * 2), dbl = dbl0 + (uint64_t)(ks * 2);
+                        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                        umma_tf32_ts(tmem + BNT, alo + ks * 8, dbh, idesc, acc);
+                        umma_tf32_ts(tmem + BNT, ahi + ks * 8, dbl, idesc, 1u);
+                        umma_tf32_ts(tmem, ahi + ks * 8, dbh, idesc, acc);
+                    }
+                    umma_commit(&bar_free[s]);
                 }
-                umma_commit(&bar_free[s]);
+                __syncwarp();
             }
-            umma_commit(&bar_accum);
+            if (elect_one()) umma_commit(&bar_accum);
+            __syncwarp();
         }
     } else if (warp < 6) {
         // ---- A converters: warp q <-> atom q (rows 32q .. 32q+31 of the M tile), lane = channel
