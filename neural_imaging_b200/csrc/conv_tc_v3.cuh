@@ -202,6 +202,8 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         const int qd = warp & 3, row = qd * 32 + lane, half = (warp - 4) >> 2;
         const int prow0 = ((row / (p.bw * p.bh)) * p.hh + (row / p.bw) % p.bh) * p.hw + row % p.bw;
         int git = 0, gkc = 0;
+        int pending = -1;            // slot whose tcgen05.st is in flight: its completion wait + "ready" arrive are deferred until
+                                     // the next iteration's shared-memory loads and hi/lo split are done (hides ~200 cycles)
 #ifdef NI_TC_PROFILE
         long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 128;
 #endif
@@ -212,10 +214,11 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 mbar_wait(&bar_afull[s], ph, 3);
                 TCP_ADD(6);
                 const uint8_t* stage = a_halo(s);
+                int ta = 0, tb = 0;
                 for (int tap = 0; tap < taps; ++tap, ++git) {
                     const int t = git % SLOTS, pt = (git / SLOTS) & 1;
-                    const int ta = tap / p.kw, tb = tap - ta * p.kw;
                     const int prow = prow0 + (p.off_sign > 0 ? ta : p.kh - 1 - ta) * p.hw + (p.off_sign > 0 ? tb : p.kw - 1 - tb);
+                    if (++tb == p.kw) { tb = 0; ++ta; }
                     float hi[16], lo[16];
                     const uint8_t* rp = stage + prow * 128;
 #pragma unroll
@@ -231,18 +234,26 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     }
                     if (tap == taps - 1) mbar_arrive(&bar_afree[s]);      // last tap is in registers: stage back to the producer
                     TCP_ADD(7);
+                    if (pending >= 0) {
+                        tmem_st_wait();
+                        tcgen05_fence_before();
+                        mbar_arrive(&bar_tready[pending]);
+                    }
+                    TCP_ADD(9);
                     mbar_wait(&bar_tfree[t], pt ^ 1, 5);
                     TCP_ADD(8);
                     tcgen05_fence_after();
                     const uint32_t dst = a_base + ((uint32_t)(qd * 32) << 16) + t * 64 + 16 * half;
                     tmem_st_32x16(dst, hi);
                     tmem_st_32x16(dst + 32, lo);
-                    tmem_st_wait();
-                    tcgen05_fence_before();
-                    mbar_arrive(&bar_tready[t]);
-                    TCP_ADD(9);
+                    pending = t;
                 }
             }
+        }
+        if (pending >= 0) {
+            tmem_st_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bar_tready[pending]);
         }
     } else if (warp >= 12) {
         // ---- epilogue: accumulator set -> (+ bias, activation) -> global, while the MMA warp works on the other set
