@@ -266,17 +266,17 @@ struct WgradParams {
     int dy_block2_f;               // > 0: dy is read through depth_to_space(2) (5-D map, see GemmParams::src_block2_f)
 };
 
-__device__ __forceinline__ void transpose_split_chunk(const uint8_t* raw, uint8_t* hi, uint8_t* lo, int row0, int r) {
+__device__ __forceinline__ void transpose_split_chunk(uint32_t raw, uint32_t hi, uint32_t lo, int row0, int r) {
     const int p = r & 31, c4 = r >> 5;
-    const float4 v = *reinterpret_cast<const float4*>(raw + p * 128 + ((c4 ^ (p & 7)) << 4));
+    const float4 v = lds128(raw + (uint32_t)(p * 128 + ((c4 ^ (p & 7)) << 4)));
     const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const int m = row0 + c4 * 4 + e;
-        const int off = (m >> 3) * 1024 + (m & 7) * 128 + (((p >> 2) ^ (m & 7)) << 4) + (p & 3) * 4;
+        const uint32_t off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128 + (((p >> 2) ^ (m & 7)) << 4) + (p & 3) * 4);
         const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xFFFFE000u);
-        *reinterpret_cast<float*>(hi + off) = h;
-        *reinterpret_cast<float*>(lo + off) = vv[e] - h;
+        sts32(hi + off, h);
+        sts32(lo + off, vv[e] - h);
     }
 }
 
@@ -382,11 +382,11 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             mbar_wait(&bar_full[s], ph, 3);
             float hi[32], lo[32];
             if (q < valid_atoms) {
-                const uint8_t* ap = raw_a(s) + q * 4096 + (lane & 3) * 4;
+                const uint32_t ap = smem_u32(raw_a(s)) + (uint32_t)(q * 4096 + (lane & 3) * 4);
 #pragma unroll
                 for (int px = 0; px < 32; ++px) {
                     // element (pixel px, channel lane): 16-byte chunk (lane / 4) XOR (px % 8), word lane % 4
-                    const float v = *reinterpret_cast<const float*>(ap + px * 128 + (((lane >> 2) ^ (px & 7)) << 4));
+                    const float v = lds32(ap + (uint32_t)(px * 128 + (((lane >> 2) ^ (px & 7)) << 4)));
                     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
                     hi[px] = h; lo[px] = v - h;
                 }
@@ -429,7 +429,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const int s = it % kWgStages, ph = (it / kWgStages) & 1;
             mbar_wait(&bar_full[s], ph, 6);
             for (int qq = tid; qq < (BNT / 32) * 256; qq += 128)
-                transpose_split_chunk(raw_b(s) + (qq >> 8) * 4096, b_hi(s), b_lo(s), (qq >> 8) * 32, qq & 255);
+                transpose_split_chunk(smem_u32(raw_b(s)) + (uint32_t)((qq >> 8) * 4096), smem_u32(b_hi(s)), smem_u32(b_lo(s)), (qq >> 8) * 32, qq & 255);
             fence_proxy_async_smem();
             mbar_arrive(&bar_bready[s]);
         }

@@ -213,17 +213,17 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 TCP_START();
                 mbar_wait(&bar_afull[s], ph, 3);
                 TCP_ADD(6);
-                const uint8_t* stage = a_halo(s);
+                const uint32_t stage = smem_u32(a_halo(s));
                 int ta = 0, tb = 0;
                 for (int tap = 0; tap < taps; ++tap, ++git) {
                     const int t = git % SLOTS, pt = (git / SLOTS) & 1;
                     const int prow = prow0 + (p.off_sign > 0 ? ta : p.kh - 1 - ta) * p.hw + (p.off_sign > 0 ? tb : p.kw - 1 - tb);
                     if (++tb == p.kw) { tb = 0; ++ta; }
                     float hi[16], lo[16];
-                    const uint8_t* rp = stage + prow * 128;
+                    const uint32_t rp = stage + (uint32_t)prow * 128u;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float4 v = *reinterpret_cast<const float4*>(rp + (((4 * half + c) ^ (prow & 7)) << 4));
+                        const float4 v = lds128(rp + (uint32_t)(((4 * half + c) ^ (prow & 7)) << 4));
                         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
