@@ -1,0 +1,47 @@
+"""Validation helpers of the manipulation-classification loop on the B200 path (API mirror of reference
+training/validation.py:163-203 `validate_fan`, :82-160 `validate_nip` without the figure rendering).
+
+The reference runs batches of 10 through `flow.run_workflow_to_decisions` and builds the confusion matrix on the host with
+an n_classes^2 Python loop per batch; here the decisions stay one device->host read per batch and the matrix is one
+np.add.at. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does;
+SSIM (skimage) is not available offline and is reported as NaN.
+"""
+import numpy as np
+
+
+def validate_fan(flow, data, get_labels=False):
+    """Confusion matrix of the FAN inside a ManipulationClassification workflow. Returns (accuracy, conf[, labels])."""
+    batch_size = int(np.minimum(10, data.count_validation))
+    n_batches = data.count_validation // batch_size
+    n_classes = flow.n_classes
+    conf = np.zeros((n_classes, n_classes))
+    out_labels, accuracies = [], []
+    for batch in range(n_batches):
+        batch_x = data.next_validation_batch(batch, batch_size)
+        if isinstance(batch_x, tuple):
+            batch_x = batch_x[0]
+        batch_y = flow._batch_labels(len(batch_x))
+        predicted = np.asarray(flow.run_workflow_to_decisions(batch_x))
+        if get_labels:
+            out_labels += [x for x in predicted]
+        np.add.at(conf, (batch_y, predicted), 1)
+        accuracies.append(np.mean(predicted == batch_y))
+    if out_labels:
+        return np.mean(accuracies), conf / (n_batches * batch_size), out_labels
+    return np.mean(accuracies), conf / (n_batches * batch_size)
+
+
+def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type='L2'):
+    """Per-image (ssim, psnr, loss) lists of a NIP on the validation set (no figures; SSIM needs skimage -> NaN)."""
+    if loss_type not in ('L1', 'L2'):
+        raise ValueError('Invalid loss! Use either L1 or L2.')
+    ssims, psnrs, losss = [], [], []
+    for b in range(data.count_validation):
+        example_x, example_y = data.next_validation_batch(b, 1)
+        developed = model.process(example_x).numpy().clip(0, 1).squeeze()
+        reference = np.asarray(example_y).squeeze()
+        mse = float(np.mean(np.power(reference - developed, 2.0)))
+        psnrs.append(float(10.0 * np.log10(1.0 / mse)) if mse > 0 else float('inf'))
+        ssims.append(float('nan'))
+        losss.append(mse if loss_type == 'L2' else float(np.mean(np.abs(reference - developed))))
+    return ssims, psnrs, losss

@@ -193,3 +193,48 @@ def test_cuda_graph_step_matches_eager():
     # weight gradients are summed with atomics (order varies run to run): compare the parameters with a small tolerance
     for a, b in ((out['graph'][1], out['eager'][1]), (out['graph'][2], out['eager'][2])):
         assert np.max(np.abs(a - b)) <= 2e-5 * max(1.0, float(np.max(np.abs(b)))), np.max(np.abs(a - b))
+
+
+class _ToyData:
+    """Stand-in for reference helpers/dataset.py Dataset (RAW + RGB patches), deterministic."""
+    _loaded_data = 'xy'
+
+    def __init__(self, n_train=8, n_valid=4, raw=16, seed=3):
+        rs = np.random.RandomState(seed)
+        self.count_training, self.count_validation = n_train, n_valid
+        self._x = rs.uniform(size=(n_train + n_valid, raw, raw, 4)).astype(np.float32)
+        self._y = rs.uniform(size=(n_train + n_valid, 2 * raw, 2 * raw, 3)).astype(np.float32)
+
+    def is_raw_and_rgb(self):
+        return True
+
+    def summary(self):
+        return 'toy data ({} + {})'.format(self.count_training, self.count_validation)
+
+    def next_training_batch(self, batch_id, batch_size, rgb_patch_size):
+        i = (batch_id * batch_size) % self.count_training
+        return self._x[i:i + batch_size], self._y[i:i + batch_size]
+
+    def next_validation_batch(self, batch_id, batch_size):
+        i = self.count_training + batch_id * batch_size
+        return self._x[i:i + batch_size], self._y[i:i + batch_size]
+
+
+def test_training_loop_api(tmp_path):
+    """training.manipulation.train_manipulation_nip (reference training/manipulation.py:36): runs epochs through
+    flow.training_step, validates with validate_fan (confusion matrix rows sum to 1/n_classes), snapshots the models."""
+    from neural_imaging_b200.training import manipulation, validation
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=16, seed=1234)
+    data = _ToyData()
+    spec = {'camera_name': 'toy', 'use_pretrained_nip': False, 'patch_size': 16, 'batch_size': 4, 'n_epochs': 3, 'validation_schedule': 2,
+            'learning_rate': 1e-3, 'lambda_nip': 0.1}
+    out = manipulation.train_manipulation_nip(flow, spec, data, {'root': str(tmp_path)}, overwrite=True)
+    assert out.endswith('models') and str(tmp_path) in out
+    assert len(flow.fan.performance['loss']['training']) == 3 and len(flow.fan.performance['accuracy']['validation']) == 2
+    conf = np.array(flow.fan.performance['confusion'])
+    assert conf.shape == (5, 5) and abs(conf.sum() - 1.0) < 1e-9 and np.allclose(conf.sum(axis=1), 0.2)
+    acc, conf2, labels = validation.validate_fan(flow, data, get_labels=True)
+    assert len(labels) == 5 * 4 and 0.0 <= acc <= 1.0
+    with pytest.raises(RuntimeError):          # 'camera_name' is a required key (reference :81-86)
+        manipulation.train_manipulation_nip(flow, {k: v for k, v in spec.items() if k != 'camera_name'}, data, {'root': str(tmp_path)})
