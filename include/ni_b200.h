@@ -139,6 +139,10 @@ int ni_maxpool2_fwd(const float* x, float* y, int n, int h, int w, int c, int sa
 int ni_maxpool2_bwd(const float* x, const float* dy, const float* add_or_null, float* dx, int n, int h, int w, int c, int same,
                     int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff, int dx_pitch, int dx_coff,
                     ni_stream_t stream);
+/* ni_maxpool2_bwd + ni_act_bwd_bias of the pooled layer (x = that layer's activated output) in one pass; dbias may be NULL */
+int ni_maxpool2_act_bwd_bias(const float* x, const float* dy, const float* add_or_null, float* dx, float* dbias_or_null, int n, int h, int w,
+                             int c, int same, int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff, int dx_pitch,
+                             int dx_coff, int act, float alpha, ni_stream_t stream);
 /* dy <- dy * act'(y) in place and dbias = column sums (Keras layer activation + bias gradients) */
 int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, int h, int w, int c, int y_pitch, int y_coff, int y_mode,
                     int dy_pitch, int dy_coff, int dy_mode, int act, float alpha, int bias_mod, ni_stream_t stream);

@@ -232,6 +232,55 @@ maxpool_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy
     }
 }
 
+// Max-pool backward fused with the backward of the activation that produced x and with the bias gradient of that layer:
+// dx = (route(dy) + add) * act'(x), dbias[c] += sum_pixels dx. Saves one read-modify-write pass over the largest gradient tensors
+// of the step (12 B per element). Grid-stride with a fixed channel quad per thread (gridDim * 256 is a multiple of c4n), per-block
+// shared-memory reduction, c atomics per block.
+__global__ void __launch_bounds__(256)
+maxpool_act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ add, float* __restrict__ dx,
+                            float* __restrict__ dbias, int n, int oh, int ow, int c4n, int xp, int xo, int dyp, int dyo, int addp, int addo,
+                            int dxp, int dxo, int act, float alpha) {
+    __shared__ float4 red[256];
+    const long long total = (long long)n * oh * ow * c4n;
+    const int c4 = threadIdx.x % c4n;                 // 256 % c4n == 0 (checked by the launcher)
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        long long t = i / c4n;
+        const int ox = (int)(t % ow); t /= ow;
+        const int oy = (int)(t % oh);
+        const long long nn = t / oh;
+        const long long r[4] = {(nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox + 1,
+                                (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox + 1};
+        float4 v[4], g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(x + r[k] * xp + xo + c4 * 4));
+        const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + ((nn * oh + oy) * ow + ox) * dyp + dyo + c4 * 4));
+        pool_route(v[0].x, v[1].x, v[2].x, v[3].x, gy.x, g[0].x, g[1].x, g[2].x, g[3].x);
+        pool_route(v[0].y, v[1].y, v[2].y, v[3].y, gy.y, g[0].y, g[1].y, g[2].y, g[3].y);
+        pool_route(v[0].z, v[1].z, v[2].z, v[3].z, gy.z, g[0].z, g[1].z, g[2].z, g[3].z);
+        pool_route(v[0].w, v[1].w, v[2].w, v[3].w, gy.w, g[0].w, g[1].w, g[2].w, g[3].w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (add) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(add + r[k] * addp + addo + c4 * 4));
+                g[k].x += a.x; g[k].y += a.y; g[k].z += a.z; g[k].w += a.w;
+            }
+            g[k].x *= act_grad_from_out(v[k].x, act, alpha); g[k].y *= act_grad_from_out(v[k].y, act, alpha);
+            g[k].z *= act_grad_from_out(v[k].z, act, alpha); g[k].w *= act_grad_from_out(v[k].w, act, alpha);
+            *reinterpret_cast<float4*>(dx + r[k] * dxp + dxo + c4 * 4) = g[k];
+            s.x += g[k].x; s.y += g[k].y; s.z += g[k].z; s.w += g[k].w;
+        }
+    }
+    if (!dbias) return;
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < c4n) {
+        float4 t = red[threadIdx.x];
+        for (int j = threadIdx.x + c4n; j < 256; j += c4n) { const float4 u = red[j]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        atomicAdd(dbias + c4 * 4, t.x); atomicAdd(dbias + c4 * 4 + 1, t.y); atomicAdd(dbias + c4 * 4 + 2, t.z); atomicAdd(dbias + c4 * 4 + 3, t.w);
+    }
+}
+
 // ------------------------------------------------------------------ global average pooling (n,h,w,c) <-> (n,c)
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c) {
     const int n = blockIdx.x;
@@ -475,6 +524,36 @@ extern "C" int ni_maxpool2_bwd(const float* x, const float* dy, const float* add
     }
     maxpool_bwd_kernel<<<grid_for((long long)n * h * w * c), kT, 0, st>>>(x, dy, add, dx, n, h, w, c, oh, ow, x_pitch, x_coff,
                                                                        dy_pitch, dy_coff, add_pitch, add_coff, dx_pitch, dx_coff);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+extern "C" int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, int h, int w, int c, int y_pitch, int y_coff,
+                               int y_mode, int dy_pitch, int dy_coff, int dy_mode, int act, float alpha, int bias_mod, cudaStream_t st);
+
+// ni_maxpool2_bwd followed by ni_act_bwd_bias on the pooled layer's own output x (conv -> activation -> pool chains of FAN and the
+// U-Net encoder), as ONE pass where the layout allows it; dbias (c floats, may be null) is overwritten.
+extern "C" int ni_maxpool2_act_bwd_bias(const float* x, const float* dy, const float* add, float* dx, float* dbias, int n, int h, int w, int c,
+                                        int same, int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff, int dx_pitch,
+                                        int dx_coff, int act, float alpha, cudaStream_t st) {
+    NI_REQUIRE(x && dy && dx && n >= 0 && h > 0 && w > 0 && c > 0, "ni_maxpool2_act_bwd_bias: invalid arguments");
+    if (n == 0) return NI_OK;
+    const int oh = same ? (h + 1) / 2 : h / 2, ow = same ? (w + 1) / 2 : w / 2;
+    const int c4n = c / 4;
+    const bool vec = !(h & 1) && !(w & 1) && !(c & 3) && c4n > 0 && (256 % c4n) == 0 && !(x_pitch & 3) && !(x_coff & 3) && !(dy_pitch & 3) &&
+                     !(dy_coff & 3) && !(dx_pitch & 3) && !(dx_coff & 3) && (!add || (!(add_pitch & 3) && !(add_coff & 3)));
+    if (!vec) {
+        int rc = ni_maxpool2_bwd(x, dy, add, dx, n, h, w, c, same, x_pitch, x_coff, dy_pitch, dy_coff, add_pitch, add_coff, dx_pitch, dx_coff, st);
+        if (rc) return rc;
+        return ni_act_bwd_bias(x, dx, dbias, n, h, w, c, x_pitch, x_coff, NI_MODE_PLAIN, dx_pitch, dx_coff, NI_MODE_PLAIN, act, alpha, 0, st);
+    }
+    if (dbias) NI_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c, st));
+    const long long total = (long long)n * oh * ow * c4n;
+    long long blocks = (total + 255) / 256;
+    const long long cap = 16LL * ni_num_sms();
+    if (blocks > cap) blocks = cap;
+    maxpool_act_bwd_bias_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, add, dx, dbias, n, oh, ow, c4n, x_pitch, x_coff, dy_pitch, dy_coff, add_pitch,
+                                                                 add_coff, dx_pitch, dx_coff, act, alpha);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }

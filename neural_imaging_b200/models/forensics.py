@@ -172,11 +172,12 @@ class FAN(TFModel):
             conv = self._convs[i]
             d = descs['c%d' % i]
             dc = ws.get('dc%d' % i, (m, d.oh, d.ow, conv.cout))
-            L.ni_maxpool2_bwd(ptr(acts['c%d' % i]), ptr(dp), None, ptr(dc), m, d.oh, d.ow, conv.cout, 0, conv.cout, 0, conv.cout, 0,
-                              0, 0, conv.cout, 0, s)
+            # pool backward + activation backward + bias gradient of conv i in one pass
+            L.ni_maxpool2_act_bwd_bias(ptr(acts['c%d' % i]), ptr(dp), None, ptr(dc), conv.bias_grad_ptr(), m, d.oh, d.ow, conv.cout, 0,
+                                       conv.cout, 0, conv.cout, 0, 0, 0, conv.cout, 0, d.act, d.act_alpha, s)
             x_in = acts['p%d' % (i - 1)] if i > 0 else acts['r']
             dp = ws.get('dp%d' % (i - 1), (m, d.h, d.w, conv.cin)) if i > 0 else ws.get('dr', (m, h, w, 3))
-            conv.bprop(x_in, acts['c%d' % i], dc, dp, d)
+            conv.bprop(x_in, acts['c%d' % i], dc, dp, d, act_bias_done=True)
         # constrained conv: filter gradient through the normalisation; input gradient through the mirrored pad
         d0 = descs['cconv']
         dx = None

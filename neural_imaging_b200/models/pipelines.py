@@ -233,12 +233,14 @@ class UNet(NIPModel):
                 m = S - n
                 cat, dcat = acts['cat%d' % m], dcats[m]
                 dec2 = ws.get('d_ec%d2' % n, (B, ch, cw, c))
-                L.ni_maxpool2_bwd(ptr(cat), ptr(dcur), ptr(dcat), ptr(dec2), B, ch, cw, c, 1, 2 * c, c, c, 0, 2 * c, c, c, 0, s)
-                y2 = cat
+                # + activation backward and bias gradient of ec_n2 (its output is the second half of `cat`) in the same pass
+                L.ni_maxpool2_act_bwd_bias(ptr(cat), ptr(dcur), ptr(dcat), ptr(dec2), c2.bias_grad_ptr(), B, ch, cw, c, 1, 2 * c, c, c, 0,
+                                           2 * c, c, c, 0, d2.act, d2.act_alpha, s)
+                y2, fused = cat, True
             else:
-                dec2, y2 = dcur, acts['dc02']
+                dec2, y2, fused = dcur, acts['dc02'], False
             da1 = ws.get('d_ec%d1' % n, a1.shape)
-            c2.bprop(a1, y2, dec2, da1, d2, dy_addr=(c, 0, MODE_PLAIN))
+            c2.bprop(a1, y2, dec2, da1, d2, dy_addr=(c, 0, MODE_PLAIN), act_bias_done=fused)
             src = acts['ep%d' % (n - 1)]
             if n > 1:
                 dsrc = ws.get('d_ep%d' % (n - 1), src.shape)

@@ -176,8 +176,11 @@ class Conv2D:
         L.ni_conv2d_fprop(ctypes.byref(d), ptr(x), ptr(self.w.value if weight is None else weight), self._bias_ptr(), ptr(y), stream())
         return y
 
+    def bias_grad_ptr(self, need_dw=True):
+        return ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
+
     def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
-              dx_accumulate=False, need_dw=True, dpad=None):
+              dx_accumulate=False, need_dw=True, dpad=None, act_bias_done=False):
         """Backward of fprop(x -> y) described by the forward descriptor `d`.
 
         For mirrored padding (REFLECT / SYMMETRIC + VALID conv) the input gradient is computed on the padded domain into
@@ -185,12 +188,13 @@ class Conv2D:
 
         dy is modified in place (multiplied by the activation derivative). dW / db go to the flat gradient buffer
         (or `dweight`). dy_addr / dx_addr = (pitch, coff, mode) of the gradient buffers when they are laid out
-        differently from y / x (default: same addressing as the forward tensors)."""
+        differently from y / x (default: same addressing as the forward tensors). act_bias_done: dy already carries the
+        activation derivative and the bias gradient has been written (ni_maxpool2_act_bwd_bias)."""
         L = _lib.lib()
         st = stream()
         dyp, dyo, dym = dy_addr if dy_addr is not None else (d.out_pitch, d.out_coff, d.out_mode)
         db = ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
-        if db is not None or d.act not in (ACT_NONE, ACT_CLIP01):
+        if not act_bias_done and (db is not None or d.act not in (ACT_NONE, ACT_CLIP01)):
             L.ni_act_bwd_bias(ptr(y), ptr(dy), db, d.n, d.oh, d.ow, d.cout, d.out_pitch, d.out_coff, d.out_mode,
                               dyp, dyo, dym, d.act, d.act_alpha, self.bias_mod, st)
         dd = ConvDesc()
