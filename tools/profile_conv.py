@@ -8,7 +8,8 @@ from neural_imaging_b200.tensor import as_device, empty, ptr, stream
 
 L = _lib.lib()
 rs = np.random.RandomState(0)
-shapes = [(256, 32, 32, 128, 128, 3), (256, 128, 128, 32, 32, 3), (1280, 64, 64, 32, 64, 5), (256, 16, 16, 256, 256, 3)]
+shapes = [(256, 32, 32, 128, 128, 3), (256, 128, 128, 32, 32, 3), (1280, 64, 64, 32, 64, 5), (256, 16, 16, 256, 256, 3),
+          (1280, 128, 128, 3, 32, 5), (256, 128, 128, 32, 12, 3)]      # 4, 5: direct FP32 kernels (through the dispatcher)
 which = [int(a) for a in sys.argv[1:]] or list(range(len(shapes)))
 res = {}
 for i in which:
@@ -21,9 +22,11 @@ for i in which:
     dy = torch.randn((n, h, w, cout), device='cuda')
     y, dx, dw = empty((n, h, w, cout)), empty((n, h, w, cin)), empty((k, k, cin, cout))
     flop = 2.0 * n * h * w * cin * cout * k * k
-    for name, fn in (('fprop', lambda: L.ni_conv2d_fprop_tc(ctypes.byref(d), ptr(x), ptr(conv.w.value), ptr(conv.b.value), ptr(y), stream())),
-                     ('dgrad', lambda: L.ni_conv2d_dgrad_tc(ctypes.byref(d), ptr(dy), ptr(conv.w.value), ptr(dx), stream())),
-                     ('wgrad', lambda: L.ni_conv2d_wgrad_tc(ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), stream()))):
+    tc = cin % 32 == 0 and cout % 32 == 0
+    fprop, dgrad, wgrad = (L.ni_conv2d_fprop_tc, L.ni_conv2d_dgrad_tc, L.ni_conv2d_wgrad_tc) if tc else (L.ni_conv2d_fprop, L.ni_conv2d_dgrad, L.ni_conv2d_wgrad)
+    for name, fn in (('fprop', lambda: fprop(ctypes.byref(d), ptr(x), ptr(conv.w.value), ptr(conv.b.value), ptr(y), stream())),
+                     ('dgrad', lambda: dgrad(ctypes.byref(d), ptr(dy), ptr(conv.w.value), ptr(dx), stream())),
+                     ('wgrad', lambda: wgrad(ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), stream()))):
         for _ in range(2):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
