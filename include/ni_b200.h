@@ -44,6 +44,16 @@ int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h, int w, co
 int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, int h, int w, const float* q_luma,
                  const float* q_chroma, int mode, ni_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ training-data feed
+ * Replaces the host-side batch assembly of Dataset.next_training_batch (helpers/dataset.py:89-131): crop, astype(float) / 65535
+ * (uint16 RGGB stacks) or / 255 (uint8 RGB), float32 batch. Results are bit-identical to the reference's float32 batches.
+ * ni_feed_convert: dst[i] = float(src[i]) / denom for n contiguous elements (src_bytes 1 = uint8, 2 = uint16; 16-byte aligned).
+ * ni_feed_gather : images (n_images,h,w,c) integers RESIDENT on the device; coords (batch,3) int32 DEVICE triples (image, y, x);
+ *                  out (batch,ph,pw,c) float32 = images[image, y:y+ph, x:x+pw, :] / denom. */
+int ni_feed_convert(const void* src, int src_bytes, float* dst, long long n, float denom, ni_stream_t stream);
+int ni_feed_gather(const void* images, int src_bytes, int n_images, int h, int w, int c, const int* coords, int batch, int ph, int pw,
+                   float denom, float* out, ni_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ manipulations
  * helpers/tf_helpers.py:68-184. All on (n,h,w,3). */
 /* manipulation_sharpen (tf_helpers.py:156-184): filt9 = HOST 3x3 filter applied to H and V; S takes tap [2,2]. */
@@ -123,8 +133,11 @@ int ni_conv2d_wgrad_small(const ni_conv_desc* d, const float* x, const float* dy
 int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d /*128x64*/, int mn_major, ni_stream_t stream);
 /* measurement probe: TMA box streaming rate vs channel pitch / boxes in flight; returns the grid size (> 0) or an error (< 0) */
 int ni_tma_probe(const float* x, int n, int h, int w, int c, int stages, int boxes_per_cta, long long* cycles_out, int max_grid, ni_stream_t stream);
-/* debug: per-role clock64 spans of the persistent tcgen05 gemm (zeros unless built with -DNI_TC_PROFILE) */
-int ni_tc_prof_read(long long* out32, int reset);
+/* measurement probes (tools/): tcgen05.mma issue / execution rate; 1-D bulk-copy (weight stream) ingest rate per SM */
+int ni_mma_probe(int n, int ts, int rounds, int nacc, long long* cycles_out, int grid, ni_stream_t stream);
+int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, long long* cycles_out, int grid, ni_stream_t stream);
+/* debug: per-role clock64 spans of the persistent tcgen05 gemm [0,32) and of the wgrad kernel [32,64) (zeros unless built with -DNI_TC_PROFILE) */
+int ni_tc_prof_read(long long* out64, int reset);
 void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */
 /* The SIMT implementations, callable directly (tests compare the two paths on the device). */
 int ni_conv2d_fprop_simt(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);

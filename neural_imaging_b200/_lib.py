@@ -9,7 +9,8 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'ni_b200.h')
-LIB_PATH = os.path.join(_HERE, 'libni_b200.so')
+# NI_B200_LIB selects a development variant of the same library (tools/: profiling build); never a different implementation
+LIB_PATH = os.environ.get('NI_B200_LIB') or os.path.join(_HERE, 'libni_b200.so')
 
 
 class ConvDesc(ctypes.Structure):

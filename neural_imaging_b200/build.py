@@ -6,8 +6,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, 'build')
-LIB = os.path.join(HERE, 'libni_b200.so')
+TAG = os.environ.get('NI_BUILD_TAG', '')          # development variants (tools/): e.g. NI_BUILD_TAG=prof -> build_prof/, libni_b200_prof.so
+OBJ = os.path.join(HERE, 'build' + ('_' + TAG if TAG else ''))
+LIB = os.path.join(HERE, 'libni_b200' + ('_' + TAG if TAG else '') + '.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr'] + os.environ.get('NI_NVCC_EXTRA', '').split()      # e.g. -DNI_TC_PROFILE (tools/gpu_tcprof.sh)

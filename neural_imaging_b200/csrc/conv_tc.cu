@@ -28,7 +28,7 @@
 
 namespace {
 
-// w (taps, cin, cout) HWIO -> tiles for the gemm kernel: block ((tap * K/32 + kc) * N/bnt + nt) = [hi | lo], each a
+// w (taps, cin, cout) HWIO -> tiles for the gemm kernel: block ((nt * K/32 + kc) * taps + tap) = [hi | lo], each a
 // (bnt rows x 32 k) K-major SWIZZLE_128B tile exactly as the MMA reads it. transpose: N = cout, K = cin (fprop); else N = cin, K = cout.
 __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int transpose, int bnt) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -40,7 +40,7 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     const int n = (int)(t % N), tap = (int)(t / N);
     const float v = transpose ? w[((long long)tap * cin + k) * cout + n] : w[((long long)tap * cin + n) * cout + k];
     const int kc = k >> 5, kl = k & 31, nt = n / bnt, nl = n - nt * bnt;
-    const long long block = ((long long)tap * (K >> 5) + kc) * (N / bnt) + nt;
+    const long long block = ((long long)nt * (K >> 5) + kc) * taps + tap;     // [n tile][k-iteration = kc * taps + tap]: a tile's stream is contiguous
     const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) + (kl & 3));
     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     float* o = out + block * (2 * bnt * 32);
@@ -178,7 +178,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         ni_set_error("conv_tc: unsupported spatial tile");
         return NI_ERR_UNSUPPORTED;
     }
-    p.sa = (K / 32) > 1 ? tcv2::kMaxSA : 1;
+    p.sa = tcv2::kMaxSA;           // two halo stages: the next chunk / the next tile's halo is in flight while this one is converted
     const int bnt = pick_bnt(N);
     float* scratch = nullptr;
     const size_t wbytes = (size_t)2 * taps * K * N * sizeof(float);
@@ -209,25 +209,39 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         // generation 3: persistent CTAs (one per SM), see conv_tc_v3.cuh
         tcv3::PersistParams q;
         q.mtiles = mtiles; q.total_tiles = mtiles * (N / bnt);
+        // Weight stream: groups of G k-iterations = one 32 KB bulk copy (the copy engine completes ~1 operation per 735 cycles whatever its
+        // size up to 32 KB). Resident: when the whole [hi | lo] weight slice of the (single) n-tile fits beside the A stages it is loaded once
+        // per CTA instead of once per pixel tile.
+        const int iters = taps * (K / 32);
+        const int G = tcv3::kGroupBytes / (2 * bnt * 128);
+        const int ngroups = (iters + G - 1) / G;
+        const int grid_ctas = q.total_tiles < ni_num_sms() ? q.total_tiles : ni_num_sms();
+        const int budget = 226 * 1024 - 1024;
+        if (p.sa * p.a_stage + tcv3::kGroupBytes > budget) p.sa = 1;
+        const int room = (budget - p.sa * p.a_stage) / tcv3::kGroupBytes;       // 32 KB groups that fit beside the A stages
+        static const int resident_on = getenv("NI_TC_B_RESIDENT") ? atoi(getenv("NI_TC_B_RESIDENT")) : 1;
+        q.b_resident = (resident_on && N == bnt && ngroups <= room && ngroups <= tcv3::kMaxGroups && q.total_tiles >= 2 * grid_ctas) ? 1 : 0;
+        if (q.b_resident) { q.sb = ngroups; q.log_sb = 0; }
+        else if (room >= 4) { q.sb = 4; q.log_sb = 2; }
+        else if (room >= 2) { q.sb = 2; q.log_sb = 1; }
+        else { q.sb = room >= 1 ? 1 : 0; q.log_sb = 0; }
+        const int bstage = tcv3::kGroupBytes;
         // TMEM budget (tcv3::Cfg): N = 128 -> one set of (nacc + 1) accumulators + 2 A slots; N <= 64 -> fixed 4 accumulators per set
         int nacc = want_nacc;
         while (bnt == 128 && (nacc + 1) * bnt + 2 * 64 > 512) --nacc;
-        if (nacc > taps * (K / 32)) nacc = taps * (K / 32);
+        if (nacc > iters) nacc = iters;
         p.nacc = nacc < 1 ? 1 : nacc;
-        const int bstage = 2 * bnt * 128;
-        int sb = (220 * 1024 - p.sa * p.a_stage) / bstage;
-        q.sb = sb > tcv3::kMaxSB ? tcv3::kMaxSB : sb;
-        if (q.sb < 2) { ni_set_error("conv_tc: not enough shared memory for the B ring"); return NI_ERR_UNSUPPORTED; }
+        if (q.sb < 1) { ni_set_error("conv_tc: not enough shared memory for the weight ring"); return NI_ERR_UNSUPPORTED; }
         const size_t smem = (size_t)p.sa * p.a_stage + (size_t)q.sb * bstage + 1024;
-        const int grid = q.total_tiles < ni_num_sms() ? q.total_tiles : ni_num_sms();
+        const int grid = grid_ctas;
 #define NI_TC_GEMM3(B)                                                                                         \
     {                                                                                                          \
         rc = set_dyn_smem(tcv3::conv_tc3_gemm_kernel<B>, smem);                                                \
         if (rc) return rc;                                                                                     \
         if (getenv("NI_TC_DEBUG")) {                                                                           \
             cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, tcv3::conv_tc3_gemm_kernel<B>);                  \
-            fprintf(stderr, "tc gemm3<%d>: grid %d, tiles %d, iters %d, smem %zu, regs %d, local %zu, sb %d, sa %d, nacc %d\n", B, grid,  \
-                    q.total_tiles, taps * (K / 32), smem, fa.numRegs, fa.localSizeBytes, q.sb, p.sa, p.nacc);  \
+            fprintf(stderr, "tc gemm3<%d>: grid %d, tiles %d, iters %d, smem %zu, regs %d, local %zu, sb %d%s, sa %d, nacc %d\n", B, grid,  \
+                    q.total_tiles, taps * (K / 32), smem, fa.numRegs, fa.localSizeBytes, q.sb, q.b_resident ? " (resident)" : "", p.sa, p.nacc);  \
         }                                                                                                      \
         tcv3::conv_tc3_gemm_kernel<B><<<grid, tcv3::kThreads, smem, st>>>(tmA, scratch, p, q);                 \
     }
@@ -261,15 +275,15 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
 
 }  // namespace
 
-// In-kernel timing counters of the persistent gemm (all zero unless the library was built with -DNI_TC_PROFILE)
-extern "C" int ni_tc_prof_read(long long* out32, int reset) {
-    NI_REQUIRE(out32, "ni_tc_prof_read: null pointer");
+// In-kernel timing counters of the persistent gemm [0,32) and of wgrad [32,64) (all zero unless the library was built with -DNI_TC_PROFILE)
+extern "C" int ni_tc_prof_read(long long* out64, int reset) {
+    NI_REQUIRE(out64, "ni_tc_prof_read: null pointer");
 #ifdef NI_TC_PROFILE
     NI_CUDA(cudaDeviceSynchronize());
-    NI_CUDA(cudaMemcpyFromSymbol(out32, tcv3::g_tc_prof, sizeof(long long) * 32));
-    if (reset) { long long z[32] = {0}; NI_CUDA(cudaMemcpyToSymbol(tcv3::g_tc_prof, z, sizeof(z))); }
+    NI_CUDA(cudaMemcpyFromSymbol(out64, tc::g_tc_prof, sizeof(long long) * 64));
+    if (reset) { long long z[64] = {0}; NI_CUDA(cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z))); }
 #else
-    for (int i = 0; i < 32; ++i) out32[i] = 0;
+    for (int i = 0; i < 64; ++i) out64[i] = 0;
 #endif
     return NI_OK;
 }
@@ -373,6 +387,9 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     p.steps_per_split = (p.steps_total + splits - 1) / splits;
     splits = (p.steps_total + p.steps_per_split - 1) / p.steps_per_split;
     dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
+    if (getenv("NI_TC_DEBUG"))
+        fprintf(stderr, "tc wgrad<%d>: grid (%d, %d, %d), steps %d total, %d per split, atoms %d\n", bnt, mtiles, ntiles, splits, p.steps_total,
+                p.steps_per_split, p.atoms);
 #define NI_TC_WGRAD(B)                                                                                         \
     {                                                                                                          \
         const size_t smem = (size_t)tcv2::WgCfg<B>::STAGES * (tcv2::kAraw + 3 * B * 128) + 1024;                      \

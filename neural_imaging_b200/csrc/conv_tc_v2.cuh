@@ -127,10 +127,10 @@ conv_tc2_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 const int s = it % SB, ph = (it / SB) & 1;
                 mbar_wait(&bar_bfree[s], ph ^ 1, 7);
                 mbar_expect_tx(&bar_bfull[s], 2 * B_BYTES);
-                // weights are pre-tiled by the prep kernel: block (tap, kc, n-tile) = [hi tile | lo tile], already in the swizzled
+                // weights are pre-tiled by the prep kernel: block (n-tile, kc, tap) = [hi tile | lo tile], already in the swizzled
                 // K-major order, so one contiguous bulk copy replaces two 128-row tensor boxes (TMA cost is per box row)
                 const int kc = it / taps, tap = it - kc * taps;
-                const float* src = wtiled + ((size_t)(tap * p.kchunks + kc) * gridDim.y + blockIdx.y) * (size_t)(2 * BNT * 32);
+                const float* src = wtiled + ((size_t)(blockIdx.y * p.kchunks + kc) * taps + tap) * (size_t)(2 * BNT * 32);
                 bulk_load_1d(b_hi(s), src, 2 * B_BYTES, &bar_bfull[s]);
             }
         }
@@ -323,9 +323,12 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
+            TCP_DECL
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+                TCP_START();
                 mbar_wait(&bar_free[s], ph ^ 1, 0);
+                TCP_ADD(32);
                 mbar_expect_tx(&bar_full[s], valid_atoms * 4096 + B_BYTES);
                 const int st = step0 + it;
                 const int tw = st % p.tiles_w, th = (st / p.tiles_w) % p.tiles_h, tn = st / (p.tiles_w * p.tiles_h);
@@ -344,15 +347,20 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         tma_load_4d(raw_b(s) + j * 4096, &tmDY, &bar_full[s], co, x0, y0, n0);
                     }
                 }
+                TCP_ADD(33);
             }
         }
     } else if (warp == 1) {
         {   // ---- MMA issuer: the whole warp walks the loop (uniform operands), one elected lane issues (see tc::elect_one)
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
+            TCP_DECL
             for (int it = 0; it < iters; ++it) {
                 const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+                TCP_START();
                 mbar_wait(&bar_aready[s], ph, 1);
+                TCP_ADD(34);
                 mbar_wait(&bar_bready[s], ph, 2);
+                TCP_ADD(35);
                 tcgen05_fence_after();
                 const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
                 const uint32_t ahi = a_base + s * 64, alo = ahi + 32;
@@ -369,6 +377,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     umma_commit(&bar_free[s]);
                 }
                 __syncwarp();
+                TCP_ADD(36);
             }
             if (elect_one()) umma_commit(&bar_accum);
             __syncwarp();
@@ -377,9 +386,14 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         // ---- A converters: warp q <-> atom q (rows 32q .. 32q+31 of the M tile), lane = channel
         // a warp may only touch TMEM lanes [32 (warp % 4), +32): warp with quarter q converts atom q (M rows 32q .. 32q+31)
         const int q = warp & 3;
+#ifdef NI_TC_PROFILE
+        long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+#endif
         for (int it = 0; it < iters; ++it) {
             const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+            TCP_START();
             mbar_wait(&bar_full[s], ph, 3);
+            TCP_ADD(37);
             float hi[32], lo[32];
             if (q < valid_atoms) {
                 const uint32_t ap = smem_u32(raw_a(s)) + (uint32_t)(q * 4096 + (lane & 3) * 4);
@@ -396,6 +410,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
             // slot s was last read by the MMAs of iteration it - kWgStages, whose completion released bar_free[s] to the
             // producer before this stage was refilled, so the slot is free once bar_full[s] has fired
+            TCP_ADD(38);
             tcgen05_fence_after();
             const uint32_t dst = a_base + ((uint32_t)(q * 32) << 16) + s * 64;
             tmem_st_32x32(dst, hi);
@@ -403,6 +418,7 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             tmem_st_wait();
             tcgen05_fence_before();
             mbar_arrive(&bar_aready[s]);
+            TCP_ADD(39);
         }
         mbar_wait(&bar_accum, 0, 4);
         tcgen05_fence_after();
@@ -425,13 +441,19 @@ conv_tc2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     } else {
         // ---- B transposers (128 threads)
         const int tid = threadIdx.x - 192;
+#ifdef NI_TC_PROFILE
+        long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 192;
+#endif
         for (int it = 0; it < iters; ++it) {
             const int s = it % kWgStages, ph = (it / kWgStages) & 1;
+            TCP_START();
             mbar_wait(&bar_full[s], ph, 6);
+            TCP_ADD(40);
             for (int qq = tid; qq < (BNT / 32) * 256; qq += 128)
                 transpose_split_chunk(smem_u32(raw_b(s)) + (uint32_t)((qq >> 8) * 4096), smem_u32(b_hi(s)), smem_u32(b_lo(s)), (qq >> 8) * 32, qq & 255);
             fence_proxy_async_smem();
             mbar_arrive(&bar_bready[s]);
+            TCP_ADD(41);
         }
     }
     __syncthreads();

@@ -10,6 +10,19 @@
 //
 // Warp roles (16 warps): 0 A producer (halo tiles, see conv_tc_v2.cuh), 1 MMA issuer, 2 B producer, 3 TMEM allocator + second MMA issuer,
 // 4-11 converters (two per TMEM lane quarter, 16 K-columns each), 12-15 epilogue (one per lane quarter).
+//
+// Generation 3b (hardware probes: tools/hw_probes.py, profiles/r1_hw_probes.txt):
+//  * a cp.async.bulk / TMA operation occupies the SM's copy engine for ~735 cycles whatever its size up to 32 KB (8, 16 and 32 KB
+//    copies all complete one per ~735 cycles, at any depth in flight). With one weight copy per k-iteration the N = 32 / 64 main
+//    loops (8 / 16 KB per copy) were bound by that, not by their MMAs (408 / 560 cycles per iteration): the weight stream now moves
+//    in GROUPS of G = 4 / 2 / 1 consecutive k-iterations = one 32 KB copy (the prep kernel lays the tiles out [n tile][k-iteration]);
+//  * the tensor pipe needs 20.5 + 0.42 N cycles per kind::tf32 MMA with A in tensor memory (34 / 47 / 74 cycles at N = 32 / 64 / 128)
+//    and its queue is shallow: whatever the issuer spends between two iterations, the pipe idles. The issue loop is free of integer
+//    divisions now (power-of-two rings, descriptors advanced by additions);
+//  * when the whole weight slice of the launch fits in shared memory it is loaded once per CTA (resident) instead of once per tile;
+//  * an A stage is handed back to the TMA producer only after the registers loaded from it have been consumed (the tcgen05.st that
+//    reads them has been issued). The release used to follow the LDS *issue*; corrupted rows showed up in the second tile of a CTA
+//    on cold launches (tools/tc_repro3.py).
 #pragma once
 #include "conv_desc.h"
 #include "conv_tc_v2.cuh"
@@ -22,49 +35,43 @@ using tcv2::act_apply;
 using tcv2::GemmParams;
 using tcv2::pow2_cols;
 
-// Optional in-kernel timing (build with -DNI_TC_PROFILE): CTA 0 accumulates clock64() spans per role into g_tc_prof.
-#ifdef NI_TC_PROFILE
-__device__ long long g_tc_prof[32];
-#define TCP_DECL long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0;
-#define TCP_START() do { if (tcp_on) tcp_t = clock64(); } while (0)
-#define TCP_ADD(i) do { if (tcp_on) { const long long n_ = clock64(); atomicAdd((unsigned long long*)&g_tc_prof[i], (unsigned long long)(n_ - tcp_t)); tcp_t = n_; } } while (0)
-#else
-#define TCP_DECL
-#define TCP_START() do {} while (0)
-#define TCP_ADD(i) do {} while (0)
-#endif
-
 constexpr int kThreads = 512;
 constexpr int kNCW = 8;            // converter warps
-constexpr int kMaxSA = 2, kMaxSB = 8;
+constexpr int kMaxSA = 2;
+constexpr int kMaxGroups = 32;     // weight-copy groups per tile in resident mode; ring stages (1, 2 or 4) when streaming
+constexpr int kGroupBytes = 32768; // one weight copy = G k-iterations of [hi | lo] tiles
 
-// In-kernel clock64 spans: ONE thread needs ~74 cycles per tcgen05.mma (ELECT + uniform-datapath descriptor arithmetic + UTCHMMA),
-// whatever N is and wherever A comes from; N = 128 executes for 64 cycles anyway, but N <= 64 is issue-bound. Those tiles get
-// TWO issuer warps (different scheduler partitions) that take alternate k-iterations and own separate accumulators
-// [D1_0, D2_0, D1_1, D2_1]; the epilogue adds them up (the sum is order-independent, only each accumulator's FIRST MMA has to
-// overwrite, and that is a per-issuer property).
+// N <= 64 is issue-bound with ONE issuer thread (~20 cycles of fixed cost per MMA against 34 / 47 of execution leave no slack for the
+// waits), so those tiles get TWO issuer warps (different scheduler partitions) that take alternate k-iterations and own separate
+// accumulators [D1_0, D2_0, D1_1, D2_1]; the epilogue adds them up (the sum is order-independent, only each accumulator's FIRST MMA
+// has to overwrite, and that is a per-issuer property).
 template <int BNT> struct Cfg {
     static constexpr int ISSUERS = BNT == 128 ? 1 : 2;
     static constexpr int SLOTS = BNT == 128 ? 2 : 4;     // A (hi | lo) slots in tensor memory, 64 columns each
+    static constexpr int LOG_SLOTS = BNT == 128 ? 1 : 2;
     static constexpr int NSETS = BNT == 32 ? 2 : 1;      // accumulator sets (512 TMEM columns: sets * set_cols + SLOTS * 64)
-    static constexpr int B_BYTES = BNT * 128;            // one (BNT x 32) tf32 tile; a B stage is hi + lo
+    static constexpr int B_BYTES = BNT * 128;            // one (BNT x 32) tf32 tile; a k-iteration reads hi + lo
+    static constexpr int G = kGroupBytes / (2 * B_BYTES); // k-iterations per weight copy: 4 / 2 / 1
+    static constexpr int LOG_G = BNT == 32 ? 2 : (BNT == 64 ? 1 : 0);
 };
 
 struct PersistParams {
     int mtiles, total_tiles;       // pixel tiles, pixel tiles * n tiles
-    int sb;                        // B stages in use (<= kMaxSB)
+    int sb, log_sb;                // weight ring: stages (1, 2 or 4 groups) and log2; resident: groups per tile (ring unused)
+    int b_resident;                // 1: the CTA's whole weight slice is loaded ONCE and stays in shared memory (single n tile)
 };
 
 template <int BNT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ wtiled, const GemmParams p, const PersistParams q) {
-    constexpr int SLOTS = Cfg<BNT>::SLOTS, NSETS = Cfg<BNT>::NSETS, B_BYTES = Cfg<BNT>::B_BYTES, ISSUERS = Cfg<BNT>::ISSUERS;
+    constexpr int SLOTS = Cfg<BNT>::SLOTS, LOG_SLOTS = Cfg<BNT>::LOG_SLOTS, NSETS = Cfg<BNT>::NSETS, B_BYTES = Cfg<BNT>::B_BYTES,
+                  ISSUERS = Cfg<BNT>::ISSUERS, G = Cfg<BNT>::G, LOG_G = Cfg<BNT>::LOG_G;
     const uint32_t set_cols = ISSUERS == 2 ? 4u * BNT : (uint32_t)(p.nacc + 1) * BNT;
     const uint32_t acc_cols = set_cols * NSETS;
     const uint32_t TMEM_COLS = pow2_cols(acc_cols + SLOTS * 64);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar_afull[kMaxSA], bar_afree[kMaxSA], bar_bfull[kMaxSB], bar_bfree[kMaxSB], bar_tready[SLOTS], bar_tfree[SLOTS],
+    __shared__ uint64_t bar_afull[kMaxSA], bar_afree[kMaxSA], bar_bfull[kMaxGroups], bar_bfree[kMaxGroups], bar_tready[SLOTS], bar_tfree[SLOTS],
         bar_accfull[NSETS], bar_accfree[NSETS];
     __shared__ uint32_t tmem_slot;
 
@@ -72,13 +79,13 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int taps = p.kh * p.kw;
     const int iters = taps * p.kchunks;
-    const int ntiles_n = p.ntot / BNT;
+    const int ngroups = (iters + G - 1) >> LOG_G;                   // weight copies per tile
     const int n_iss = (ISSUERS == 2 && iters >= 2) ? 2 : 1;          // active issuer warps
     const int nsum = ISSUERS == 2 ? 2 * n_iss : p.nacc + 1;         // accumulators the epilogue adds up
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxSA; ++s) { mbar_init(&bar_afull[s], 1); mbar_init(&bar_afree[s], kNCW * 32); }
-        for (int s = 0; s < kMaxSB; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bfree[s], 1); }
+        for (int s = 0; s < kMaxGroups; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bfree[s], n_iss); }
         for (int t = 0; t < SLOTS; ++t) { mbar_init(&bar_tready[t], kNCW * 32); mbar_init(&bar_tfree[t], 1); }
         for (int a = 0; a < NSETS; ++a) { mbar_init(&bar_accfull[a], n_iss); mbar_init(&bar_accfree[a], 128); }
         fence_barrier_init();
@@ -92,8 +99,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     const uint32_t a_base = tmem + acc_cols;
 
     auto a_halo = [&](int s) { return smem + s * p.a_stage; };
-    auto b_hi = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES; };
-    auto b_lo = [&](int s) { return smem + p.sa * p.a_stage + s * 2 * B_BYTES + B_BYTES; };
+    uint8_t* const b_base = smem + p.sa * p.a_stage;                 // weight stages / resident groups, kGroupBytes apart
     // tile t -> (pixel tile m = t % mtiles, n tile = t / mtiles): neighbouring CTAs share the weight slice in L2
     auto tile_origin = [&](int tile, int& x0, int& y0, int& n0, int& nt) {
         const int m = tile % q.mtiles;
@@ -105,14 +111,13 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     if (warp == 0) {
         if (lane == 0) {   // ---- A producer: one halo box per (tile, 32-channel chunk)
             const uint32_t bytes = (uint32_t)(p.hw * p.hh * p.bn) * 128u;
-            int gkc = 0;
+            int s = 0, ph = 0;
             TCP_DECL
             for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
                 int x0, y0, n0, nt;
                 tile_origin(tile, x0, y0, n0, nt);
                 const int bx = x0 + p.off_x0 + (p.off_sign < 0 ? -(p.kw - 1) : 0), by = y0 + p.off_y0 + (p.off_sign < 0 ? -(p.kh - 1) : 0);
-                for (int kc = 0; kc < p.kchunks; ++kc, ++gkc) {
-                    const int s = gkc % p.sa, ph = (gkc / p.sa) & 1;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
                     TCP_START();
                     mbar_wait(&bar_afree[s], ph ^ 1, 0);
                     TCP_ADD(12);
@@ -123,24 +128,27 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     } else {
                         tma_load_4d(a_halo(s), &tmA, &bar_afull[s], kc * 32, bx, by, n0);
                     }
+                    if (++s == p.sa) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {   // ---- B producer: pre-tiled [hi | lo] weight blocks, one contiguous bulk copy per iteration
-            int git = 0;
+        if (lane == 0) {   // ---- B producer: pre-tiled [hi | lo] weight tiles of G consecutive k-iterations per bulk copy
+            int gg = 0;
             TCP_DECL
             for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
+                if (q.b_resident && tile != (int)blockIdx.x) break;      // resident weights: loaded while the first tile runs
                 const int nt = tile / q.mtiles;
-                for (int it = 0; it < iters; ++it, ++git) {
-                    const int s = git % q.sb, ph = (git / q.sb) & 1;
+                const float* src = wtiled + (size_t)nt * iters * (size_t)(2 * BNT * 32);
+                for (int g = 0; g < ngroups; ++g, ++gg) {
+                    const int s = q.b_resident ? g : (gg & (q.sb - 1)), ph = q.b_resident ? 0 : ((gg >> q.log_sb) & 1);
+                    const int n_it = min(G, iters - (g << LOG_G));
                     TCP_START();
                     mbar_wait(&bar_bfree[s], ph ^ 1, 7);
                     TCP_ADD(13);
-                    mbar_expect_tx(&bar_bfull[s], 2 * B_BYTES);
-                    const int kc = it / taps, tap = it - kc * taps;
-                    const float* src = wtiled + ((size_t)(tap * p.kchunks + kc) * ntiles_n + nt) * (size_t)(2 * BNT * 32);
-                    bulk_load_1d(b_hi(s), src, 2 * B_BYTES, &bar_bfull[s]);
+                    mbar_expect_tx(&bar_bfull[s], (uint32_t)n_it * 2u * B_BYTES);
+                    bulk_load_1d(b_base + (size_t)s * kGroupBytes, src + (size_t)(g << LOG_G) * (size_t)(2 * BNT * 32), (uint32_t)n_it * 2u * B_BYTES,
+                                 &bar_bfull[s]);
                 }
             }
         }
@@ -148,49 +156,67 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         const int iss = warp == 1 ? 0 : 1;
         if (iss < n_iss) {   // ---- MMA issuer(s): the whole warp walks the loop (uniform control flow), one elected lane issues
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
-            int gbase = 0, tcount = 0;
+            const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(b_base), 16, 1024);     // start-address field in 16-byte units
+            const int tail_n = iters - ((ngroups - 1) << LOG_G);              // k-iterations in the last group of a tile
+            int gbase = 0, ggbase = 0, tcount = 0;
             TCP_DECL
-            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tcount, gbase += iters) {
-                const int aset = tcount % NSETS, use = tcount / NSETS;
+            for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tcount, gbase += iters, ggbase += ngroups) {
+                const int aset = NSETS == 2 ? (tcount & 1) : 0, use = NSETS == 2 ? (tcount >> 1) : tcount;
                 TCP_START();
                 mbar_wait(&bar_accfree[aset], (use & 1) ^ 1, 8);          // epilogue has drained this accumulator set
                 TCP_ADD(3);
                 tcgen05_fence_after();
                 const uint32_t dbase = tmem + (uint32_t)aset * set_cols;
+                int cur_g = -1, bs = 0, acc_i = 0;
+                uint64_t gdesc = bdesc0;
                 for (int it = iss; it < iters; it += n_iss) {
                     const int git = gbase + it;
-                    const int s = git % q.sb, ph = (git / q.sb) & 1;
-                    const int t = git % SLOTS, pt = (git / SLOTS) & 1;
+                    const int t = git & (SLOTS - 1), pt = (git >> LOG_SLOTS) & 1;
+                    const int g = it >> LOG_G;
                     TCP_START();
-                    mbar_wait(&bar_bfull[s], ph, 1);
+                    if (g != cur_g) {                                     // first k-iteration of this issuer in a new weight group
+                        cur_g = g;
+                        const int gg = ggbase + g;
+                        bs = q.b_resident ? g : (gg & (q.sb - 1));
+                        mbar_wait(&bar_bfull[bs], q.b_resident ? 0 : ((gg >> q.log_sb) & 1), 1);
+                        gdesc = bdesc0 + (uint64_t)((uint32_t)bs * (uint32_t)(kGroupBytes >> 4));
+                    }
                     TCP_ADD(1);
                     mbar_wait(&bar_tready[t], pt, 2);
                     TCP_ADD(2);
                     tcgen05_fence_after();
-                    const uint32_t bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
                     const uint32_t ahi = a_base + t * 64, alo = ahi + 32;
                     uint32_t d1, d2, first1, first2;
                     if (ISSUERS == 2) {
                         d1 = dbase + (uint32_t)(2 * iss) * BNT; d2 = d1 + BNT;
                         first1 = first2 = it == iss ? 1u : 0u;
                     } else {
-                        d1 = dbase + (uint32_t)(it % p.nacc) * BNT; d2 = dbase + (uint32_t)p.nacc * BNT;
+                        d1 = dbase + (uint32_t)acc_i * BNT; d2 = dbase + (uint32_t)p.nacc * BNT;
                         first1 = it < p.nacc ? 1u : 0u; first2 = it == 0 ? 1u : 0u;
+                        if (++acc_i == p.nacc) acc_i = 0;
                     }
-                    const uint64_t dbh0 = make_smem_desc_sw128(bh, 16, 1024), dbl0 = make_smem_desc_sw128(bl, 16, 1024);
+                    const uint64_t dbh0 = gdesc + (uint64_t)((uint32_t)(it & (G - 1)) * (uint32_t)(2 * B_BYTES >> 4)), dbl0 = dbh0 + (uint64_t)(B_BYTES >> 4);
+                    // last k-iteration of THIS issuer inside the weight group: its commit hands the stage back (bfree counts n_iss arrivals)
+                    const bool group_done = !q.b_resident && (it + n_iss >= min((g + 1) << LOG_G, iters));
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t dbh = dbh0 + (uint64_t)(ks * 2), dbl = dbl0 + (uint64_t)(ks * 2);   // +32 bytes (start address is in 16-byte units)
+                            const uint64_t dbh = dbh0 + (uint64_t)(ks * 2), dbl = dbl0 + (uint64_t)(ks * 2);   // +32 bytes
                             umma_tf32_ts(d2, alo + ks * 8, dbh, idesc, (first2 && ks == 0) ? 0u : 1u);
                             umma_tf32_ts(d2, ahi + ks * 8, dbl, idesc, 1u);
                             umma_tf32_ts(d1, ahi + ks * 8, dbh, idesc, (first1 && ks == 0) ? 0u : 1u);
                         }
                         TCP_ADD(17);
-                        umma_commit(&bar_bfree[s]);
                         umma_commit(&bar_tfree[t]);
+                        if (group_done) umma_commit(&bar_bfree[bs]);
                         TCP_ADD(4);
                     }
+                    __syncwarp();
+                }
+                // a last group holding a single k-iteration is read by one issuer only: the other one still owes the stage its arrival
+                if (!q.b_resident && n_iss == 2 && tail_n == 1 && ((iters - 1) & 1) != iss) {
+                    const int gg = ggbase + ngroups - 1;
+                    if (elect_one()) mbar_arrive(&bar_bfree[gg & (q.sb - 1)]);
                     __syncwarp();
                 }
                 if (elect_one()) umma_commit(&bar_accfull[aset]);
@@ -201,22 +227,30 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         // ---- converters: A halo row -> registers -> hi / lo -> TMEM (two warps per lane quarter, 16 K-columns each)
         const int qd = warp & 3, row = qd * 32 + lane, half = (warp - 4) >> 2;
         const int prow0 = ((row / (p.bw * p.bh)) * p.hh + (row / p.bw) % p.bh) * p.hw + row % p.bw;
-        int git = 0, gkc = 0;
+        int git = 0, s = 0, ph = 0;
         int pending = -1;            // slot whose tcgen05.st is in flight: its completion wait + "ready" arrive are deferred until
                                      // the next iteration's shared-memory loads and hi/lo split are done (hides ~200 cycles)
 #ifdef NI_TC_PROFILE
         long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 128;
 #endif
         for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < p.kchunks; ++kc, ++gkc) {
-                const int s = gkc % p.sa, ph = (gkc / p.sa) & 1;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
                 TCP_START();
-                mbar_wait(&bar_afull[s], ph, 3);
+                if (!mbar_try_wait(&bar_afull[s], ph)) {
+                    // the halo has not landed yet: do not keep the MMA warp waiting for the previous iteration's operand meanwhile
+                    if (pending >= 0) {
+                        tmem_st_wait();
+                        tcgen05_fence_before();
+                        mbar_arrive(&bar_tready[pending]);
+                        pending = -1;
+                    }
+                    mbar_wait(&bar_afull[s], ph, 3);
+                }
                 TCP_ADD(6);
                 const uint32_t stage = smem_u32(a_halo(s));
                 int ta = 0, tb = 0;
                 for (int tap = 0; tap < taps; ++tap, ++git) {
-                    const int t = git % SLOTS, pt = (git / SLOTS) & 1;
+                    const int t = git & (SLOTS - 1), pt = (git >> LOG_SLOTS) & 1;
                     const int prow = prow0 + (p.off_sign > 0 ? ta : p.kh - 1 - ta) * p.hw + (p.off_sign > 0 ? tb : p.kw - 1 - tb);
                     if (++tb == p.kw) { tb = 0; ++ta; }
                     float hi[16], lo[16];
@@ -232,7 +266,6 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                             lo[4 * c + e] = vv[e] - h;
                         }
                     }
-                    if (tap == taps - 1) mbar_arrive(&bar_afree[s]);      // last tap is in registers: stage back to the producer
                     TCP_ADD(7);
                     if (pending >= 0) {
                         tmem_st_wait();
@@ -247,7 +280,12 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     tmem_st_32x16(dst, hi);
                     tmem_st_32x16(dst + 32, lo);
                     pending = t;
+                    // Stage back to the TMA producer only now: the tcgen05.st above consumed the registers of the last tap, so every
+                    // shared-memory load of this thread from the stage has completed (an arrive right behind the LDS *issue* is not
+                    // ordered after the loads' data phase)
+                    if (tap == taps - 1) mbar_arrive(&bar_afree[s]);
                 }
+                if (++s == p.sa) { s = 0; ph ^= 1; }
             }
         }
         if (pending >= 0) {
@@ -264,7 +302,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 384;
 #endif
         for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x, ++tcount) {
-            const int aset = tcount % NSETS, use = tcount / NSETS;
+            const int aset = NSETS == 2 ? (tcount & 1) : 0, use = NSETS == 2 ? (tcount >> 1) : tcount;
             int x0, y0, n0, nt;
             tile_origin(tile, x0, y0, n0, nt);
             const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;

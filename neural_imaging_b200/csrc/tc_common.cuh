@@ -208,4 +208,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, int a_mn_ma
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Optional in-kernel timing (build with -DNI_TC_PROFILE): CTA 0 accumulates clock64() spans per role into g_tc_prof
+// (slots 0-31: persistent gemm, 32-63: wgrad), read back with ni_tc_prof_read.
+#ifdef NI_TC_PROFILE
+static __device__ long long g_tc_prof[64];
+#define TCP_DECL long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0;
+#define TCP_START() do { if (tcp_on) tcp_t = clock64(); } while (0)
+#define TCP_ADD(i) do { if (tcp_on) { const long long n_ = clock64(); atomicAdd((unsigned long long*)&tc::g_tc_prof[i], (unsigned long long)(n_ - tcp_t)); tcp_t = n_; } } while (0)
+#else
+#define TCP_DECL
+#define TCP_START() do {} while (0)
+#define TCP_ADD(i) do {} while (0)
+#endif
+
 }  // namespace tc

@@ -70,3 +70,103 @@ extern "C" int ni_tma_probe(const float* x, int n, int h, int w, int c, int stag
     NI_LAUNCH_CHECK();
     return grid;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Probe 2: tcgen05.mma rate. One CTA per SM; one elected lane issues `rounds` x 12 back-to-back kind::tf32 MMAs (M = 128, N = n,
+// K = 8) on garbage operands, A from tensor memory (ts = 1) or shared memory (ts = 0), then commits and waits. Reports the cycles
+// per MMA of every CTA: the hardware floor the convolution main loops are measured against.
+namespace {
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int ts, int rounds, int nacc, long long* cycles_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    for (int i = threadIdx.x; i < (16384 + 32768 + 8192) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, n, 0, 0);
+        const uint64_t da0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024), db0 = make_smem_desc_sw128(smem_u32(smem + 16384), 16, 1024);
+        const uint32_t a_t = tmem + 448;       // 64 columns of A at the top of tensor memory
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+            const uint32_t d = tmem + (uint32_t)((r % nacc) * n);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        if (ts) umma_tf32_ts(d, a_t + ks * 8 + (j == 0 ? 32 : 0), db0 + (uint64_t)(ks * 2 + (j == 1 ? 256 : 0)), idesc, 1u);
+                        else umma_tf32(d, da0 + (uint64_t)(ks * 2), db0 + (uint64_t)(ks * 2 + (j == 1 ? 256 : 0)), idesc, 1u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0, 9);
+        const long long t2 = clock64();
+        if ((threadIdx.x & 31) == 0) { cycles_out[2 * blockIdx.x] = t1 - t0; cycles_out[2 * blockIdx.x + 1] = t2 - t0; }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// Probe 3: 1-D bulk copies (cp.async.bulk) global -> shared, `bytes` each, `depth` in flight, `copies` per CTA. same = 1: every CTA
+// reads the SAME source sequence (the weight stream of the convolution kernels), same = 0: every CTA its own region.
+__global__ void __launch_bounds__(32, 1) bulk_probe_kernel(const uint8_t* __restrict__ src, long long src_bytes, int bytes, int depth, int copies,
+                                                           int same, long long* cycles_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar[16];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 16; ++s) mbar_init(&bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const long long region = same ? 0 : (long long)blockIdx.x * bytes * copies;
+    const long long t0 = clock64();
+    for (int i = 0; i < copies + depth; ++i) {
+        if (i >= depth) mbar_wait(&bar[(i - depth) % depth], ((i - depth) / depth) & 1, 0);
+        if (i < copies) {
+            const int s = i % depth;
+            const long long off = (region + (long long)i * bytes) % (src_bytes - bytes);
+            mbar_expect_tx(&bar[s], bytes);
+            bulk_load_1d(smem + (size_t)s * bytes, src + (off & ~15LL), bytes, &bar[s]);
+        }
+    }
+    cycles_out[blockIdx.x] = clock64() - t0;
+}
+}  // namespace
+
+extern "C" int ni_mma_probe(int n, int ts, int rounds, int nacc, long long* cycles_out, int grid, cudaStream_t st) {
+    NI_REQUIRE(cycles_out && n >= 16 && n <= 256 && n % 16 == 0 && rounds > 0 && nacc >= 1 && nacc * n <= 448 && grid > 0, "ni_mma_probe: invalid arguments");
+    const size_t smem = 16384 + 32768 + 8192 + 1024;
+    NI_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mma_probe_kernel<<<grid, 128, smem, st>>>(n, ts, rounds, nacc, cycles_out);
+    NI_LAUNCH_CHECK();
+    return NI_OK;
+}
+
+extern "C" int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, long long* cycles_out, int grid,
+                             cudaStream_t st) {
+    NI_REQUIRE(src && cycles_out && bytes >= 1024 && bytes % 16 == 0 && depth >= 1 && depth <= 16 && (size_t)depth * bytes <= 200 * 1024 && copies > 0 &&
+                   src_bytes > 2LL * bytes && grid > 0, "ni_bulk_probe: invalid arguments");
+    const size_t smem = (size_t)depth * bytes + 1024;
+    NI_CUDA(cudaFuncSetAttribute(bulk_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bulk_probe_kernel<<<grid, 32, smem, st>>>(static_cast<const uint8_t*>(src), src_bytes, bytes, depth, copies, same, cycles_out);
+    NI_LAUNCH_CHECK();
+    return NI_OK;
+}

@@ -1,0 +1,309 @@
+"""Training-data feed of the B200 path — mirror of the reference's `helpers/dataset.py:13-131` and
+`helpers/loading.py:132-211` for data that is already in memory.
+
+What changes against the reference (which crops on the host, converts to float64, divides and ships 268 MB of float32
+per 256-patch step over PCIe):
+
+* the full-resolution training set stays **resident in HBM as integers** (uint16 RGGB stacks, uint8 RGB; 120 6-MP images
+  are 3.5 GB of the 180 GB); `next_training_batch_device` draws the patch positions on the host exactly like the reference
+  (same `np.random` call sequence, same discard policies) and one gather kernel (`ni_feed_gather`) cuts and converts all
+  patches of the batch on the device — only (image, y, x) triples cross the bus;
+* the patch statistics of the discard policies come from per-image integral images (exact integer sums, O(1) per candidate
+  instead of a float64 pass over the patch);
+* `DeviceFeed` double-buffers host batches (float32, or the stored uint16 / uint8 = 4x fewer bytes) through a copy stream so
+  that the transfer of step i + 1 overlaps the compute of step i.
+
+File discovery / PNG / NPY loading (`helpers/loading.py:17-129`) is I/O tooling outside the hot path: use `Dataset.from_arrays`.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from ..tensor import device, ptr, wrap
+
+DISCARD_MODES = (None, 'flat', 'flat-aggressive', 'dark-n-textured')
+
+
+class PatchStats:
+    """Mean / variance of any axis-aligned patch of one uint8 image in O(1) (integral images of sum v and sum v^2 over channels)."""
+
+    def __init__(self, rgb_u8):
+        v = rgb_u8.astype(np.int64)
+        self.c = rgb_u8.shape[2] if rgb_u8.ndim == 3 else 1
+        s1 = v.sum(axis=2) if rgb_u8.ndim == 3 else v
+        s2 = (v * v).sum(axis=2) if rgb_u8.ndim == 3 else v * v
+        self.i1 = np.zeros((s1.shape[0] + 1, s1.shape[1] + 1), dtype=np.int64)
+        self.i2 = np.zeros_like(self.i1)
+        np.cumsum(np.cumsum(s1, axis=0), axis=1, out=self.i1[1:, 1:])
+        np.cumsum(np.cumsum(s2, axis=0), axis=1, out=self.i2[1:, 1:])
+
+    @staticmethod
+    def _box(ii, y, x, p):
+        return int(ii[y + p, x + p] - ii[y, x + p] - ii[y + p, x] + ii[y, x])
+
+    def mean_var(self, y, x, p):
+        """(mean, variance) of image[y:y+p, x:x+p] / 255 — what np.mean / np.var return for the reference's float patch."""
+        n = float(p * p * self.c)
+        m = self._box(self.i1, y, x, p) / n / 255.0
+        q = self._box(self.i2, y, x, p) / n / (255.0 * 255.0)
+        return m, max(q - m * m, 0.0)
+
+
+def sample_patch(rgb_image, rgb_patch_size=128, discard=None, max_attempts=25, stats=None):
+    """Top-left (x, y) of one training patch (reference `helpers/loading.py:132-211`): even coordinates (Bayer alignment), drawn
+    with the global `np.random` stream in the reference's order (x first, then y; one extra uniform() only in the middle band of
+    'flat'). `stats` (PatchStats) replaces the float64 pass over every candidate patch."""
+    h, w = rgb_image.shape[0], rgb_image.shape[1]
+    room_x, room_y = w - rgb_patch_size, h - rgb_patch_size
+    if room_x <= 0 and room_y <= 0:
+        return 0, 0
+
+    def measure(px, py):
+        if stats is not None:
+            return stats.mean_var(py, px, rgb_patch_size)
+        patch = rgb_image[py:py + rgb_patch_size, px:px + rgb_patch_size].astype(np.float64) / 255
+        return float(np.mean(patch)), float(np.var(patch))
+
+    attempts_left = max_attempts
+    fallback = None                      # best rejected candidate so far: (x, y, mean, var)
+    while True:
+        px = 2 * (np.random.randint(0, room_x) // 2) if room_x > 0 else 0
+        py = 2 * (np.random.randint(0, room_y) // 2) if room_y > 0 else 0
+        if not discard:
+            return px, py
+        mean, var = measure(px, py)
+        if discard == 'flat':
+            if var >= 0.01:
+                return px, py
+            if var >= 0.005:
+                if np.random.uniform() > 0.5:
+                    return px, py
+                continue
+            attempts_left -= 1
+            if attempts_left <= 0:
+                return px, py
+        elif discard == 'flat-aggressive':
+            if var >= 0.02:
+                return px, py
+            if attempts_left == max_attempts or var > fallback[3]:
+                fallback = (px, py, mean, var)
+            attempts_left -= 1
+            if attempts_left <= 0:
+                return fallback[0], fallback[1]
+        elif discard == 'dark-n-textured':
+            if 0 < var < 0.005 and 0.35 < mean < 0.99:
+                return px, py
+            if attempts_left == max_attempts or (var < 2 * fallback[3] and mean > 1.1 * fallback[2]):
+                fallback = (px, py, mean, var)
+            attempts_left -= 1
+            if attempts_left <= 0:
+                return fallback[0], fallback[1]
+        else:
+            raise ValueError('Unrecognized discard mode: {}'.format(discard))
+
+
+class Dataset(object):
+    """In-memory RAW / RGB training set with the reference's batch interface (`helpers/dataset.py:13-160`).
+
+    `data['training']['x']`: (n, H/2, W/2, 4) uint16 RGGB stacks, `['y']`: (n, H, W, 3) uint8 RGB (either may be absent, `load`
+    = 'xy' | 'x' | 'y'); `data['validation']` holds pre-cut patches of the same dtypes.
+    """
+
+    def __init__(self, training, validation=None, load='xy', fast_stats=True):
+        if load not in ('xy', 'x', 'y'):
+            raise ValueError('Invalid X/Y data requested!')
+        for k in load:
+            if k not in training:
+                raise ValueError('training data lacks {!r}'.format(k))
+        self._loaded_data = load
+        self.data = {'training': {k: np.ascontiguousarray(training[k]) for k in load},
+                     'validation': {k: np.ascontiguousarray(validation[k]) for k in load} if validation else {}}
+        if 'y' in self.data['training']:
+            self.H, self.W = self.data['training']['y'].shape[1:3]
+        else:
+            self.H, self.W = (2 * d for d in self.data['training']['x'].shape[1:3])
+        self._fast_stats = fast_stats
+        self._stats = {}
+        self._resident = {}
+        self._coords = None
+
+    @classmethod
+    def from_arrays(cls, x=None, y=None, val_x=None, val_y=None, **kw):
+        load = ('x' if x is not None else '') + ('y' if y is not None else '')
+        tr = {k: v for k, v in (('x', x), ('y', y)) if v is not None}
+        va = {k: v for k, v in (('x', val_x), ('y', val_y)) if v is not None}
+        return cls(tr, va or None, load=load, **kw)
+
+    def __getitem__(self, key):
+        if key in ('training', 'validation'):
+            return self.data[key]
+        raise KeyError('Key: {} not found!'.format(key))
+
+    def __len__(self):
+        return len(next(iter(self.data['training'].values())))
+
+    # ---- patch positions (host; identical random stream to the reference)
+    def _positions(self, batch_id, batch_size, rgb_patch_size, discard, max_attempts):
+        tr = self.data['training']
+        if discard is not None and 'y' not in tr:
+            raise ValueError('Cannot discard patches if RGB data is not loaded.')
+        if (batch_id + 1) * batch_size > len(self):
+            raise ValueError('Not enough images for the requested batch_id & batch_size')
+        out = np.empty((batch_size, 3), dtype=np.int32)
+        for b in range(batch_size):
+            bid = batch_id * batch_size + b
+            if 'y' in tr:
+                img = tr['y'][bid]
+                st = None
+                if self._fast_stats and discard:
+                    st = self._stats.get(bid)
+                    if st is None:
+                        st = self._stats[bid] = PatchStats(img)
+                xx, yy = sample_patch(img, rgb_patch_size, discard, max_attempts, stats=st)
+            else:                     # RAW only: the reference indexes data['training']['y'] and fails; positions from the RAW size
+                xx, yy = sample_patch(np.empty((self.H, self.W, 0), dtype=np.uint8), rgb_patch_size, None, max_attempts)
+            out[b] = (bid, yy, xx)
+        return out
+
+    # ---- the reference's host path (float32 numpy batches)
+    def next_training_batch(self, batch_id, batch_size, rgb_patch_size, discard='flat', max_attempts=25):
+        pos = self._positions(batch_id, batch_size, rgb_patch_size, discard, max_attempts)
+        tr, rp = self.data['training'], rgb_patch_size // 2
+        bx = np.zeros((batch_size, rp, rp, 4), dtype=np.float32) if 'x' in tr else None
+        by = np.zeros((batch_size, rgb_patch_size, rgb_patch_size, 3), dtype=np.float32) if 'y' in tr else None
+        for b, (bid, yy, xx) in enumerate(pos):
+            if bx is not None:
+                bx[b] = tr['x'][bid][yy // 2:yy // 2 + rp, xx // 2:xx // 2 + rp].astype(np.float64) / (2 ** 16 - 1)
+            if by is not None:
+                by[b] = tr['y'][bid][yy:yy + rgb_patch_size, xx:xx + rgb_patch_size].astype(np.float64) / (2 ** 8 - 1)
+        return self._pack(bx, by)
+
+    def _pack(self, bx, by):
+        if self._loaded_data == 'xy':
+            return bx, by
+        return by if self._loaded_data == 'y' else bx
+
+    # ---- the B200 path: same positions, patches cut from the HBM-resident integers by one kernel per modality
+    def to_device(self):
+        """Upload the training images once (integers, as stored). Idempotent."""
+        for k, a in self.data['training'].items():
+            if k not in self._resident:
+                if a.dtype not in (np.uint8, np.uint16):
+                    raise ValueError('resident feed needs uint8 / uint16 images, got {}'.format(a.dtype))
+                t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)       # torch has no uint16 arithmetic; bytes only
+                self._resident[k] = t.to(device())
+        return self
+
+    def next_training_batch_device(self, batch_id, batch_size, rgb_patch_size, discard='flat', max_attempts=25, out=None):
+        """Device tensors (x: (B,p/2,p/2,4), y: (B,p,p,3), float32 in [0,1]) bit-identical to `next_training_batch`."""
+        self.to_device()
+        pos = self._positions(batch_id, batch_size, rgb_patch_size, discard, max_attempts)
+        L, st = _lib.lib(), torch.cuda.current_stream().cuda_stream
+        res, tr, rp = {}, self.data['training'], rgb_patch_size // 2
+        if 'x' in tr:
+            half = pos.copy()
+            half[:, 1:] //= 2
+            cx = torch.from_numpy(half).to(device(), non_blocking=True)
+            n, h, w, c = tr['x'].shape
+            ox = out[0] if out is not None else torch.empty((batch_size, rp, rp, c), dtype=torch.float32, device=device())
+            L.ni_feed_gather(ptr(self._resident['x']), tr['x'].dtype.itemsize, n, h, w, c, ptr(cx), batch_size, rp, rp, float(2 ** 16 - 1 if tr['x'].dtype == np.uint16 else 255), ptr(ox), st)
+            res['x'] = wrap(ox)
+        if 'y' in tr:
+            cy = torch.from_numpy(pos).to(device(), non_blocking=True)
+            n, h, w, c = tr['y'].shape
+            oy = (out[1] if self._loaded_data == 'xy' else out[0]) if out is not None else torch.empty((batch_size, rgb_patch_size, rgb_patch_size, c), dtype=torch.float32, device=device())
+            L.ni_feed_gather(ptr(self._resident['y']), tr['y'].dtype.itemsize, n, h, w, c, ptr(cy), batch_size, rgb_patch_size, rgb_patch_size, float(255 if tr['y'].dtype == np.uint8 else 2 ** 16 - 1), ptr(oy), st)
+            res['y'] = wrap(oy)
+        return self._pack(res.get('x'), res.get('y'))
+
+    def next_validation_batch(self, batch_id, batch_size):
+        va = self.data['validation']
+        sl = slice(batch_id * batch_size, (batch_id + 1) * batch_size)
+        bx = (va['x'][sl].astype(np.float64) / (2 ** 16 - 1)).astype(np.float32) if 'x' in va else None
+        by = (va['y'][sl].astype(np.float64) / (2 ** 8 - 1)).astype(np.float32) if 'y' in va else None
+        return self._pack(bx, by)
+
+    def is_raw_and_rgb(self):
+        return self._loaded_data == 'xy'
+
+    def summary(self):
+        tr = self.data['training']
+        return 'Dataset[{}]: {} training images {}x{}'.format(self._loaded_data, len(self), self.H, self.W) + \
+               ''.join(', {}: {} {}'.format(k, v.dtype, v.shape) for k, v in tr.items())
+
+
+_DENOM = {torch.uint8: 255.0, torch.int16: 65535.0}
+
+
+class DeviceFeed(object):
+    """Double-buffered host -> device feed of (x, y) training batches.
+
+        feed = DeviceFeed()
+        feed.submit(x0, y0)                      # pinned host tensors / numpy arrays: float32, or the stored uint16 (x) / uint8 (y)
+        for i in range(steps):
+            x, y = feed.next()                   # compute stream now waits for batch i
+            feed.submit(x_next, y_next)          # H2D of batch i + 1 runs on the copy stream under the compute of batch i
+            flow.training_step_device(x, y, ...)
+
+    Integer batches are converted by `ni_feed_convert` on the copy stream (float(v) / 65535 or / 255: identical to the reference's
+    host conversion). Slots are recycled: `next()` returns views that stay valid until the second `submit` after it.
+    """
+
+    def __init__(self, depth=2):
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream()
+        self._slots = [dict() for _ in range(depth)]
+        self._ready = []                  # FIFO of (slot index, event)
+        self._free_at = [None] * depth    # event after which slot i may be overwritten (recorded on the compute stream)
+        self._w = 0
+        self.h2d_bytes = 0
+
+    @staticmethod
+    def _host(t):
+        if isinstance(t, np.ndarray):
+            if t.dtype == np.uint16:
+                t = t.view(np.int16)
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        return t
+
+    def _stage(self, slot, key, src):
+        src = self._host(src)
+        ent = slot.get(key)
+        if ent is None or ent['raw'].shape != src.shape or ent['raw'].dtype != src.dtype:
+            raw = torch.empty(src.shape, dtype=src.dtype, device=device())
+            ent = slot[key] = {'raw': raw, 'f32': raw if src.dtype == torch.float32 else torch.empty(src.shape, dtype=torch.float32, device=device())}
+        ent['raw'].copy_(src, non_blocking=True)
+        self.h2d_bytes += src.numel() * src.element_size()
+        if src.dtype != torch.float32:
+            if src.dtype not in _DENOM:
+                raise ValueError('DeviceFeed: unsupported batch dtype {}'.format(src.dtype))
+            _lib.lib().ni_feed_convert(ptr(ent['raw']), src.element_size(), ptr(ent['f32']), src.numel(), _DENOM[src.dtype], self.copy_stream.cuda_stream)
+        return ent['f32']
+
+    def submit(self, *batches):
+        if len(self._ready) >= self.depth:
+            raise RuntimeError('DeviceFeed: all {} slots hold batches that were not consumed yet'.format(self.depth))
+        i = self._w
+        self._w = (self._w + 1) % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if self._free_at[i] is not None:
+                self.copy_stream.wait_event(self._free_at[i])      # the step that read this slot has finished
+            outs = tuple(self._stage(self._slots[i], k, b) for k, b in enumerate(batches))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._ready.append((i, ev, outs))
+
+    def next(self):
+        if not self._ready:
+            raise RuntimeError('DeviceFeed.next() without a submitted batch')
+        i, ev, outs = self._ready.pop(0)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        self._last = i
+        return outs if len(outs) > 1 else outs[0]
+
+    def release(self):
+        """Mark the batch returned by the last `next()` as consumed by everything enqueued so far on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._free_at[self._last] = ev

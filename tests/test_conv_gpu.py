@@ -254,3 +254,41 @@ def test_tc_path_is_taken_and_matches_simt():
         L.ni_conv2d_wgrad_tc(ctypes.byref(d), ptr(x), ptr(dy), ptr(dw_tc), stream())
         L.ni_conv2d_wgrad_simt(ctypes.byref(d), ptr(x), ptr(dy), ptr(dw_si), stream())
         assert_parity(dw_tc.cpu().numpy(), dw_si.cpu().numpy(), tol=2e-5, what='wgrad tc vs simt')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(1, 256, 256, 32, 32, 3), (1, 256, 256, 64, 64, 3), (1, 256, 256, 32, 64, 5), (1, 256, 256, 64, 32, 3),
+                                   (16, 64, 64, 128, 128, 3), (8, 128, 128, 32, 32, 3), (20, 64, 64, 32, 64, 5)])
+def test_persistent_gemm_many_tiles_per_cta(shape):
+    """More pixel tiles than SMs: every persistent CTA walks several tiles (stage / slot / accumulator-set recycling, resident and
+    streamed weights). Cold launches into fresh output buffers, repeated: a stage handed back to the TMA producer too early showed
+    up as corrupted rows in the SECOND tile of a CTA on the first launches of a process only."""
+    from neural_imaging_b200 import _lib, nn
+    from neural_imaging_b200.tensor import as_device, ptr, stream
+    L = _lib.lib()
+    n, h, w, cin, cout, k = shape
+    rs = np.random.RandomState(11)
+    st = nn.ParamStore()
+    conv = nn.Conv2D(st, 'c', k, cin, cout, activation='relu', rng=rs)
+    st.finalize()
+    d = conv.desc(n, h, w)
+    x = as_device(rs.normal(size=(n, h, w, cin)).astype(np.float32))
+    dy = as_device(rs.normal(size=(n, h, w, cout)).astype(np.float32))
+    y_si = torch.empty((n, h, w, cout), device='cuda')
+    dx_si = torch.empty((n, h, w, cin), device='cuda')
+    L.ni_conv2d_fprop_simt(ctypes.byref(d), ptr(x), ptr(conv.w.value), ptr(conv.b.value), ptr(y_si), stream())
+    L.ni_conv2d_set_force_simt(1)
+    L.ni_conv2d_dgrad(ctypes.byref(d), ptr(dy), ptr(conv.w.value), ptr(dx_si), stream())
+    L.ni_conv2d_set_force_simt(-1)
+    scale_y, scale_dx = float(y_si.abs().max()), float(dx_si.abs().max())
+    keep = []
+    for rep in range(3):
+        y = torch.full((n, h, w, cout), 777.0, device='cuda')          # fresh buffers on purpose
+        dx = torch.full((n, h, w, cin), 777.0, device='cuda')
+        keep.append((y, dx))
+        L.ni_conv2d_fprop_tc(ctypes.byref(d), ptr(x), ptr(conv.w.value), ptr(conv.b.value), ptr(y), stream())
+        L.ni_conv2d_dgrad_tc(ctypes.byref(d), ptr(dy), ptr(conv.w.value), ptr(dx), stream())
+        ey = float((y - y_si).abs().max()) / scale_y
+        edx = float((dx - dx_si).abs().max()) / scale_dx
+        assert ey <= 1e-5, 'fprop rep {}: relative error {:.3e}'.format(rep, ey)
+        assert edx <= 1e-5, 'dgrad rep {}: relative error {:.3e}'.format(rep, edx)
