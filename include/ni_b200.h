@@ -135,7 +135,8 @@ int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d
 int ni_tma_probe(const float* x, int n, int h, int w, int c, int stages, int boxes_per_cta, long long* cycles_out, int max_grid, ni_stream_t stream);
 /* measurement probes (tools/): tcgen05.mma issue / execution rate; 1-D bulk-copy (weight stream) ingest rate per SM */
 int ni_mma_probe(int n, int ts, int rounds, int nacc, long long* cycles_out, int grid, ni_stream_t stream);
-int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, long long* cycles_out, int grid, ni_stream_t stream);
+int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, int warps, long long* cycles_out, int grid,
+                  ni_stream_t stream);
 /* debug: per-role clock64 spans of the persistent tcgen05 gemm [0,32) and of the wgrad kernel [32,64) (zeros unless built with -DNI_TC_PROFILE) */
 int ni_tc_prof_read(long long* out64, int reset);
 void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */

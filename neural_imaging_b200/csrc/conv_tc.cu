@@ -23,6 +23,7 @@
 #include "conv_desc.h"
 #include "conv_tc_v2.cuh"
 #include "conv_tc_v3.cuh"
+#include "conv_tc_wgrad3.cuh"
 #include "ni_common.cuh"
 #include "tc_common.cuh"
 
@@ -363,6 +364,7 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     p.cin_chunks = d->cin / 32; p.atoms = taps * p.cin_chunks; p.mtot = taps * d->cin; p.cout = d->cout;
     p.steps_total = p.tiles_w * p.tiles_h * (d->n / p.bn);
     p.dw = dw;
+    p.defer_st = 0;
     const int bnt = pick_bnt(d->cout);
     const int mtiles = (p.atoms + 3) / 4, ntiles = d->cout / bnt;
     // split-K over pixel ranges. Cost model (us): waves x steps per CTA x t_iter + per-wave fixed cost + the cross-CTA reduction
@@ -370,7 +372,9 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     // (16 KB of A + BNT x 128 B of B per 32 pixels ~ 3.5 TB/s over 148 SMs), measured 1.4 - 1.8 us for every tile width. The old rule (always
     // ~4 waves) made the 1x1 transposed-conv layers reduction-bound: 592 CTAs x 16 K atomics for 28 iterations of work each.
     // Chains are capped at 2048 steps (65 K pixels) to bound the truncation bias of the in-TMEM accumulation.
-    const int tiles = mtiles * ntiles, sms = ni_num_sms() * (bnt == 128 ? 1 : 2);   // resident CTAs (BNT <= 64: two per SM)
+    static const bool wgrad_v2 = getenv("NI_TC_WGRAD_V2") != nullptr;      // generation 2 kernel (one producer thread, two CTAs per SM for N <= 64)
+    const int tiles = mtiles * ntiles, sms = ni_num_sms() * ((bnt == 128 || !wgrad_v2) ? 1 : 2);   // resident CTAs
+    const double t_iter = wgrad_v2 ? 1.5 : 0.7;                             // us per 32-pixel step of one CTA
     const int min_splits = (p.steps_total + 2047) / 2048;
     int max_splits = (p.steps_total + 15) / 16;
     if (max_splits > 1024) max_splits = 1024;
@@ -381,15 +385,38 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
         const int per = (p.steps_total + sp - 1) / sp;
         const int eff = (p.steps_total + per - 1) / per;
         const int waves = (tiles * eff + sms - 1) / sms;
-        const double cost = waves * (per * 1.5 + 6.0) + (double)eff * p.mtot * d->cout / 50e3;
+        const double cost = waves * (per * t_iter + 6.0) + (double)eff * p.mtot * d->cout / 50e3;
         if (cost < best) { best = cost; splits = eff; }
     }
     p.steps_per_split = (p.steps_total + splits - 1) / splits;
     splits = (p.steps_total + p.steps_per_split - 1) / p.steps_per_split;
     dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
     if (getenv("NI_TC_DEBUG"))
-        fprintf(stderr, "tc wgrad<%d>: grid (%d, %d, %d), steps %d total, %d per split, atoms %d\n", bnt, mtiles, ntiles, splits, p.steps_total,
-                p.steps_per_split, p.atoms);
+        fprintf(stderr, "tc wgrad<%d>%s: grid (%d, %d, %d), steps %d total, %d per split, atoms %d\n", bnt, wgrad_v2 ? " v2" : "", mtiles, ntiles, splits,
+                p.steps_total, p.steps_per_split, p.atoms);
+    if (!wgrad_v2) {
+#define NI_TC_WGRAD3(B, NPW)                                                                                   \
+    {                                                                                                          \
+        using C = tcw3::Cfg<B, NPW>;                                                                           \
+        const size_t smem = (size_t)C::STAGES * C::STAGE_BYTES + 1024;                                         \
+        rc = set_dyn_smem(tcw3::conv_tc3_wgrad_kernel<B, NPW>, smem);                                          \
+        if (rc) return rc;                                                                                     \
+        tcw3::conv_tc3_wgrad_kernel<B, NPW><<<grid, C::THREADS, smem, st>>>(tmX, tmDY, p);                     \
+    }
+        // producer warps per tile width (measured, tools/profile_conv.py): the copy engine's row rate (one 128-byte box row per ~4.5
+        // cycles) bounds a step, more issuing warps than needed to reach it only add polling
+        static const int np_env = getenv("NI_TC_WG_NP") ? atoi(getenv("NI_TC_WG_NP")) : 0;
+        const bool many = np_env > 4;        // measured: 4 producer warps are enough for every tile width (more only add polling)
+        static const int defer_env = getenv("NI_TC_WG_DEFER") ? atoi(getenv("NI_TC_WG_DEFER")) : -1;
+        p.defer_st = defer_env > 0 ? 1 : 0;   // measured: deferring the converters' tcgen05.st completion delays the MMA warp more than it hides (-10 .. -25 %)
+        if (bnt == 128) { if (many) NI_TC_WGRAD3(128, 8) else NI_TC_WGRAD3(128, 4) }
+        else if (bnt == 64) { if (many) NI_TC_WGRAD3(64, 6) else NI_TC_WGRAD3(64, 4) }
+        else { if (many) NI_TC_WGRAD3(32, 5) else NI_TC_WGRAD3(32, 4) }
+#undef NI_TC_WGRAD3
+        NI_LAUNCH_CHECK();
+        NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
 #define NI_TC_WGRAD(B)                                                                                         \
     {                                                                                                          \
         const size_t smem = (size_t)tcv2::WgCfg<B>::STAGES * (tcv2::kAraw + 3 * B * 128) + 1024;                      \

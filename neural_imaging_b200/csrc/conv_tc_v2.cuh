@@ -264,6 +264,7 @@ struct WgradParams {
     int steps_total, steps_per_split;
     float* dw;
     int dy_block2_f;               // > 0: dy is read through depth_to_space(2) (5-D map, see GemmParams::src_block2_f)
+    int defer_st;                  // generation 3: X converters complete their tcgen05.st behind the next step's loads
 };
 
 __device__ __forceinline__ void transpose_split_chunk(uint32_t raw, uint32_t hi, uint32_t lo, int row0, int r) {

@@ -45,6 +45,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int wh
     }
 }
 
+// Long waits (TMA producers waiting for a free stage): try_wait with a suspend-time hint, so that the waiting thread sleeps in hardware
+// instead of competing with the working warps for issue slots and shared-memory bandwidth.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int who) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("ni_b200: mbarrier timeout (role %d, block %d,%d,%d, thread %d, parity %u)\n", who, blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
 // Whole-warp wait: lane 0 polls, the warp reconverges behind it. 32 lanes polling the same mbarrier are 32 serialised shared-memory
 // operations (~180 cycles per wait measured with clock64 against ~40 for a single lane).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int who) {

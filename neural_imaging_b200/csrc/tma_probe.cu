@@ -123,31 +123,43 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int ts, int ro
     if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-// Probe 3: 1-D bulk copies (cp.async.bulk) global -> shared, `bytes` each, `depth` in flight, `copies` per CTA. same = 1: every CTA
-// reads the SAME source sequence (the weight stream of the convolution kernels), same = 0: every CTA its own region.
-__global__ void __launch_bounds__(32, 1) bulk_probe_kernel(const uint8_t* __restrict__ src, long long src_bytes, int bytes, int depth, int copies,
-                                                           int same, long long* cycles_out) {
+// Probe 3: 1-D bulk copies (cp.async.bulk) global -> shared, `bytes` each, `depth` in flight per issuing warp, `copies` per warp.
+// same = 1: every CTA reads the SAME source sequence (the weight stream of the convolution kernels), same = 0: its own region.
+// `warps` issuing warps per CTA (lane 0 of each, own barriers and buffers): is the ~735-cycle cost per copy a property of the
+// issuing thread or of the SM's copy engine?
+__global__ void __launch_bounds__(256, 1) bulk_probe_kernel(const uint8_t* __restrict__ src, long long src_bytes, int bytes, int depth, int copies,
+                                                            int same, int warps, long long* cycles_out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar[16];
+    __shared__ uint64_t bar[8][8];
+    __shared__ long long t_end[8];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 16; ++s) mbar_init(&bar[s], 1);
+        for (int w = 0; w < 8; ++w) for (int s = 0; s < 8; ++s) mbar_init(&bar[w][s], 1);
         fence_barrier_init();
     }
-    __syncwarp();
-    if (threadIdx.x != 0) return;
-    const long long region = same ? 0 : (long long)blockIdx.x * bytes * copies;
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
     const long long t0 = clock64();
-    for (int i = 0; i < copies + depth; ++i) {
-        if (i >= depth) mbar_wait(&bar[(i - depth) % depth], ((i - depth) / depth) & 1, 0);
-        if (i < copies) {
-            const int s = i % depth;
-            const long long off = (region + (long long)i * bytes) % (src_bytes - bytes);
-            mbar_expect_tx(&bar[s], bytes);
-            bulk_load_1d(smem + (size_t)s * bytes, src + (off & ~15LL), bytes, &bar[s]);
+    if ((threadIdx.x & 31) == 0 && w < warps) {
+        const long long region = (same ? 0 : (long long)blockIdx.x * bytes * copies * warps) + (long long)w * bytes * copies;
+        uint8_t* buf = smem + (size_t)w * depth * bytes;
+        for (int i = 0; i < copies + depth; ++i) {
+            if (i >= depth) mbar_wait(&bar[w][(i - depth) % depth], ((i - depth) / depth) & 1, 0);
+            if (i < copies) {
+                const int s = i % depth;
+                const long long off = (region + (long long)i * bytes) % (src_bytes - bytes);
+                mbar_expect_tx(&bar[w][s], bytes);
+                bulk_load_1d(buf + (size_t)s * bytes, src + (off & ~15LL), bytes, &bar[w][s]);
+            }
         }
+        t_end[w] = clock64() - t0;
     }
-    cycles_out[blockIdx.x] = clock64() - t0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long m = 0;
+        for (int i = 0; i < warps; ++i) m = t_end[i] > m ? t_end[i] : m;
+        cycles_out[blockIdx.x] = m;
+    }
 }
 }  // namespace
 
@@ -160,13 +172,13 @@ extern "C" int ni_mma_probe(int n, int ts, int rounds, int nacc, long long* cycl
     return NI_OK;
 }
 
-extern "C" int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, long long* cycles_out, int grid,
-                             cudaStream_t st) {
-    NI_REQUIRE(src && cycles_out && bytes >= 1024 && bytes % 16 == 0 && depth >= 1 && depth <= 16 && (size_t)depth * bytes <= 200 * 1024 && copies > 0 &&
-                   src_bytes > 2LL * bytes && grid > 0, "ni_bulk_probe: invalid arguments");
-    const size_t smem = (size_t)depth * bytes + 1024;
+extern "C" int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, int warps, long long* cycles_out,
+                             int grid, cudaStream_t st) {
+    NI_REQUIRE(src && cycles_out && bytes >= 1024 && bytes % 16 == 0 && depth >= 1 && depth <= 8 && warps >= 1 && warps <= 8 &&
+                   (size_t)warps * depth * bytes <= 200 * 1024 && copies > 0 && src_bytes > 2LL * bytes && grid > 0, "ni_bulk_probe: invalid arguments");
+    const size_t smem = (size_t)warps * depth * bytes + 1024;
     NI_CUDA(cudaFuncSetAttribute(bulk_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bulk_probe_kernel<<<grid, 32, smem, st>>>(static_cast<const uint8_t*>(src), src_bytes, bytes, depth, copies, same, cycles_out);
+    bulk_probe_kernel<<<grid, 256, smem, st>>>(static_cast<const uint8_t*>(src), src_bytes, bytes, depth, copies, same, warps, cycles_out);
     NI_LAUNCH_CHECK();
     return NI_OK;
 }

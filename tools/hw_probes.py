@@ -16,15 +16,15 @@ for grid in (1, 148):
                 torch.cuda.synchronize()
                 c = cyc[:2 * grid].view(grid, 2).float().median(dim=0).values / (12 * rounds)
                 print('grid %3d  A from %s  N %3d  accumulators %d: issue %.1f  complete %.1f' % (grid, 'TMEM' if ts else 'smem', n, nacc, float(c[0]), float(c[1])))
-print('== cp.async.bulk 1-D global->shared: bytes/clk per CTA (one CTA per SM), median over CTAs')
+print('== cp.async.bulk 1-D global->shared: cycles per copy and bytes/clk per SM (one CTA per SM), median over CTAs')
 src = torch.empty(1 << 30, dtype=torch.uint8, device='cuda')
 for same in (1, 0):
-    for bytes_ in (8192, 16384, 32768):
-        for depth in (1, 2, 4, (6 if bytes_ == 32768 else 8)):
-            copies = 256
-            for grid in (148,):
-                L.ni_bulk_probe(ptr(src), (1 << 21) if same else src.numel(), bytes_, depth, copies, same, ptr(cyc), grid, stream())
-                L.ni_bulk_probe(ptr(src), (1 << 21) if same else src.numel(), bytes_, depth, copies, same, ptr(cyc), grid, stream())
-                torch.cuda.synchronize()
-                c = float(cyc[:grid].float().median())
-                print('%s source  copy %5d B  depth %d: %.0f clk/copy, %.1f B/clk/CTA' % ('same' if same else 'own ', bytes_, depth, c / copies, bytes_ * copies / c))
+    for bytes_, depth, warps in ((8192, 4, 1), (16384, 4, 1), (32768, 4, 1), (4096, 4, 1), (4096, 4, 2), (4096, 4, 4), (8192, 4, 2), (8192, 4, 4), (16384, 2, 2), (16384, 2, 4),
+                                 (32768, 2, 2), (32768, 1, 4), (65536, 2, 1)):
+        copies, grid = 256, 148
+        for _ in range(2):
+            L.ni_bulk_probe(ptr(src), (1 << 21) if same else src.numel(), bytes_, depth, copies, same, warps, ptr(cyc), grid, stream())
+        torch.cuda.synchronize()
+        c = float(cyc[:grid].float().median())
+        print('%s source  copy %5d B  depth %d  issuing warps %d: %.0f clk per copy (per warp), %.1f B/clk/SM' % (
+            'same' if same else 'own ', bytes_, depth, warps, c / copies, bytes_ * copies * warps / c))
