@@ -5,7 +5,8 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (restated; TF absent)
 
 Prints ONE JSON line (rank 0). `value` = raw 128x128 patches / s with inputs resident in HBM; `e2e` = the same through
-ManipulationClassification.training_step with pinned-host inputs (H2D inside the timed region) and a D2H loss read.
+helpers.dataset.DeviceFeed + ManipulationClassification.training_step_device with pinned-host inputs (H2D of every
+step inside the timed region, overlapped with the previous step's compute) and a D2H loss read.
 Global batch is fixed at 256 raw patches (strong scaling): each rank processes 256/N patches = 1280/N codec/FAN images.
 """
 import argparse
@@ -206,17 +207,34 @@ def run_ours(args, rank, world, local_rank):
         launches = flow.graph_launches_per_step * args.steps
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, through the public training_step()
-    xe, ye = torch.empty_like(xd), torch.empty_like(yd)
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step, through the public API a training loop uses:
+    # helpers.dataset.DeviceFeed (double-buffered: the H2D copy of batch i + 1 is enqueued on the copy stream before step i is
+    # launched, so it runs under that step's compute) + ManipulationClassification.training_step_device + loss.numpy()
+    from neural_imaging_b200.helpers.dataset import DeviceFeed
 
-    def step_e2e():
-        xe.copy_(xp, non_blocking=True)
-        ye.copy_(yp, non_blocking=True)
-        loss, _ = flow.training_step_device(xe, ye, LAMBDA_NIP, 0, False, LR, grad_sync=sync)
-        return float(loss.numpy())            # device -> host read of the step's loss (synchronises)
+    def make_e2e(hx, hy):
+        feed = DeviceFeed()
+        feed.submit(hx, hy)
+
+        def step():
+            xe, ye = feed.next()
+            feed.submit(hx, hy)                   # next step's inputs: same pinned buffers, a full H2D copy every step
+            loss, _ = flow.training_step_device(xe, ye, LAMBDA_NIP, 0, False, LR, grad_sync=sync)
+            feed.release()
+            return float(loss.numpy())            # device -> host read of the step's loss (synchronises)
+        return step, feed
+    step_e2e, feed32 = make_e2e(xp, yp)
     for _ in range(2):
         last = step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # same with the batches in their stored integer form (uint16 RGGB stacks, uint8 RGB: helpers/loading.py:69-71): 4x fewer
+    # bytes over PCIe, converted on the device by ni_feed_convert (bit-identical to the reference's host conversion)
+    xi = torch.from_numpy(np.round(xh * 65535).astype(np.uint16).view(np.int16)).pin_memory()
+    yi = torch.from_numpy(np.round(yh * 255).astype(np.uint8)).pin_memory()
+    step_e2e_int, feed_int = make_e2e(xi, yi)
+    for _ in range(2):
+        step_e2e_int()
+    ms_e2e_int = timed(step_e2e_int, args.steps)
     if flow._optimizer.nonfinite():
         raise RuntimeError('non-finite gradients during the benchmark')
 
@@ -285,7 +303,11 @@ def run_ours(args, rank, world, local_rank):
                    'global_batch': gb, 'per_gpu_batch': bl, 'codec_fan_images_per_step': 5 * gb, 'parallelism': 'dp%d' % world,
                    'l2': 'working set (multi-GB activations per step) >> 126 MB L2; no explicit flush needed'},
         'e2e': {'value': gb / (ms_e2e * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms_e2e,
-                'h2d_bytes_per_step': int(xp.numel() * 4 + yp.numel() * 4) * world, 'd2h_bytes_per_step': 4 * world},
+                'h2d_bytes_per_step': int(xp.numel() * 4 + yp.numel() * 4) * world, 'd2h_bytes_per_step': 4 * world,
+                'api': 'helpers.dataset.DeviceFeed (float32 host batches, H2D of step i+1 under the compute of step i) -> training_step_device -> loss.numpy()'},
+        'e2e_integer_feed': {'value': gb / (ms_e2e_int * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms_e2e_int,
+                             'h2d_bytes_per_step': int(xi.numel() * 2 + yi.numel()) * world, 'd2h_bytes_per_step': 4 * world,
+                             'api': 'as e2e, host batches as stored (uint16 RAW / uint8 RGB), converted on the device (ni_feed_convert)'},
         'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'cuda_graph': not args.no_graph,
         'host_enqueue_ms_per_step': host_ms.get('step_resident'), 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:12],
         'images_per_sec_codec_fan': 5 * gb / (ms * 1e-3), 'loss': float(loss.numpy()),

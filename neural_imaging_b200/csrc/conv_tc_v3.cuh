@@ -132,8 +132,12 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 }
             }
         }
-    } else if (warp == 2) {
-        if (lane == 0) {   // ---- B producer: pre-tiled [hi | lo] weight tiles of G consecutive k-iterations per bulk copy
+    } else if (warp == 2 || (warp == 3 && ISSUERS == 1)) {
+        // ---- B producer(s): pre-tiled [hi | lo] weight tiles of G consecutive k-iterations per bulk copy. A copy occupies its ISSUING
+        // thread for ~735 - 870 cycles (tools/hw_probes.py), about one N = 128 iteration of MMAs, so where warp 3 is not an MMA issuer
+        // (N = 128) it takes every other group.
+        if (lane == 0) {
+            const int nbp = ISSUERS == 1 ? 2 : 1, pb = warp == 2 ? 0 : 1;
             int gg = 0;
             TCP_DECL
             for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
@@ -141,6 +145,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 const int nt = tile / q.mtiles;
                 const float* src = wtiled + (size_t)nt * iters * (size_t)(2 * BNT * 32);
                 for (int g = 0; g < ngroups; ++g, ++gg) {
+                    if (nbp == 2 && (gg & 1) != pb) continue;
                     const int s = q.b_resident ? g : (gg & (q.sb - 1)), ph = q.b_resident ? 0 : ((gg >> q.log_sb) & 1);
                     const int n_it = min(G, iters - (g << LOG_G));
                     TCP_START();
@@ -152,7 +157,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 }
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (warp == 1 || (warp == 3 && ISSUERS == 2)) {
         const int iss = warp == 1 ? 0 : 1;
         if (iss < n_iss) {   // ---- MMA issuer(s): the whole warp walks the loop (uniform control flow), one elected lane issues
             constexpr uint32_t idesc = make_idesc_tf32(128, BNT, 0, 0);
