@@ -54,6 +54,14 @@ int ni_feed_convert(const void* src, int src_bytes, float* dst, long long n, flo
 int ni_feed_gather(const void* images, int src_bytes, int n_images, int h, int w, int c, const int* coords, int batch, int ph, int pw,
                    float denom, float* out, ni_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ metrics
+ * Structural similarity, one value per image: mean over the VALID region and the channels of the SSIM map built from a separable
+ * k-tap window (HOST pointer, k <= 15). Replaces tf.image.ssim(a, b, 1.0) (models/compression.py:89, helpers/tf_helpers.py:39-40):
+ * Gaussian 11 taps sigma 1.5, cov_norm 1, c1 = 1e-4, c2 = 9e-4; and helpers/metrics.py:9-26 (skimage structural_similarity,
+ * multichannel, data_range 1): uniform 7 taps, cov_norm 49/48, same constants. a, b: (n,h,w,c); out_n: n floats. */
+int ni_ssim(const float* a, const float* b, float* out_n, int n, int h, int w, int c, const float* win_host, int k, float cov_norm, float c1,
+            float c2, ni_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ manipulations
  * helpers/tf_helpers.py:68-184. All on (n,h,w,3). */
 /* manipulation_sharpen (tf_helpers.py:156-184): filt9 = HOST 3x3 filter applied to H and V; S takes tap [2,2]. */

@@ -59,6 +59,7 @@ struct PersistParams {
     int mtiles, total_tiles;       // pixel tiles, pixel tiles * n tiles
     int sb, log_sb;                // weight ring: stages (1, 2 or 4 groups) and log2; resident: groups per tile (ring unused)
     int b_resident;                // 1: the CTA's whole weight slice is loaded ONCE and stays in shared memory (single n tile)
+    int defer_st;                  // 1: converters complete their tcgen05.st one iteration later (behind the next loads + split)
 };
 
 template <int BNT>
@@ -285,6 +286,12 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     tmem_st_32x16(dst, hi);
                     tmem_st_32x16(dst + 32, lo);
                     pending = t;
+                    if (!q.defer_st) {
+                        tmem_st_wait();
+                        tcgen05_fence_before();
+                        mbar_arrive(&bar_tready[pending]);
+                        pending = -1;
+                    }
                     // Stage back to the TMA producer only now: the tcgen05.st above consumed the registers of the last tap, so every
                     // shared-memory load of this thread from the stage has completed (an arrive right behind the LDS *issue* is not
                     // ordered after the loads' data phase)

@@ -88,20 +88,10 @@ class DCN(TFModel):
 
     @staticmethod
     def ssim(a, b):
-        """mean tf.image.ssim(a, b, max_val=1): 11x11 Gaussian (sigma 1.5), VALID, k1=0.01, k2=0.03. Reporting metric only
-        (not on the gradient path); evaluated with plain tensor ops."""
-        a, b = as_device(a).permute(0, 3, 1, 2), as_device(b).permute(0, 3, 1, 2)
-        g = torch.arange(11, dtype=torch.float32, device=a.device) - 5.0
-        g = torch.exp(-g * g / (2 * 1.5 * 1.5))
-        g = (g / g.sum())
-        k = (g[:, None] * g[None, :]).expand(3, 1, 11, 11).contiguous()
-        f = lambda t: torch.nn.functional.conv2d(t, k, groups=3)
-        c1, c2 = 0.01 ** 2, 0.03 ** 2
-        ma, mb = f(a), f(b)
-        saa, sbb, sab = f(a * a) - ma * ma, f(b * b) - mb * mb, f(a * b) - ma * mb
-        lum = (2 * ma * mb + c1) / (ma * ma + mb * mb + c1)
-        cs = (2 * sab + c2) / (saa + sbb + c2)
-        return wrap((lum * cs).mean(dim=(2, 3)).mean(dim=1).mean())
+        """mean tf.image.ssim(a, b, max_val=1): 11x11 Gaussian (sigma 1.5), VALID, k1=0.01, k2=0.03 (reporting metric of the training
+        step, models/compression.py:89) — one fused kernel (csrc/metrics.cu) instead of five filtered copies of both images."""
+        from ..helpers import metrics
+        return wrap(metrics.ssim_tf(a, b).mean())
 
     # ---- public API (models/compression.py:106-139)
     def compress(self, batch_x):

@@ -3,10 +3,12 @@ training/validation.py:163-203 `validate_fan`, :82-160 `validate_nip` without th
 
 The reference runs batches of 10 through `flow.run_workflow_to_decisions` and builds the confusion matrix on the host with
 an n_classes^2 Python loop per batch; here the decisions stay one device->host read per batch and the matrix is one
-np.add.at. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does;
-SSIM (skimage) is not available offline and is reported as NaN.
+np.add.at. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does; SSIM
+(skimage structural_similarity in the reference, helpers/metrics.py:9-26) runs in the fused device kernel ni_ssim.
 """
 import numpy as np
+
+from ..helpers import metrics
 
 
 def validate_fan(flow, data, get_labels=False):
@@ -32,7 +34,7 @@ def validate_fan(flow, data, get_labels=False):
 
 
 def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type='L2'):
-    """Per-image (ssim, psnr, loss) lists of a NIP on the validation set (no figures; SSIM needs skimage -> NaN)."""
+    """Per-image (ssim, psnr, loss) lists of a NIP on the validation set (no figures)."""
     if loss_type not in ('L1', 'L2'):
         raise ValueError('Invalid loss! Use either L1 or L2.')
     ssims, psnrs, losss = [], [], []
@@ -42,6 +44,6 @@ def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type=
         reference = np.asarray(example_y).squeeze()
         mse = float(np.mean(np.power(reference - developed, 2.0)))
         psnrs.append(float(10.0 * np.log10(1.0 / mse)) if mse > 0 else float('inf'))
-        ssims.append(float('nan'))
+        ssims.append(metrics.ssim(reference, developed))
         losss.append(mse if loss_type == 'L2' else float(np.mean(np.abs(reference - developed))))
     return ssims, psnrs, losss

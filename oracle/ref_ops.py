@@ -409,3 +409,48 @@ def discrete_latent(z, scale, codebook, v=50, gamma=25):
 def l2_loss(t):
     """tf.nn.l2_loss."""
     return (t * t).sum() / 2
+
+
+# ---------------------------------------------------------------------------------------------------------------- SSIM
+def _window_moments(x, y, win):
+    """VALID separable filtering of x, y, x^2, y^2, xy with the 1-D window `win` along H and W (float64; arrays (H, W, C))."""
+    import scipy.ndimage as ndi
+    k = len(win)
+    lo, hi = k // 2, k - 1 - k // 2
+
+    def f(t):
+        t = ndi.correlate1d(t, win, axis=0, mode='constant')
+        t = ndi.correlate1d(t, win, axis=1, mode='constant')
+        return t[lo:t.shape[0] - hi, lo:t.shape[1] - hi]
+    return f(x), f(y), f(x * x), f(y * y), f(x * y)
+
+
+def ssim_tf(a, b, max_val=1.0):
+    """tf.image.ssim(a, b, max_val) restated (TF 2.1 python/ops/image_ops_impl.py: _fspecial_gauss(11, 1.5), VALID depthwise conv,
+    luminance * contrast-structure, mean over space then over channels), as called by models/compression.py:89. (N,H,W,C) -> (N,)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    x = np.arange(11, dtype=np.float64) - 5.0
+    g = np.exp(-0.5 * x * x / 1.5 ** 2)
+    g /= g.sum()
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    out = []
+    for i in range(a.shape[0]):
+        m0, m1, e00, e11, e01 = _window_moments(a[i], b[i], g)
+        lum = (2 * m0 * m1 + c1) / (m0 * m0 + m1 * m1 + c1)
+        cs = (2 * e01 - 2 * m0 * m1 + c2) / (e00 + e11 - m0 * m0 - m1 * m1 + c2)
+        out.append(np.mean(np.mean(lum * cs, axis=(0, 1))))
+    return np.array(out)
+
+
+def ssim_skimage(a, b):
+    """skimage.metrics.structural_similarity(a, b, multichannel=True, data_range=1) restated (scikit-image 0.16: 7 x 7 uniform filter,
+    use_sample_covariance -> N / (N - 1), K1 = 0.01, K2 = 0.03, 3-pixel border cropped before the mean), as wrapped by
+    helpers/metrics.py:9-26. (H,W,C) -> float."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    win = np.full((7,), 1.0 / 7.0)
+    ux, uy, uxx, uyy, uxy = _window_moments(a, b, win)
+    cov = 49.0 / 48.0
+    vx, vy, vxy = cov * (uxx - ux * ux), cov * (uyy - uy * uy), cov * (uxy - ux * uy)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
+    return float(np.mean(s))
