@@ -45,10 +45,11 @@ constexpr int kGroupBytes = 32768; // one weight copy = G k-iterations of [hi | 
 // waits), so those tiles get TWO issuer warps (different scheduler partitions) that take alternate k-iterations and own separate
 // accumulators [D1_0, D2_0, D1_1, D2_1]; the epilogue adds them up (the sum is order-independent, only each accumulator's FIRST MMA
 // has to overwrite, and that is a per-issuer property).
-template <int BNT> struct Cfg {
+template <int BNT, int SL = (BNT == 128 ? 2 : 4)> struct Cfg {
     static constexpr int ISSUERS = BNT == 128 ? 1 : 2;
-    static constexpr int SLOTS = BNT == 128 ? 2 : 4;     // A (hi | lo) slots in tensor memory, 64 columns each
-    static constexpr int LOG_SLOTS = BNT == 128 ? 1 : 2;
+    static constexpr int SLOTS = SL;                     // A (hi | lo) slots in tensor memory, 64 columns each (N = 128: 2, or 4 with one
+                                                         // hi*hi accumulator, i.e. shallow contractions only)
+    static constexpr int LOG_SLOTS = SL == 2 ? 1 : 2;
     static constexpr int NSETS = BNT == 32 ? 2 : 1;      // accumulator sets (512 TMEM columns: sets * set_cols + SLOTS * 64)
     static constexpr int B_BYTES = BNT * 128;            // one (BNT x 32) tf32 tile; a k-iteration reads hi + lo
     static constexpr int G = kGroupBytes / (2 * B_BYTES); // k-iterations per weight copy: 4 / 2 / 1
@@ -62,11 +63,11 @@ struct PersistParams {
     int defer_st;                  // 1: converters complete their tcgen05.st one iteration later (behind the next loads + split)
 };
 
-template <int BNT>
+template <int BNT, int SL = (BNT == 128 ? 2 : 4)>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ wtiled, const GemmParams p, const PersistParams q) {
-    constexpr int SLOTS = Cfg<BNT>::SLOTS, LOG_SLOTS = Cfg<BNT>::LOG_SLOTS, NSETS = Cfg<BNT>::NSETS, B_BYTES = Cfg<BNT>::B_BYTES,
-                  ISSUERS = Cfg<BNT>::ISSUERS, G = Cfg<BNT>::G, LOG_G = Cfg<BNT>::LOG_G;
+    using C = Cfg<BNT, SL>;
+    constexpr int SLOTS = C::SLOTS, LOG_SLOTS = C::LOG_SLOTS, NSETS = C::NSETS, B_BYTES = C::B_BYTES, ISSUERS = C::ISSUERS, G = C::G, LOG_G = C::LOG_G;
     const uint32_t set_cols = ISSUERS == 2 ? 4u * BNT : (uint32_t)(p.nacc + 1) * BNT;
     const uint32_t acc_cols = set_cols * NSETS;
     const uint32_t TMEM_COLS = pow2_cols(acc_cols + SLOTS * 64);
