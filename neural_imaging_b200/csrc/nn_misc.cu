@@ -236,25 +236,32 @@ maxpool_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ dy
 // dx = (route(dy) + add) * act'(x), dbias[c] += sum_pixels dx. Saves one read-modify-write pass over the largest gradient tensors
 // of the step (12 B per element). Grid-stride with a fixed channel quad per thread (gridDim * 256 is a multiple of c4n), per-block
 // shared-memory reduction, c atomics per block.
+// IDX = int when every pixel index fits 31 bits (always the case in the training step): the 64-bit divisions of the index
+// decomposition were a third of the kernel's instructions.
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 maxpool_act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ add, float* __restrict__ dx,
                             float* __restrict__ dbias, int n, int oh, int ow, int c4n, int xp, int xo, int dyp, int dyo, int addp, int addo,
                             int dxp, int dxo, int act, float alpha) {
     __shared__ float4 red[256];
-    const long long total = (long long)n * oh * ow * c4n;
+    const IDX total = (IDX)n * oh * ow * c4n;
     const int c4 = threadIdx.x % c4n;                 // 256 % c4n == 0 (checked by the launcher)
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        long long t = i / c4n;
-        const int ox = (int)(t % ow); t /= ow;
-        const int oy = (int)(t % oh);
-        const long long nn = t / oh;
-        const long long r[4] = {(nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox + 1,
-                                (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox, (nn * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox + 1};
+    // pixel index advanced incrementally: one decomposition per thread, then additions (stride = gridDim * 256 / c4n pixels)
+    const IDX pstride = (IDX)gridDim.x * (256 / c4n);
+    IDX pix = (IDX)blockIdx.x * (256 / c4n) + threadIdx.x / c4n;
+    const IDX npix = total / c4n;
+    const int sx = (int)(pstride % ow), sy = (int)((pstride / ow) % oh);
+    const IDX sn = pstride / ((IDX)ow * oh);
+    int ox = (int)(pix % ow), oy = (int)((pix / ow) % oh);
+    IDX nn = pix / ((IDX)ow * oh);
+    for (; pix < npix; pix += pstride) {
+        const long long r0 = ((long long)nn * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox;
+        const long long r[4] = {r0, r0 + 1, r0 + 2 * ow, r0 + 2 * ow + 1};
         float4 v[4], g[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(x + r[k] * xp + xo + c4 * 4));
-        const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + ((nn * oh + oy) * ow + ox) * dyp + dyo + c4 * 4));
+        const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + (((long long)nn * oh + oy) * ow + ox) * dyp + dyo + c4 * 4));
         pool_route(v[0].x, v[1].x, v[2].x, v[3].x, gy.x, g[0].x, g[1].x, g[2].x, g[3].x);
         pool_route(v[0].y, v[1].y, v[2].y, v[3].y, gy.y, g[0].y, g[1].y, g[2].y, g[3].y);
         pool_route(v[0].z, v[1].z, v[2].z, v[3].z, gy.z, g[0].z, g[1].z, g[2].z, g[3].z);
@@ -270,6 +277,9 @@ maxpool_act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict
             *reinterpret_cast<float4*>(dx + r[k] * dxp + dxo + c4 * 4) = g[k];
             s.x += g[k].x; s.y += g[k].y; s.z += g[k].z; s.w += g[k].w;
         }
+        ox += sx; oy += sy; nn += sn;
+        if (ox >= ow) { ox -= ow; ++oy; }
+        if (oy >= oh) { oy -= oh; ++nn; }
     }
     if (!dbias) return;
     red[threadIdx.x] = s;
@@ -552,8 +562,12 @@ extern "C" int ni_maxpool2_act_bwd_bias(const float* x, const float* dy, const f
     long long blocks = (total + 255) / 256;
     const long long cap = 16LL * ni_num_sms();
     if (blocks > cap) blocks = cap;
-    maxpool_act_bwd_bias_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, dy, add, dx, dbias, n, oh, ow, c4n, x_pitch, x_coff, dy_pitch, dy_coff, add_pitch,
-                                                                 add_coff, dx_pitch, dx_coff, act, alpha);
+    if (total + 16LL * 148 * 256 < 2147483647LL)
+        maxpool_act_bwd_bias_kernel<int><<<(unsigned)blocks, 256, 0, st>>>(x, dy, add, dx, dbias, n, oh, ow, c4n, x_pitch, x_coff, dy_pitch, dy_coff,
+                                                                          add_pitch, add_coff, dx_pitch, dx_coff, act, alpha);
+    else
+        maxpool_act_bwd_bias_kernel<long long><<<(unsigned)blocks, 256, 0, st>>>(x, dy, add, dx, dbias, n, oh, ow, c4n, x_pitch, x_coff, dy_pitch,
+                                                                                dy_coff, add_pitch, add_coff, dx_pitch, dx_coff, act, alpha);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
@@ -570,6 +584,15 @@ extern "C" int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, i
     const long long npix = (long long)n * h * w;
     if (npix == 0) return NI_OK;
     if (!dbias && (act == NI_ACT_NONE || act == NI_ACT_CLIP01)) return NI_OK;
+    // Bias gradient of a transposed convolution (1x1 conv + depth_to_space(2), no activation): the logical (n,h,w,4F) gradient is the
+    // physical (n,2h,2w,F) buffer and the bias index is the physical channel, so the sum over logical pixels and sub-pixel blocks is
+    // a plain per-channel sum over the physical tensor: take the vectorised streaming path (the scalar depth_to_space path ran at
+    // 10 % of the HBM bandwidth: 1.9 ms per step for 1.2 GB).
+    if (dy_mode == NI_MODE_BLOCK2 && (act == NI_ACT_NONE || act == NI_ACT_CLIP01) && dbias && !(c & 3) && bias_mod == c / 4 && !((c / 4) & 3) &&
+        !(dy_pitch & 3) && !(dy_coff & 3)) {
+        return ni_act_bwd_bias(nullptr, dy, dbias, n, 2 * h, 2 * w, c / 4, dy_pitch, dy_coff, NI_MODE_PLAIN, dy_pitch, dy_coff, NI_MODE_PLAIN, NI_ACT_NONE, alpha,
+                               0, st);
+    }
     if (y_mode == NI_MODE_PLAIN && dy_mode == NI_MODE_PLAIN && !(c & 3) && !(dy_pitch & 3) && !(dy_coff & 3) &&
         (!y || (!(y_pitch & 3) && !(y_coff & 3)))) {
         int nx = c / 4; if (nx > 64) nx = 64;
