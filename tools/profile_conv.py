@@ -9,7 +9,8 @@ from neural_imaging_b200.tensor import as_device, empty, ptr, stream
 L = _lib.lib()
 rs = np.random.RandomState(0)
 shapes = [(256, 32, 32, 128, 128, 3), (256, 128, 128, 32, 32, 3), (1280, 64, 64, 32, 64, 5), (256, 16, 16, 256, 256, 3),
-          (1280, 128, 128, 3, 32, 5), (256, 128, 128, 32, 12, 3)]      # 4, 5: direct FP32 kernels (through the dispatcher)
+          (1280, 128, 128, 3, 32, 5), (256, 128, 128, 32, 12, 3),      # 4, 5: direct FP32 kernels (through the dispatcher)
+          (256, 64, 64, 64, 64, 3), (256, 64, 64, 128, 64, 3)]          # 6, 7: N = 64 tiles in both directions / fprop
 which = [int(a) for a in sys.argv[1:]] or list(range(len(shapes)))
 res = {}
 for i in which:
