@@ -284,6 +284,10 @@ def run_ours(args, rank, world, local_rank):
                 'traffic': traffic.get('conv_top_launch', {}).get('dram_bytes'), 'traffic_launch': traffic.get('conv_top_launch'),
                 'flop_per_launch_avg': conv_flop / max(n_conv_launches, 1), 'ms_per_launch_avg': conv_ms / max(n_conv_launches, 1),
                 'share_of_step': conv_ms / max(prof_ms / args.steps, 1e-9), 'peak_source': pk['source'],
+                # measured with tools/hw_probes.py (profiles/r1_hw_probes.txt): a kind::tf32 MMA (M 128, K 8, A in tensor memory) takes
+                # 20.5 + 0.42 N cycles; a 32-deep 3xTF32 k-iteration is 12 of them => 2*128*N*32 / (12 * (20.5 + 0.42 N)) flop/clk/SM
+                'ceiling_3xtf32_tflops_at_n128': 2 * 128 * 128 * 32 / (12 * (20.5 + 0.42 * 128)) * 148 * 1.965e9 / 1e12,
+                'frac_of_3xtf32_ceiling': conv_tf / (2 * 128 * 128 * 32 / (12 * (20.5 + 0.42 * 128)) * 148 * 1.965e9 / 1e12),
                 'note': 'FP32 results (1e-5 parity) => 3xTF32 (three tensor-core passes per product) / FP32 SIMT; the denominator is the dense bf16 cuBLAS peak, '
                         'so 1/6 of it is the ceiling of an ideal 3xTF32 kernel; traffic = DRAM bytes of the single most expensive launch (ncu), see traffic_launch'}
     roofline_djpeg = None

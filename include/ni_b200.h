@@ -199,6 +199,8 @@ int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* 
                                int ncodes, double nu, double gamma, ni_stream_t stream);
 int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
                                const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, ni_stream_t stream);
+/* Quantization layer, scalar modes (models/layers.py:118-136): 0 'round', 1 'sin', 2 'soft', 3 'harmonic', 4 'identity' (forward values) */
+int ni_quantize_scalar(const float* x, float* y, long long n, int mode, int taylor_terms, ni_stream_t stream);
 /* entropy estimate from the accumulated soft histogram (helpers/tf_helpers.py:326-331) and its gradient w.r.t. the histogram */
 int ni_entropy_from_hist(const double* hist_acc, long long n, int ncodes, double upstream, float* h_out, double* gh_out, ni_stream_t stream);
 /* tf.nn.leaky_relu on a residual-branch input (models/compression.py:224) */

@@ -234,3 +234,38 @@ extern "C" int ni_entropy_from_hist(const double* hist_acc, long long n, int nco
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Quantization layer, scalar modes (models/layers.py:118-136): 0 'round', 1 'sin', 2 'soft' (forward value = round, the sine only
+// shapes the gradient), 3 'harmonic' (taylor_terms terms), 4 'identity'. The differentiable JPEG fuses these into its own kernel;
+// this entry point serves the stand-alone layer (models.layers.Quantization).
+namespace {
+__global__ void quantize_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int mode, int taylor_terms) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = x[i];
+        float r;
+        // period-1 argument reduction, exact in FP32: sin(2 pi k v) == sin(2 pi k (v - rint(v))) for integer k
+        const float f = v - rintf(v);
+        const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+        if (mode == 0 || mode == 2) r = rintf(v);
+        else if (mode == 1) r = v - sinf(two_pi * f) / two_pi;
+        else if (mode == 3) {
+            r = v - sinf(two_pi * f) / pi;
+            for (int k = 2; k < taylor_terms; ++k) r += ((k & 1) ? -1.f : 1.f) * sinf(two_pi * (float)k * f) / ((float)k * pi);
+        } else r = v;
+        y[i] = r;
+    }
+}
+}  // namespace
+
+extern "C" int ni_quantize_scalar(const float* x, float* y, long long n, int mode, int taylor_terms, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0 && mode >= 0 && mode <= 4 && taylor_terms >= 1, "ni_quantize_scalar: invalid arguments");
+    if (n == 0) return NI_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = 16LL * ni_num_sms();
+    quantize_scalar_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>(x, y, n, mode, taylor_terms);
+    NI_LAUNCH_CHECK();
+    NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}

@@ -1,0 +1,62 @@
+"""Stand-alone layer mirrors (neural_imaging_b200/models/layers.py) against the oracle restatement of reference models/layers.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models as M
+from oracle import ref_ops as R
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rounding', ['round', 'sin', 'soft', 'harmonic', 'identity'])
+def test_quantization_scalar_modes(rounding):
+    from neural_imaging_b200.models.layers import Quantization
+    rs = np.random.RandomState(0)
+    x = (rs.normal(size=(3, 16, 16, 8)) * 20).astype(np.float32)
+    got = Quantization(rounding).call(x).numpy()
+    ref = R.quantization(torch.tensor(x, dtype=torch.float64), rounding).numpy()
+    if rounding in ('round', 'soft', 'identity'):
+        ties = np.abs(np.abs(x - np.floor(x)) - 0.5) < 1e-6
+        assert np.array_equal(got[~ties], ref[~ties].astype(np.float32))
+    else:
+        assert np.max(np.abs(got - ref)) < 2e-6          # float32 sine after an exact period-1 reduction vs float64 truth
+
+
+@pytest.mark.gpu
+def test_quantization_soft_codebook_and_discrete_latent():
+    from neural_imaging_b200.models.layers import DiscreteLatent, Quantization
+    rs = np.random.RandomState(1)
+    z = (rs.normal(size=(2, 8, 8, 16)) * 4).astype(np.float32)
+    q = Quantization('soft-codebook', latent_bpf=5)
+    assert q.codebook.shape == (1, 32) and q.codebook[0, 0] == -15 and q.codebook[0, -1] == 16
+    cb = torch.tensor(q.codebook.reshape(-1))
+    got = q(z).numpy()
+    ref = R.soft_codebook_quantization(torch.tensor(z), cb).numpy()
+    assert np.max(np.abs(got - ref)) < 1e-6
+    dl = DiscreteLatent('soft-codebook', latent_bpf=5)
+    lat, ent = dl(z)
+    rq, rent = R.discrete_latent(torch.tensor(z), torch.tensor(1.0), cb)
+    assert np.max(np.abs(lat.numpy() - rq.numpy())) < 1e-6
+    assert abs(float(ent.numpy()) - float(rent)) < 1e-5 * max(1.0, abs(float(rent)))
+    with pytest.raises(ValueError):
+        Quantization('no-such-mode')
+    with pytest.raises(NotImplementedError):
+        DiscreteLatent('sin')
+
+
+@pytest.mark.gpu
+def test_constrained_conv2d():
+    from neural_imaging_b200.models.layers import ConstrainedConv2D
+    rs = np.random.RandomState(2)
+    x = rs.uniform(size=(2, 24, 40, 3)).astype(np.float32)
+    layer = ConstrainedConv2D()
+    k = layer.kernel.numpy()
+    assert k.shape == (5, 5, 3, 3) and k[2, 2, 0, 0] == 12 and k[2, 2, 0, 1] == 0
+    nf = M.constrained_filter(torch.tensor(k, dtype=torch.float64))
+    ref = R.conv2d(R.tf_pad(torch.tensor(x, dtype=torch.float64), 2, 'SYMMETRIC'), nf, None, 1, 'VALID').numpy()
+    got = layer(x).numpy()
+    assert got.shape == x.shape
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-5
+    assert np.max(np.abs(layer.normalized_kernel().numpy() - nf.numpy())) < 1e-4
+    with pytest.raises(ValueError):
+        layer(np.zeros((1, 8, 8, 4), np.float32))
