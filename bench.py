@@ -345,7 +345,7 @@ def cpu_step_factory(b):
     return lambda: M.training_step(Pn, Pf, opt, xt, yt, lambda_nip=LAMBDA_NIP, lr=LR, train_nip=True)
 
 
-def cpu_baseline(bounded_batch=4, steps=2):
+def cpu_baseline(bounded_batch=32, steps=4):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     step = cpu_step_factory(bounded_batch)
@@ -368,7 +368,7 @@ def run_reference(args, rank, world):
     step = cpu_step_factory(b)
     for _ in range(max(1, min(args.warmup, 1))):
         step()
-    k = max(1, min(args.steps, 3))
+    k = max(1, min(args.steps, args.cpu_steps))
     t0 = time.perf_counter()
     for _ in range(k):
         step()
@@ -391,8 +391,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=GLOBAL_BATCH, help='global raw batch (BASELINE config 4: 256)')
-    ap.add_argument('--cpu-batch', type=int, default=4)
-    ap.add_argument('--cpu-steps', type=int, default=2)
+    ap.add_argument('--cpu-batch', type=int, default=32, help='raw patches per step of the CPU legs (bounded sample of config 4: ~10 s of host work)')
+    ap.add_argument('--cpu-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying the captured CUDA graphs')
     ap.add_argument('--layer-report', default=None, help='write a per-layer (per conv shape) timing table to this JSON file')

@@ -1,5 +1,9 @@
-"""JPEG quantisation-table helpers (host, NumPy). Behaviour follows reference compression/jpeg_helpers.py:253-310;
-the libjpeg / marker-parsing tooling of that file is out of scope."""
+"""JPEG helpers (host, NumPy). Quantisation tables follow reference compression/jpeg_helpers.py:253-310; `compress_batch`
+(:82-114) is the reference's HOST-side libjpeg codec (used for the "final validation" with JPEG(codec='libjpeg')): it is a
+per-image file codec by definition (the reference goes through imageio -> Pillow -> libjpeg), not a fallback of a device operator.
+The marker-parsing tooling of that file is out of scope."""
+import io
+
 import numpy as np
 
 # IJG base tables (ITU-T T.81 Annex K), row-major
@@ -37,3 +41,36 @@ def jpeg_qf_estimation(q_mtx, channel=0):
     q_mtx = np.asarray(q_mtx)
     errors = [np.mean(np.abs(jpeg_qtable(qf, channel) - q_mtx)) for qf in range(1, 101)]
     return int(np.argmin(errors)) + 1
+
+
+_SUBSAMPLING = {'4:4:4': 0, '4:2:2': 1, '4:2:0': 2}
+
+
+def _libjpeg_roundtrip(img_u8, quality, subsampling):
+    from PIL import Image                       # Pillow's libjpeg: what imageio.imsave(format='jpg') calls in the reference
+    buf = io.BytesIO()
+    Image.fromarray(img_u8).save(buf, format='JPEG', quality=int(quality), subsampling=_SUBSAMPLING[subsampling])
+    data = buf.getvalue()
+    return np.asarray(Image.open(io.BytesIO(data)).convert('RGB' if img_u8.ndim == 3 else 'L')), len(data)
+
+
+def compress_batch(batch_x, jpeg_quality, effective=False, subsampling='4:4:4'):
+    """Standard JPEG round trip of an (n,h,w,3) / (h,w,3) array in [0,1] (or [0,255]); returns (images in [0,1], sizes in bytes)
+    (reference compression/jpeg_helpers.py:82-114). `effective=True` (payload without headers) needs the marker parser, which is out
+    of scope."""
+    if effective:
+        raise NotImplementedError('effective payload size needs the JPEG marker parser (out of scope)')
+    batch_x = np.asarray(batch_x)
+    if batch_x.max() > 1:
+        batch_x = batch_x.astype(np.float32) / (2 ** 8 - 1)
+    if batch_x.ndim == 3:
+        img, nbytes = _libjpeg_roundtrip((255 * batch_x).astype(np.uint8).squeeze(), jpeg_quality, subsampling)
+        return img / (2 ** 8 - 1), nbytes
+    if batch_x.ndim == 4:
+        out, sizes = np.zeros_like(batch_x), []
+        for r in range(batch_x.shape[0]):
+            img, nbytes = _libjpeg_roundtrip((255 * batch_x[r]).astype(np.uint8).squeeze(), jpeg_quality, subsampling)
+            out[r] = img.astype(np.float32).reshape(out[r].shape) / (2 ** 8 - 1)
+            sizes.append(nbytes)
+        return out, sizes
+    raise ValueError('compress_batch expects an (n,h,w,c) or (h,w,c) array')

@@ -9,6 +9,7 @@
 import numpy as np
 
 from .. import ops
+from ..compression import jpeg_helpers
 from ..compression.jpeg_helpers import jpeg_qf_estimation, jpeg_qtable
 from ..helpers.utils import is_number
 from ..tensor import as_device, wrap
@@ -121,8 +122,10 @@ class JPEG(TFModel):
     def process(self, batch_x, quality=None, return_entropy=False):
         quality = self._draw_quality(quality)
         if self._model is None:
-            raise NotImplementedError("codec='libjpeg' (host-side PIL/imageio validation codec, reference "
-                                      "models/jpeg.py:227-233) is outside the B200 hot path")
+            # codec='libjpeg': the reference's host-side file codec for the final validation (models/jpeg.py:227-233); numpy in, numpy out
+            batch_x = batch_x if isinstance(batch_x, np.ndarray) else np.asarray(batch_x.numpy() if hasattr(batch_x, 'numpy') else batch_x)
+            y = jpeg_helpers.compress_batch(batch_x, quality)[0]
+            return (y, np.nan) if return_entropy else y
         y = self._with_quality(quality, lambda: self._model(batch_x, want_coeffs=False))
         return (y, np.nan) if return_entropy else y
 
