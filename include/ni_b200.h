@@ -61,6 +61,19 @@ int ni_feed_gather(const void* images, int src_bytes, int n_images, int h, int w
  * multichannel, data_range 1): uniform 7 taps, cov_norm 49/48, same constants. a, b: (n,h,w,c); out_n: n floats. */
 int ni_ssim(const float* a, const float* b, float* out_n, int n, int h, int w, int c, const float* win_host, int k, float cov_norm, float c1,
             float c2, ni_stream_t stream);
+/* SSIM / MS-SSIM as image LOSSES of the ISPs (NIPModel.construct_loss, models/pipelines.py:53-63 -> helpers/tf_helpers.py:39-44:
+ * mean(255 (1 - tf.image.ssim(a, b, 1))), mean(255 (1 - tf.image.ssim_multiscale(a, b, 1)))), forward and backward w.r.t. a.
+ * ni_ssim_stats    : stats_nc2[(img*c+ch)*2 + {0,1}] = mean over the VALID region of {luminance*cs, cs} (TF's _ssim_per_channel).
+ * ni_msssim_combine: stats / coef are [levels][n*c][2]; levels = 1 -> SSIM loss, levels = 5 with the TF power factors (HOST pointer)
+ *                    -> MS-SSIM (relu of cs at scales 0..3 and of ssim at the last scale, weighted geometric mean, mean over
+ *                    channels and images). Adds loss * loss_scale to *loss_acc; coef = grad_scale * d loss / d stats.
+ * ni_ssim_bwd      : da (+)= d/da of sum_{img,ch} coef[.][0] * mean(lum*cs) + coef[.][1] * mean(cs), fused in shared memory. */
+int ni_ssim_stats(const float* a, const float* b, float* stats_nc2, int n, int h, int w, int c, const float* win_host, int k, float cov_norm,
+                  float c1, float c2, ni_stream_t stream);
+int ni_ssim_bwd(const float* a, const float* b, const float* coef_nc2, float* da, int accumulate, int n, int h, int w, int c,
+                const float* win_host, int k, float cov_norm, float c1, float c2, ni_stream_t stream);
+int ni_msssim_combine(const float* stats, float* coef, float* loss_acc, int n, int c, int levels, const float* weights_host, float loss_scale,
+                      float grad_scale, ni_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ manipulations
  * helpers/tf_helpers.py:68-184. All on (n,h,w,3). */

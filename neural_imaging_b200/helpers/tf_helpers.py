@@ -67,6 +67,25 @@ def mae(a, b):
     return wrap(ops.image_loss(a, b, 'L1').reshape(()))
 
 
+def _structural(a, b, multiscale):
+    a, b = as_device(a), as_device(b)
+    if a.dim() == 3:
+        a, b = a.unsqueeze(0), b.unsqueeze(0)
+    acc = zeros((1,))
+    ops.StructuralLoss(multiscale).forward(a, b, acc)
+    return wrap(acc.reshape(()))
+
+
+def ssim_loss(a, b):
+    """mean(255 (1 - tf.image.ssim(a, b, 1.0))) (helpers/tf_helpers.py:39-40)."""
+    return _structural(a, b, False)
+
+
+def msssim_loss(a, b):
+    """mean(255 (1 - tf.image.ssim_multiscale(a, b, 1.0))) (helpers/tf_helpers.py:43-44)."""
+    return _structural(a, b, True)
+
+
 def quantize_and_clip(x):
     """clip(soft_quantization(x), 0, 1) == awgn with zero noise strength."""
     return manipulation_awgn(x, 0.0)

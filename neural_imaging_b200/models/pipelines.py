@@ -43,8 +43,10 @@ class NIPModel(TFModel):
             self.loss = tf_helpers.mse
         elif loss_metric == 'L1':
             self.loss = tf_helpers.mae
-        elif loss_metric in ('SSIM', 'MS-SSIM'):
-            raise NotImplementedError('SSIM losses (tf.image.ssim, reference helpers/tf_helpers.py:39-44) are not on the B200 path yet')
+        elif loss_metric == 'SSIM':
+            self.loss = tf_helpers.ssim_loss
+        elif loss_metric == 'MS-SSIM':
+            self.loss = tf_helpers.msssim_loss
         else:
             raise ValueError('Unsupported loss metric!')
 
@@ -66,18 +68,34 @@ class NIPModel(TFModel):
         """One optimisation step on (raw, rgb target); returns the loss (reference models/pipelines.py:77-90)."""
         x, t = self._prep(batch_x), self._prep(batch_y)
         y = self._forward(x, save=True)
-        kind = 0 if self.loss_metric == 'L2' else 1
         L = _lib.lib()
         acc = self._ws.get('loss_acc', (1,))
         L.ni_fill(ptr(acc), 0.0, 1, stream())
-        L.ni_image_loss(ptr(y), ptr(t), ptr(acc), y.numel(), kind, stream())
         dy = self._ws.get('dY', y.shape)
-        L.ni_image_loss_grad(ptr(y), ptr(t), ptr(dy), y.numel(), kind, 1.0, 0, stream())
+        self.loss_forward(y, t, acc, 1.0)
+        self.loss_backward(y, t, dy, 1.0)
         self._backward(dy)
         if learning_rate is not None:
             self.optimizer.lr = float(learning_rate)
         self.optimizer.apply([self._store])
         return wrap((acc / float(y.numel())).reshape(()))
+
+    def loss_forward(self, y, t, acc, grad_scale=1.0):
+        """acc += numel(y) * loss(y, t) on the device (callers divide by numel, the L2 / L1 convention of ni_image_loss).
+        grad_scale is the factor loss_backward will be asked for (the structural losses fix it in the forward pass)."""
+        if self.loss_metric in ('SSIM', 'MS-SSIM'):
+            if getattr(self, '_sloss', None) is None:
+                self._sloss = ops.StructuralLoss(self.loss_metric == 'MS-SSIM', self._ws)
+            self._sloss.forward(y, t, acc, loss_scale=float(y.numel()), grad_scale=float(grad_scale))
+        else:
+            _lib.lib().ni_image_loss(ptr(y), ptr(t), ptr(acc), y.numel(), 0 if self.loss_metric == 'L2' else 1, stream())
+
+    def loss_backward(self, y, t, dy, scale):
+        """dy = scale * d loss(y, t) / dy (after loss_forward on the same tensors with grad_scale = scale)."""
+        if self.loss_metric in ('SSIM', 'MS-SSIM'):
+            self._sloss.backward(dy, accumulate=False)
+        else:
+            _lib.lib().ni_image_loss_grad(ptr(y), ptr(t), ptr(dy), y.numel(), 0 if self.loss_metric == 'L2' else 1, float(scale), 0, stream())
 
     def reset_performance_stats(self):
         self.performance = {'loss': {'training': [], 'validation': []}, 'psnr': {'validation': []}, 'ssim': {'validation': []}}

@@ -230,3 +230,80 @@ def image_loss(a, b, kind='L2'):
     acc = zeros((1,))
     _lib.lib().ni_image_loss(ptr(a), ptr(b), ptr(acc), a.numel(), 0 if kind == 'L2' else 1, stream())
     return acc / float(a.numel())
+
+
+class StructuralLoss:
+    """SSIM / MS-SSIM image losses of the ISPs with an explicit backward (reference helpers/tf_helpers.py:39-44, selected by
+    NIPModel.construct_loss, models/pipelines.py:53-63): loss = mean_n 255 (1 - tf.image.ssim[_multiscale](a, b, 1.0)).
+
+    forward() adds `loss * loss_scale` to a device accumulator and keeps the image pyramid and the per-(image, channel) gradient
+    coefficients; backward() writes (or accumulates) `grad_scale * d loss / d a`. Every buffer lives in the given Workspace, so the
+    pair is CUDA-graph safe. Kernels: ni_ssim_stats, ni_msssim_combine, ni_ssim_bwd (csrc/metrics.cu) + the average-pool kernels."""
+    WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)     # TF 2.1 _MSSSIM_WEIGHTS
+    K1, K2, SIZE, SIGMA = 0.01, 0.03, 11, 1.5
+
+    def __init__(self, multiscale=False, workspace=None, tag='sloss'):
+        from .tensor import Workspace
+        self.levels = len(self.WEIGHTS) if multiscale else 1
+        self._ws = workspace if workspace is not None else Workspace()
+        self._tag = tag
+        x = np.arange(self.SIZE, dtype=np.float64) - (self.SIZE - 1) / 2.0
+        g = np.exp(-0.5 * x * x / self.SIGMA ** 2)
+        self._win, self._pwin = _f32(g / g.sum())
+        self._wts, self._pwts = _f32(self.WEIGHTS)
+        self._pyr = None
+
+    def _check(self, a, b):
+        if a.shape != b.shape or a.dim() != 4:
+            raise ValueError('SSIM loss: expected two (N,H,W,C) tensors of the same shape')
+        n, h, w, c = (int(v) for v in a.shape)
+        div = 2 ** (self.levels - 1)
+        if self.levels > 1 and (h % div or w % div or c != 3):
+            raise ValueError('MS-SSIM loss on the B200 path needs (N,H,W,3) images with H and W divisible by {}'.format(div))
+        if h // div < self.SIZE or w // div < self.SIZE:
+            raise ValueError('SSIM loss: the {0} x {0} window does not fit the coarsest scale ({1} x {2})'.format(self.SIZE, h // div, w // div))
+        return n, h, w, c
+
+    def forward(self, a, b, acc, loss_scale=1.0, grad_scale=1.0):
+        n, h, w, c = self._check(a, b)
+        L, s, ws, t = _lib.lib(), stream(), self._ws, self._tag
+        stats = ws.get(t + '_stats', (self.levels, n * c, 2))
+        self._coef = ws.get(t + '_coef', (self.levels, n * c, 2))
+        self._pyr = [(a, b)]
+        c1, c2 = self.K1 ** 2, self.K2 ** 2
+        for l in range(self.levels):
+            if l > 0:
+                pa, pb = self._pyr[-1]
+                shape = (n, pa.shape[1] // 2, pa.shape[2] // 2, c)
+                self._pyr.append((avgpool_fwd(pa, 2, out=ws.get('{}_a{}'.format(t, l), shape)),
+                                  avgpool_fwd(pb, 2, out=ws.get('{}_b{}'.format(t, l), shape))))
+            la, lb = self._pyr[-1]
+            L.ni_ssim_stats(ptr(la), ptr(lb), ptr(stats[l]), n, int(la.shape[1]), int(la.shape[2]), c, self._pwin, self.SIZE, 1.0, c1, c2, s)
+        L.ni_msssim_combine(ptr(stats), ptr(self._coef), ptr(acc), n, c, self.levels, self._pwts, float(loss_scale), float(grad_scale), s)
+        return acc
+
+    def backward(self, da, accumulate=False):
+        """da (+)= grad_scale * d loss / d a for the (a, b) of the last forward()."""
+        if self._pyr is None:
+            raise RuntimeError('StructuralLoss.backward() before forward()')
+        L, s, ws, t = _lib.lib(), stream(), self._ws, self._tag
+        c1, c2 = self.K1 ** 2, self.K2 ** 2
+        n, c = int(da.shape[0]), int(da.shape[3])
+        g_coarse = None
+        for l in range(self.levels - 1, -1, -1):
+            la, lb = self._pyr[l]
+            if l == 0:
+                g, acc_flag = da, accumulate
+            else:
+                g, acc_flag = ws.get('{}_g{}'.format(t, l), la.shape), False
+            if g_coarse is not None:            # chain rule through the 2 x 2 average pooling of the next coarser scale
+                if l == 0 and accumulate:
+                    tmp = avgpool_bwd(g_coarse, la.shape, 2, out=ws.get(t + '_g0', la.shape))
+                    L.ni_axpy(ptr(g), ptr(tmp), 1.0, g.numel(), s)
+                else:
+                    avgpool_bwd(g_coarse, la.shape, 2, out=g)
+                acc_flag = True
+            L.ni_ssim_bwd(ptr(la), ptr(lb), ptr(self._coef[l]), ptr(g), int(acc_flag), n, int(la.shape[1]), int(la.shape[2]), c, self._pwin,
+                          self.SIZE, 1.0, c1, c2, s)
+            g_coarse = g
+        return da

@@ -346,8 +346,7 @@ class ManipulationClassification(object):
         probs, loss_ce, dlogits = self.fan.forward_loss(C, labels)
         acc = ws.get('loss_nip', (1,))
         L.ni_fill(ptr(acc), 0.0, 1, s)
-        kind = 0 if self.nip.loss_metric == 'L2' else 1
-        L.ni_image_loss(ptr(Y), ptr(t), ptr(acc), Y.numel(), kind, s)
+        self.nip.loss_forward(Y, t, acc, float(lambda_nip))
 
         # ---- backward
         codec_bwd = comp == 'dcn' and (train_nip or train_dcn)
@@ -368,7 +367,7 @@ class ManipulationClassification(object):
             dm = self._downsample_bwd(dc, m.shape, ws)
             dY = ws.get('dY', Y.shape)
             # dY = lambda_nip * d(nip loss)/dY + native slot + manipulation branches
-            L.ni_image_loss_grad(ptr(Y), ptr(t), ptr(dY), Y.numel(), kind, float(lambda_nip), 0, s)
+            self.nip.loss_backward(Y, t, dY, float(lambda_nip))
             L.ni_axpy(ptr(dY), ptr(dm[:B]), 1.0, dY.numel(), s)
             for i, (name, op) in enumerate(self._ops.items()):
                 if op.has_grad:

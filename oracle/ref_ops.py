@@ -454,3 +454,52 @@ def ssim_skimage(a, b):
     c1, c2 = 0.01 ** 2, 0.03 ** 2
     s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
     return float(np.mean(s))
+
+
+# ------------------------------------------------------------------------------------------------ SSIM / MS-SSIM losses (autograd)
+MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def _ssim_per_channel_t(a, b, max_val=1.0):
+    """TF 2.1 image_ops_impl._ssim_per_channel restated on torch tensors (NHWC): Gaussian 11 x 11 (sigma 1.5) VALID depthwise filter,
+    (luminance * cs, cs) averaged over space -> two (N, C) tensors. Differentiable."""
+    x = torch.arange(11, dtype=a.dtype) - 5.0
+    g = torch.exp(-0.5 * x * x / 1.5 ** 2)
+    g = g / g.sum()
+    c = a.shape[-1]
+    w = (g[:, None] * g[None, :])[None, None].repeat(c, 1, 1, 1)
+
+    def red(t):
+        return F.conv2d(t.permute(0, 3, 1, 2), w, groups=c)
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    m0, m1 = red(a), red(b)
+    num0 = m0 * m1 * 2.0
+    den0 = m0 * m0 + m1 * m1
+    lum = (num0 + c1) / (den0 + c1)
+    num1 = red(a * b) * 2.0
+    den1 = red(a * a + b * b)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (lum * cs).mean(dim=(2, 3)), cs.mean(dim=(2, 3))
+
+
+def ssim_loss(a, b):
+    """helpers/tf_helpers.py:39-40: mean(255 * (1 - tf.image.ssim(a, b, 1.0)))."""
+    s, _ = _ssim_per_channel_t(a, b)
+    return (255.0 * (1.0 - s.mean(dim=-1))).mean()
+
+
+def msssim_loss(a, b):
+    """helpers/tf_helpers.py:43-44: mean(255 * (1 - tf.image.ssim_multiscale(a, b, 1.0))) — TF 2.1 ssim_multiscale: five scales
+    (2 x 2 average pooling between them; even sizes assumed, so TF's SYMMETRIC padding of odd sizes never triggers), relu(cs) of
+    scales 0..3 and relu(ssim) of scale 4, weighted geometric mean, mean over channels."""
+    vals = []
+    for k in range(len(MSSSIM_WEIGHTS)):
+        if k > 0:
+            a, b = avg_pool(a, 2), avg_pool(b, 2)
+        s, cs = _ssim_per_channel_t(a, b)
+        vals.append(torch.relu(cs))
+    vals[-1] = torch.relu(s)
+    ms = torch.ones_like(vals[0])
+    for v, p in zip(vals, MSSSIM_WEIGHTS):
+        ms = ms * v ** p
+    return (255.0 * (1.0 - ms.mean(dim=-1))).mean()

@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from conftest import assert_parity
 from oracle import ref_ops as R
 
 
@@ -60,3 +61,75 @@ def test_dcn_training_step_reports_tf_ssim():
     a, b = _pair(2, 64, 64, 3)
     v = float(TwitterDCN.ssim(a, b).numpy())
     assert abs(v - R.ssim_tf(a, b).mean()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- SSIM / MS-SSIM as ISP losses (a3)
+def _loss_oracle(name, a, b, dt):
+    import torch as T
+    ta = T.tensor(a, dtype=dt, requires_grad=True)
+    loss = getattr(R, name)(ta, T.tensor(b, dtype=dt))
+    g, = T.autograd.grad(loss, ta)
+    return float(loss.detach()), g.numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,shape', [('ssim_loss', (2, 50, 45, 3)), ('ssim_loss', (3, 11, 11, 1)), ('ssim_loss', (1, 64, 64, 4)),
+                                        ('msssim_loss', (2, 176, 192, 3)), ('msssim_loss', (1, 256, 256, 3))])
+def test_structural_losses_forward_backward(name, shape):
+    """helpers/tf_helpers.py:39-44 — value and gradient w.r.t. the first image against float64 autograd of the restatement."""
+    import torch as T
+    from neural_imaging_b200 import ops
+    from neural_imaging_b200.helpers import tf_helpers
+    from neural_imaging_b200.tensor import as_device, zeros
+    rs = np.random.RandomState(5)
+    a = rs.uniform(size=shape).astype(np.float32)
+    b = np.clip(a + 0.15 * rs.normal(size=shape), 0, 1).astype(np.float32)
+    l64, g64 = _loss_oracle(name, a, b, T.float64)
+    l32, g32 = _loss_oracle(name, a, b, T.float32)
+    got = float(getattr(tf_helpers, name)(a, b).numpy())
+    assert abs(got - l64) <= max(1e-5 * abs(l64), 4 * abs(l32 - l64)), (got, l64, l32)
+    op = ops.StructuralLoss(name == 'msssim_loss')
+    da, db_ = as_device(a), as_device(b)
+    acc = zeros((1,))
+    op.forward(da, db_, acc, loss_scale=2.0, grad_scale=0.5)
+    g = T.full(shape, 3.0, dtype=T.float32, device=da.device)
+    op.backward(g, accumulate=True)                      # accumulate on top of a constant
+    assert abs(float(acc.item()) - 2.0 * l64) <= 1e-4 * abs(l64)
+    assert_parity(g.cpu().numpy() - 3.0, 0.5 * g64, 0.5 * g32, tol=2e-5, slack=6.0, what=name + ' grad (accumulate)')
+    g2 = T.full(shape, 7.0, dtype=T.float32, device=da.device)
+    op.backward(g2, accumulate=False)                    # overwrite
+    assert_parity(g2.cpu().numpy(), 0.5 * g64, 0.5 * g32, tol=2e-5, slack=6.0, what=name + ' grad')
+    assert float(getattr(tf_helpers, name)(a, a).numpy()) < 1e-3          # identical images: zero loss
+
+
+@pytest.mark.gpu
+def test_structural_loss_errors_and_nip_training():
+    from neural_imaging_b200.helpers import tf_helpers
+    from neural_imaging_b200.models import pipelines
+    rs = np.random.RandomState(11)
+    with pytest.raises(ValueError):
+        tf_helpers.ssim_loss(np.zeros((1, 8, 8, 3), np.float32), np.zeros((1, 8, 8, 3), np.float32))       # window does not fit
+    with pytest.raises(ValueError):
+        tf_helpers.msssim_loss(np.zeros((1, 64, 64, 3), np.float32), np.zeros((1, 64, 64, 3), np.float32))  # coarsest scale 4 x 4
+    with pytest.raises(ValueError):
+        pipelines.ONet(loss_metric='bogus', patch_size=16)
+    # an ISP trained with the SSIM loss: the step's loss equals the oracle's on the model output and goes down
+    import torch as T
+    from oracle import ref_models as M
+    model = pipelines.UNet(loss_metric='SSIM', patch_size=32, seed=3)
+    x = rs.uniform(size=(2, 32, 32, 4)).astype(np.float32)
+    t = rs.uniform(size=(2, 64, 64, 3)).astype(np.float32)
+    P = M.to_params(model._store.state_dict(), T.float64)
+    yt = M.unet_forward(P, T.tensor(x, dtype=T.float64))
+    ref = R.ssim_loss(yt, T.tensor(t, dtype=T.float64))
+    gref = T.autograd.grad(ref, list(P.values()))
+    first = float(model.training_step(x, t, learning_rate=1e-3).numpy())
+    assert abs(first - float(ref)) < 1e-4 * float(ref)
+    g = {p.name: p.grad.detach().cpu().numpy() for p in model._store.trainable}
+    for (k, _), gr in zip(P.items(), gref):
+        assert_parity(g[k], gr.numpy(), tol=5e-4, what='UNet SSIM-loss grad ' + k)
+    for _ in range(5):
+        last = float(model.training_step(x, t, learning_rate=1e-3).numpy())
+    assert last < first
+    v = float(model.loss(model.process(x), t).numpy())
+    assert np.isfinite(v) and v < first
