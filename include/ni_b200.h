@@ -75,6 +75,34 @@ int ni_ssim_bwd(const float* a, const float* b, const float* coef_nc2, float* da
 int ni_msssim_combine(const float* stats, float* coef, float* loss_acc, int n, int c, int levels, const float* weights_host, float loss_scale,
                       float grad_scale, ni_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ l3ic bit-stream codec
+ * Batched, bit-exact replacements of the reference's only native component: pyfse (pyfse/pyfse.pyx:24-72 over the vendored FSE
+ * library, fse_compress.c:648-714 / fse_decompress.c:262-302) and of the host loop around it (compression/codec.py:87-265).
+ * All pointers are DEVICE pointers; one warp codes one stream, so throughput comes from the number of streams per launch.
+ *
+ * ni_fse_compress_batch  : pyfse.compress of n byte strings; string i = src + i*src_stride, src_len[i] bytes; the result goes to
+ *                          dst + i*dst_stride (dst_stride >= src_len[i] is enough). dst_len[i] = coded size (> 1), 0 = not
+ *                          compressible (FSENotCompressibleError), 1 = one repeated byte (FSESymbolRepetitionError), < 0 = FSEException.
+ * ni_fse_decompress_batch: pyfse.decompress(src_i, max_length = dst_cap) into rows of dst_stride >= dst_cap bytes; dst_len[i] = decoded
+ *                          size or < 0 (FSEException).
+ * ni_l3ic_encode         : codec.compress for a batch. latent (n,h,w,c) float32; codebook n_codes <= 256 floats; scratch: indices
+ *                          n*c*h*w bytes, layer_bytes n*c*layer_slot bytes (layer_slot >= h*w), layer_len n*c ints. Output: stream i at
+ *                          streams + i*stream_stride (stream_stride >= 5 + 2c + c*h*w), stream_len[i] bytes; status[i] != 0 flags the
+ *                          conditions under which the reference raises (L3ICError / uncaught pyfse errors).
+ * ni_l3ic_decode         : codec.decompress up to the latent: streams as above -> latent (n,h,w,c) = codebook[decoded indices];
+ *                          scratch layer_off / layer_len n*c ints, indices n*c*index_slot bytes (index_slot >= h*w + 4);
+ *                          status[i] != 0: corrupt / truncated stream, shape mismatch, symbol outside the code book. */
+int ni_fse_compress_batch(const unsigned char* src, long long src_stride, const int* src_len, unsigned char* dst, long long dst_stride,
+                          int* dst_len, int n, ni_stream_t stream);
+int ni_fse_decompress_batch(const unsigned char* src, long long src_stride, const int* src_len, unsigned char* dst, long long dst_stride,
+                            int dst_cap, int* dst_len, int n, ni_stream_t stream);
+int ni_l3ic_encode(const float* latent, int n, int h, int w, int c, const float* codebook, int n_codes, unsigned char* indices,
+                   unsigned char* layer_bytes, int layer_slot, int* layer_len, unsigned char* streams, long long stream_stride,
+                   int* stream_len, int* status, ni_stream_t stream);
+int ni_l3ic_decode(const unsigned char* streams, long long stream_stride, const int* stream_len, int n, int h, int w, int c,
+                   const float* codebook, int n_codes, int* layer_off, int* layer_len, unsigned char* indices, int index_slot, float* latent,
+                   int* status, ni_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ manipulations
  * helpers/tf_helpers.py:68-184. All on (n,h,w,3). */
 /* manipulation_sharpen (tf_helpers.py:156-184): filt9 = HOST 3x3 filter applied to H and V; S takes tap [2,2]. */

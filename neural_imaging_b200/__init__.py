@@ -6,13 +6,13 @@ pipeline behind the reference's own model / operator API.
     from models import jpeg                  # -> neural_imaging_b200.models.jpeg
 
 Sub-packages mirror the reference layout: models/ (jpeg, pipelines, forensics, compression, layers, tfmodel),
-helpers/ (tf_helpers, kernels, paramspec, utils), compression/ (jpeg_helpers), workflows/, training/.
+helpers/ (tf_helpers, kernels, paramspec, utils, dataset, metrics), compression/ (jpeg_helpers, codec), pyfse/, workflows/, training/.
 """
 import importlib
 import sys
 
 __version__ = '0.1.0'
-_ALIASES = ('models', 'helpers', 'workflows', 'compression', 'training')
+_ALIASES = ('models', 'helpers', 'workflows', 'compression', 'training', 'pyfse')
 
 
 def install_aliases():
