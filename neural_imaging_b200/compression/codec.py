@@ -130,7 +130,7 @@ def decompress(stream, model=None, verbose=False):
     else:
         raise ValueError('Unsupported stream type!')
     if model is None:
-        raise ValueError('A DCN model is required: restoring pre-trained models by name (codec.restore) needs the Keras snapshots, SURVEY 8f N4')
+        model = restore('{}c'.format(stream[2]))        # codec.py:228-229: a preset name or a directory (raises ValueError when absent)
     if verbose:
         print('[l3ic decoder]', 'Latent space', tuple(stream[:3]))
     return decompress_batch([stream], model).numpy()
@@ -141,3 +141,36 @@ def simulate_compression(batch_x, dcn):
     compressed_image = compress(batch_x, dcn)
     batch_y = decompress(compressed_image, dcn)
     return batch_y, len(compressed_image)
+
+
+def compress_n_stats(batch_x, dcn):
+    """Code every image of the batch through the byte stream and report ssim / psnr / entropy / bytes / bpp per image
+    (codec.py:29-55; scalars instead of arrays for a batch of one)."""
+    from ..helpers import metrics
+    x = batch_x.numpy() if hasattr(batch_x, 'numpy') and not isinstance(batch_x, np.ndarray) else np.asarray(batch_x)
+    if x.ndim == 3:
+        x = x[None]
+    streams = compress_batch(x, dcn)
+    batch_y = decompress_batch(streams, dcn).numpy()
+    z = dcn.compress(x).numpy()
+    code_book = np.asarray(dcn.get_codebook(), dtype=np.float64).reshape(-1)
+    stats = {k: np.zeros((x.shape[0],)) for k in ('ssim', 'psnr', 'entropy', 'bytes', 'bpp')}
+    for i in range(x.shape[0]):
+        # helpers/stats.py:119-131 on one image's latent: histogram over the code-book bins, empty bins counted once
+        edges = np.concatenate(([-2 * np.abs(code_book).max()], np.convolve(code_book, [0.5, 0.5], mode='valid'), [2 * np.abs(code_book).max()]))
+        counts = np.histogram(z[i].reshape(-1), bins=edges)[0].clip(min=1)
+        probs = counts / counts.sum()
+        stats['entropy'][i] = -np.sum(probs * np.log2(probs))
+        stats['bytes'][i] = len(streams[i])
+        stats['ssim'][i] = metrics.ssim(x[i], batch_y[i])
+        stats['psnr'][i] = metrics.psnr(x[i], batch_y[i])
+        stats['bpp'][i] = 8 * len(streams[i]) / x[i].shape[0] / x[i].shape[1]
+    if x.shape[0] == 1:
+        stats = {k: v[0] for k, v in stats.items()}
+    return batch_y, stats
+
+
+def restore(dir_name, patch_size=None, fetch_stats=False):
+    """Restore a DCN by directory or preset name — wrapper over tfmodel.restore (codec.py:275-291)."""
+    from ..models import compression, tfmodel
+    return tfmodel.restore(dir_name, compression, key='codec', patch_size=patch_size, fetch_stats=fetch_stats)

@@ -13,6 +13,51 @@ import numpy as np
 from ..helpers import utils
 
 
+def restore(dir_name, module, key=None, patch_size=None, restore_perf=False, fetch_stats=False):
+    """Restore a trained model from a training directory (*.json training log + weights) — reference models/tfmodel.py:16-83, same
+    arguments, errors and return value; the weights are this stack's .npz snapshots (Keras .h5 interchange: SURVEY 8f N4)."""
+    training_log_path = None
+    if dir_name is None:
+        raise ValueError('dcn directory cannot be None')
+    if not os.path.exists(dir_name):
+        preset_file = 'config/presets/{}.json'.format(module.__name__.split('.')[-1])
+        if os.path.isfile(preset_file):
+            with open(preset_file) as f:
+                presets = json.load(f)
+            if dir_name in presets:
+                dir_name = presets[dir_name]
+            else:
+                raise ValueError('Directory {} does not exist & key not found in presets (config/presets/*)!'.format(dir_name))
+        else:
+            raise ValueError('Directory {} does not exist (presets not available)!'.format(dir_name))
+    for filename in Path(dir_name).glob('**/*.json'):
+        training_log_path = str(filename)
+    if training_log_path is None:
+        raise FileNotFoundError('Could not find a training log (JSON file) in {}'.format(dir_name))
+    with open(training_log_path) as f:
+        training_log = json.load(f)
+    if key is not None:
+        training_log = training_log[key]
+    parameters = dict(training_log['args'])
+    parameters['patch_size'] = patch_size
+    for k, value in parameters.items():
+        if isinstance(value, str) and value and value[0] == '(' and value[-1] == ')':
+            parameters[k] = eval(value)         # tuples are stored as strings (JSON has no tuple type)
+    model = getattr(module, training_log['model'])(**parameters)
+    model.load_model(dir_name)
+    if restore_perf:
+        model.performance = training_log['performance']
+    if fetch_stats:
+        stats = {}
+        for k, v in model.performance.items():
+            if 'validation' in v and len(v['validation']) > 0:
+                stats[k] = np.round(v['validation'][-1], 3)
+            elif 'training' in v and len(v['training']) > 0:
+                stats[k] = np.round(v['training'][-1], 3)
+        return model, stats
+    return model
+
+
 class TFModel(object):
 
     def __init__(self, **kwargs):

@@ -180,6 +180,14 @@ def test_pyfse_batch_matches_golden_and_oracle(vectors):
     # the one-string API and its exceptions (pyfse.pyx:24-72)
     one = coded[0][0]
     assert pyfse.compress(one) == coded[0][1] and pyfse.decompress(coded[0][1], len(one)) == one and pyfse.decompress(coded[0][1]) == one
+    # edges: empty and one-byte strings, and the largest layer the l3ic length table can describe (65,535 symbols: un-staged kernel path)
+    big = np.clip(np.round(np.random.RandomState(1).normal(100, 9, 65535)), 0, 255).astype(np.uint8).tobytes()
+    edge = pyfse.compress_batch([b'', b'a', big])
+    assert isinstance(edge[0], pyfse.FSENotCompressibleError) and isinstance(edge[1], pyfse.FSENotCompressibleError)
+    if lib is not None:
+        assert edge[2] == R.ref_compress(lib, big)
+    assert len(edge[2]) < 50000 and pyfse.decompress(edge[2], 65535) == big
+    assert pyfse.compress_batch([]) == [] and pyfse.decompress_batch([]) == []
     with pytest.raises(pyfse.FSESymbolRepetitionError):
         pyfse.compress(b'\x05' * 100)
     with pytest.raises(pyfse.FSENotCompressibleError):
@@ -259,7 +267,7 @@ def test_l3ic_streams_match_golden_and_oracle(vectors):
 
 
 @pytest.mark.gpu
-def test_codec_through_the_dcn_model():
+def test_codec_through_the_dcn_model(tmp_path):
     """codec.compress / decompress / simulate_compression with a TwitterDCN (compression/codec.py:18-26,87-265): the byte stream decodes
     to exactly the image the model itself reconstructs from its quantised latent, for one image and for a batch."""
     from neural_imaging_b200.compression import codec
@@ -279,6 +287,23 @@ def test_codec_through_the_dcn_model():
     assert n_bytes == len(streams[0]) and np.array_equal(y0, y[:1])
     with pytest.raises(ValueError):
         codec.decompress(12345, model)
+    # per-image statistics through the byte stream (codec.py:29-55)
+    y_b, stats = codec.compress_n_stats(x[:2], model)
+    assert np.array_equal(y_b, y[:2]) and stats['bytes'].tolist() == [len(s) for s in streams[:2]]
+    assert np.allclose(stats['bpp'], [8 * len(s) / 64 / 64 for s in streams[:2]]) and all(0 < v <= 5 for v in stats['entropy'])
+    assert all(0 < v <= 1 for v in stats['ssim']) and all(v > 0 for v in stats['psnr'])
+    # codec.restore / tfmodel.restore from a snapshot directory (models/tfmodel.py:16-83, codec.py:275-291)
+    import json
+    model.save_model(str(tmp_path))
+    with open(os.path.join(str(tmp_path), 'progress.json'), 'w') as f:
+        json.dump({'codec': {'model': 'TwitterDCN', 'args': model.get_hyperparameters(), 'performance': {}}}, f)
+    restored = codec.restore(str(tmp_path), patch_size=64)
+    assert codec.compress(x[0], restored) == streams[0]
+    assert np.array_equal(codec.decompress(streams[1], restored), y[1:2])
+    with pytest.raises(ValueError):
+        codec.restore('no-such-preset')
+    with pytest.raises(ValueError):
+        codec.decompress(streams[0])                    # no model: looks for the preset '8c' like the reference, which is absent here
 
 
 @pytest.mark.gpu
