@@ -102,14 +102,14 @@ def batch_labels(batch_size, n_classes):
 
 def training_step(P_nip, P_fan, opt_state, x, y_target, lambda_nip=0.1, lr=1e-4, train_nip=True,
                   names=('sharpen', 'resample', 'gaussian', 'jpeg'), quality=50, pool=2, nip='UNet',
-                  P_dcn=None, lambda_dcn=0.0, train_dcn=False):
-    """ManipulationClassification.training_step (:260-285): loss = ce + lambda_nip * mse; shared Keras Adam.
+                  P_dcn=None, lambda_dcn=0.0, train_dcn=False, nip_loss=None):
+    """ManipulationClassification.training_step (:260-285): loss = ce + lambda_nip * nip_loss (mse unless given); shared Keras Adam.
     opt_state = {'t': int, 'm': {name: tensor}, 'v': {...}}; parameters are updated in place. Returns loss dict + grads."""
     out = workflow_forward(P_nip, P_fan, x, names, quality, pool, nip, P_dcn)
     Y, c, C, probs = out[:4]
     n_classes = len(names) + 1
     loss_ce = R.sparse_categorical_crossentropy(batch_labels(x.shape[0], n_classes), probs)
-    loss_nip = R.mse(y_target, Y)
+    loss_nip = (nip_loss or R.mse)(y_target, Y)
     loss = loss_ce + (lambda_nip * loss_nip if train_nip else 0)
     loss_dcn = dcn_loss(c, C, out[4]) if P_dcn is not None else None
     if train_dcn:

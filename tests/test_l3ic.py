@@ -289,9 +289,9 @@ def test_codec_through_the_dcn_model(tmp_path):
         codec.decompress(12345, model)
     # per-image statistics through the byte stream (codec.py:29-55)
     y_b, stats = codec.compress_n_stats(x[:2], model)
-    assert np.array_equal(y_b, y[:2]) and stats['bytes'].tolist() == [len(s) for s in streams[:2]]
+    assert np.allclose(y_b, y[:2], atol=1e-5) and stats['bytes'].tolist() == [len(s) for s in streams[:2]]
     assert np.allclose(stats['bpp'], [8 * len(s) / 64 / 64 for s in streams[:2]]) and all(0 < v <= 5 for v in stats['entropy'])
-    assert all(0 < v <= 1 for v in stats['ssim']) and all(v > 0 for v in stats['psnr'])
+    assert all(-1 <= v <= 1 for v in stats['ssim']) and all(v > 0 for v in stats['psnr'])
     # codec.restore / tfmodel.restore from a snapshot directory (models/tfmodel.py:16-83, codec.py:275-291)
     import json
     model.save_model(str(tmp_path))
@@ -299,7 +299,7 @@ def test_codec_through_the_dcn_model(tmp_path):
         json.dump({'codec': {'model': 'TwitterDCN', 'args': model.get_hyperparameters(), 'performance': {}}}, f)
     restored = codec.restore(str(tmp_path), patch_size=64)
     assert codec.compress(x[0], restored) == streams[0]
-    assert np.array_equal(codec.decompress(streams[1], restored), y[1:2])
+    assert np.allclose(codec.decompress(streams[1], restored), y[1:2], atol=1e-5)
     with pytest.raises(ValueError):
         codec.restore('no-such-preset')
     with pytest.raises(ValueError):

@@ -143,6 +143,33 @@ def test_joint_training_step(train_nip):
     assert 0 < moved.max() <= 1.01e-4
 
 
+def test_joint_training_step_with_ssim_loss():
+    """loss_metric='SSIM' in the workflow (workflows/manipulation_classification.py:63-68 -> helpers/tf_helpers.py:39-40): the NIP part of
+    the loss and the gradients that reach the ISP through BOTH the structural loss and the manipulation / codec / FAN branch."""
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    rs = np.random.RandomState(4321)
+    B, ps = 2, 32
+    flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=ps, loss_metric='SSIM', seed=6)
+    x = rs.uniform(size=(B, ps, ps, 4)).astype(np.float32)
+    t = rs.uniform(size=(B, 2 * ps, 2 * ps, 3)).astype(np.float32)
+    s_nip, s_fan = flow.nip._store.state_dict(), flow.fan._store.state_dict()
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        Pn, Pf = M.to_params(s_nip, dt), M.to_params(s_fan, dt)
+        res[dt] = M.training_step(Pn, Pf, {'t': 0, 'm': {}, 'v': {}}, torch.tensor(x, dtype=dt), torch.tensor(t, dtype=dt), lambda_nip=0.5,
+                                  lr=1e-4, train_nip=True, nip_loss=R.ssim_loss)
+    (l64, g64), (l32, g32) = res[torch.float64], res[torch.float32]
+    loss, parts = flow.training_step(x, t, lambda_nip=0.5, learning_rate=1e-4)
+    assert abs(float(parts['nip'].numpy()) - l64['nip']) < 1e-4 * l64['nip']
+    assert abs(float(loss.numpy()) - l64['loss']) < 2e-3 * l64['loss']
+    for name, g in _grads(flow.nip._store).items():
+        ref64, ref32 = g64['nip/' + name].numpy(), g32['nip/' + name].numpy()
+        e = rel_err(g, ref64)
+        assert e < max(2e-2, 4 * rel_err(ref32, ref64)), 'nip grad {} err {}'.format(name, e)
+    with pytest.raises(ValueError):
+        ManipulationClassification('UNet', raw_patch_size=ps, loss_metric='MS-SSIM')       # the reference accepts L2 / L1 / SSIM here (:63)
+
+
 def test_onet_rgb_training_and_api_surface():
     from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
     rs = np.random.RandomState(7)
