@@ -1,5 +1,5 @@
 """Validation helpers of the manipulation-classification loop on the B200 path (API mirror of reference
-training/validation.py:163-203 `validate_fan`, :82-160 `validate_nip` without the figure rendering).
+training/validation.py:163-203 `validate_fan`, :96-160 `validate_nip`, :19-41 `validate_jpeg`, :44-93 `validate_dcn`, without the figure rendering).
 
 The reference runs batches of 10 through `flow.run_workflow_to_decisions` and builds the confusion matrix on the host with
 an n_classes^2 Python loop per batch; here the decisions stay one device->host read per batch and the matrix is one
@@ -47,3 +47,42 @@ def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type=
         ssims.append(metrics.ssim(reference, developed))
         losss.append(mse if loss_type == 'L2' else float(np.mean(np.abs(reference - developed))))
     return ssims, psnrs, losss
+
+
+def validate_jpeg(jpeg, data, batch_size=1):
+    """Mean psnr / ssim / entropy of a JPEG codec model on the validation set (reference training/validation.py:19-41)."""
+    from ..models.jpeg import JPEG
+    if not isinstance(jpeg, JPEG):
+        raise ValueError('Codec needs to be as instance of {} but is {}'.format(JPEG, getattr(jpeg, 'class_name', type(jpeg).__name__)))
+    batch_size = int(np.minimum(batch_size, data.count_validation))
+    n_batches = data.count_validation // batch_size
+    results = {k: [] for k in ('psnr', 'ssim', 'entropy')}
+    for batch_id in range(n_batches):
+        batch_x = data.next_validation_batch(batch_id, batch_size)
+        if isinstance(batch_x, tuple):
+            batch_x = batch_x[-1]
+        batch_y, entropy = jpeg.process(batch_x, return_entropy=True)
+        batch_y = batch_y.numpy() if hasattr(batch_y, 'numpy') else np.asarray(batch_y)
+        results['ssim'].append(metrics.batch(batch_x, batch_y, metrics.ssim))
+        results['psnr'].append(metrics.batch(batch_x, batch_y, metrics.psnr))
+        results['entropy'].append(entropy)
+    return {k: float(np.mean(v)) for k, v in results.items()}
+
+
+def validate_dcn(dcn, data, save_dir=None, epoch=0, show_ref=False):
+    """Validation metrics of a learned codec: {'ssim', 'psnr', 'loss', 'entropy'} over the whole validation set in one batch
+    (reference training/validation.py:44-93 without the figure; returns None for anything that is not a DCN, like the reference)."""
+    from ..models.compression import DCN
+    if not isinstance(dcn, DCN):
+        return None
+    batch_x = data.next_validation_batch(0, data.count_validation)
+    if isinstance(batch_x, tuple):
+        batch_x = batch_x[-1]
+    batch_x = np.asarray(batch_x)
+    batch_y, entropy = dcn.process(batch_x, return_entropy=True)
+    entropy = float(np.asarray(entropy.numpy()).reshape(-1)[0])
+    out = batch_y.numpy()
+    ssim = np.atleast_1d(metrics.ssim(batch_x, out)).tolist()
+    psnr = np.atleast_1d(metrics.psnr(batch_x, out)).tolist()
+    loss = float(dcn.loss(batch_x, batch_y, entropy).numpy())
+    return {'ssim': float(np.mean(ssim)), 'psnr': float(np.mean(psnr)), 'loss': loss, 'entropy': entropy}
