@@ -79,3 +79,48 @@ def test_batch_sharded_gradients_equal_full_batch_oracle():
     for gf, *gs in zip(full, *parts):
         avg = sum(gs) / world
         assert np.max(np.abs(avg - gf)) <= 1e-9 * max(1.0, np.max(np.abs(gf)))
+
+
+def _entropy_worker(rank, world, port, out):
+    """Each rank holds a shard of the quantised latent; the 32-bin soft-histogram partial sums are all-reduced BEFORE the log
+    (product: DCN.set_data_parallel -> one 32-double all-reduce), which must reproduce the single-process entropy and its
+    gradient exactly — the per-shard entropy would not (it is smaller, by concavity)."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import ref_ops as R
+    g = torch.Generator().manual_seed(7)
+    z = (torch.randn((4, 6, 6, 8), generator=g, dtype=torch.float64) * torch.tensor([0.5, 1.0, 2.0, 4.0], dtype=torch.float64).view(4, 1, 1, 1))
+    cb = torch.arange(-15, 17, dtype=torch.float64)
+    full = z.clone().requires_grad_(True)
+    h_full, _ = R.entropy(full, cb)
+    g_full, = torch.autograd.grad(h_full.double(), full)
+    per = z.shape[0] // world
+    mine = z[rank * per:(rank + 1) * per].clone().requires_grad_(True)
+    w = R._codebook_weights(mine, cb)
+    partial = w.sum(dim=0)
+    total = partial.detach().clone()
+    dist.all_reduce(total)                                           # the one data-path collective of the DCN forward
+    n_total = z.numel()
+    hist = (total / n_total).clamp(1e-9, float(np.finfo(np.float32).max))
+    hist = hist / hist.sum()
+    h_global = float(-(hist * torch.log(hist)).sum() / 0.6931)
+    # backward re-uses the GLOBAL histogram: dH/dhist at the global point, chained through this rank's own weights
+    hg = hist.clone().requires_grad_(True)
+    dh, = torch.autograd.grad(-(hg * torch.log(hg)).sum() / 0.6931, hg)
+    s = (total / n_total).sum()
+    dpartial = (dh - (dh * hist).sum()) / s / n_total                # through hist / hist.sum() and the mean over all values
+    g_mine, = torch.autograd.grad(partial, mine, grad_outputs=dpartial)
+    h_shard, _ = R.entropy(mine.detach(), cb)
+    ok = abs(h_global - float(h_full)) < 1e-6 and float((g_mine - g_full[rank * per:(rank + 1) * per]).abs().max()) < 1e-9 * max(1.0, float(g_full.abs().max()))
+    out[rank] = (bool(ok), float(h_shard), float(h_full))
+    dist.destroy_process_group()
+
+
+def test_dcn_entropy_from_allreduced_histogram_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_entropy_worker, args=(world, 29741, out), nprocs=world, join=True)
+    assert all(out[r][0] for r in range(world)), dict(out)
+    assert any(out[r][1] < out[r][2] - 1e-3 for r in range(world))      # a per-shard entropy is NOT the global one
