@@ -110,3 +110,59 @@ def test_alias_install():
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert 'neural_imaging_b200.models.jpeg ManipulationClassification' in out.stdout
+
+
+def test_reference_import_lines_for_the_codec_resolve():
+    """`from pyfse import pyfse` and `from compression import codec` (compression/codec.py:9-10, test_dcn.py) land on the device mirrors."""
+    code = ('import sys; sys.path.insert(0, %r); import neural_imaging_b200 as ni; ni.install_aliases(); '
+            'from pyfse import pyfse; from compression import codec; from training import validation; '
+            'print(pyfse.__name__, codec.L3ICError.__name__, issubclass(pyfse.FSESymbolRepetitionError, pyfse.FSEException), '
+            'hasattr(validation, "validate_dcn") and hasattr(validation, "validate_jpeg"))') % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert 'neural_imaging_b200.pyfse.pyfse L3ICError True True' in out.stdout
+
+
+def test_tfmodel_restore_host_logic(tmp_path, monkeypatch):
+    """models/tfmodel.py:16-83 `restore(dir_name, module, key, patch_size, restore_perf, fetch_stats)`: training-log discovery, key
+    lookup, tuple strings, presets and their errors — with a stand-in model class (no device needed)."""
+    import json
+    import types
+    from neural_imaging_b200.models import tfmodel
+
+    class Dummy:
+        def __init__(self, **kw):
+            self.kw, self.loaded = kw, None
+            self.performance = {'loss': {'training': [], 'validation': []}}
+
+        def load_model(self, dirname):
+            self.loaded = dirname
+    module = types.ModuleType('pkg.compression')
+    module.Dummy = Dummy
+    d = tmp_path / 'run' / 'dummy'
+    d.mkdir(parents=True)
+    log = {'codec': {'model': 'Dummy', 'args': {'n_features': 8, 'shape': '(4, 4)', 'name': 'x'},
+                     'performance': {'loss': {'training': [3.0, 2.0], 'validation': [2.5, 1.23456]}, 'ssim': {'training': [0.5], 'validation': []}}}}
+    (d / 'progress.json').write_text(json.dumps(log))
+    m = tfmodel.restore(str(tmp_path / 'run'), module, key='codec', patch_size=64)
+    assert isinstance(m, Dummy) and m.kw == {'n_features': 8, 'shape': (4, 4), 'name': 'x', 'patch_size': 64} and m.loaded == str(tmp_path / 'run')
+    m, stats = tfmodel.restore(str(tmp_path / 'run'), module, key='codec', restore_perf=True, fetch_stats=True)
+    assert m.kw['patch_size'] is None and stats == {'loss': 1.235, 'ssim': 0.5}
+    _, stats = tfmodel.restore(str(tmp_path / 'run'), module, key='codec', fetch_stats=True)
+    assert stats == {}                                       # without restore_perf the statistics are those of the fresh model
+    with pytest.raises(ValueError):
+        tfmodel.restore(None, module)
+    with pytest.raises(KeyError):
+        tfmodel.restore(str(tmp_path / 'run'), module, key='nip')
+    empty = tmp_path / 'empty'
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        tfmodel.restore(str(empty), module)
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(ValueError, match='presets not available'):
+        tfmodel.restore('32c', module)
+    (tmp_path / 'config' / 'presets').mkdir(parents=True)
+    (tmp_path / 'config' / 'presets' / 'compression.json').write_text(json.dumps({'32c': str(tmp_path / 'run')}))
+    assert isinstance(tfmodel.restore('32c', module, key='codec'), Dummy)
+    with pytest.raises(ValueError, match='key not found in presets'):
+        tfmodel.restore('64c', module)
