@@ -1,0 +1,209 @@
+"""Host logic of the stand-alone training loops (reference training/pipeline.py:105-258 `train_nip_model`, training/compression.py:123-309
+`train_dcn`) with stand-in models: schedules, directory layout, resume, snapshots, progress.json, early stopping, error behaviour.
+The real models' `training_step` / `process` / `compress` are covered by the GPU parity tests; nothing here needs a device (the SSIM
+metric, a device kernel in the product, is replaced by a NumPy stand-in for these tests only)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from neural_imaging_b200.models.tfmodel import TFModel
+
+
+class _Data:
+    def __init__(self, n_train=8, n_val=4, raw=True, size=32):
+        self.count_training, self.count_validation, self.raw, self.size = n_train, n_val, raw, size
+        self.calls = []
+        rs = np.random.RandomState(0)
+        self._val_y = rs.uniform(size=(n_val, size, size, 3)).astype(np.float32)
+
+    def __getitem__(self, key):
+        n = self.count_training if key == 'training' else self.count_validation
+        return {'x': np.zeros((n, self.size // 2, self.size // 2, 4)), 'y': np.zeros((n, self.size, self.size, 3))}
+
+    def next_training_batch(self, batch_id, batch_size, rgb_patch_size, discard='flat'):
+        self.calls.append((batch_id, batch_size, rgb_patch_size, discard))
+        y = np.full((batch_size, rgb_patch_size, rgb_patch_size, 3), 0.25, np.float32)
+        y[:, 0, 0, 0] = 1.0                     # a marker pixel: flips move it
+        if not self.raw:
+            return y
+        return np.zeros((batch_size, rgb_patch_size // 2, rgb_patch_size // 2, 4), np.float32), y
+
+    def next_validation_batch(self, batch_id, batch_size):
+        y = self._val_y[batch_id * batch_size:(batch_id + 1) * batch_size]
+        return (np.zeros((len(y), self.size // 2, self.size // 2, 4), np.float32), y) if self.raw else y
+
+    def summary(self):
+        return 'stand-in data'
+
+
+class _NIP(TFModel):
+    loss_metric = 'L2'
+    model_code = 'FakeNet'
+
+    def __init__(self, losses=None):
+        super().__init__()
+        self.performance = self._reset_performance(['loss', 'psnr', 'ssim'])
+        self.lrs, self.saved, self.loaded, self.quality = [], [], None, 0.5
+        self._losses = losses
+
+    def training_step(self, x, y, lr):
+        self.lrs.append(lr)
+        return 10.0 / len(self.lrs)
+
+    def process(self, x):
+        n = len(x)
+
+        class _T:
+            def numpy(_):
+                return np.full((n, 32, 32, 3), self.quality, np.float32)
+        if self._losses:
+            self.quality = self._losses[min(len(self.performance['loss']['validation']), len(self._losses) - 1)]
+        return _T()
+
+    def save_model(self, dirname, epoch=0, quiet=False):
+        self.saved.append(epoch)
+
+    def load_model(self, dirname):
+        self.loaded = dirname
+
+    def get_hyperparameters(self):
+        return {'in_channels': 4}
+
+    def summary(self):
+        return 'FakeNet summary'
+
+
+@pytest.fixture
+def numpy_ssim(monkeypatch):
+    from neural_imaging_b200.helpers import metrics
+    monkeypatch.setattr(metrics, 'ssim', lambda a, b: 1.0 - float(np.mean(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)))))
+
+
+def test_train_nip_model_loop(tmp_path, numpy_ssim):
+    from neural_imaging_b200.training import pipeline
+    data, model = _Data(), _NIP()
+    out = pipeline.train_nip_model(model, 'cam', n_epochs=7, lr_schedule={0: 1e-3, 4: 1e-4}, validation_schedule=3, patch_size=16, batch_size=4,
+                                   data=data, out_directory_root=str(tmp_path))
+    assert out == os.path.join(str(tmp_path), 'cam', 'FakeNet', model.scoped_name) and os.path.isfile(os.path.join(out, 'progress.json'))
+    assert data.calls[0] == (0, 5, 32, 'flat') and data.calls[1] == (0, 4, 16, 'flat')            # the shape probe, then the loop's own call
+    assert model.lrs == [1e-3] * 8 + [1e-4] * 6                                                   # 2 batches x 7 epochs, schedule at epoch 4
+    assert len(model.performance['loss']['training']) == 7 and len(model.performance['loss']['validation']) == 3      # epochs 0, 3, 6
+    assert model.saved == [0, 3, 6, 6]                                                            # every validation + the final snapshot
+    log = json.load(open(os.path.join(out, 'progress.json')))
+    assert set(log) == {'performance', 'args', 'model', 'init', 'summary'} and log['model'] == '_NIP' and log['summary']['Epoch'] == 6
+    assert log['summary']['Saved checkpoint'] == 6 and log['summary']['# batches'] == 2 and log['summary']['Training data size'] == [8, 16, 16, 4]
+    expect = np.mean([np.mean((255 * y.astype(np.float64) - 127.5) ** 2) for y in data._val_y])       # metrics.mse(255 ref, 255 developed), mean over images
+    assert abs(log['performance']['loss']['validation'][0] - expect) < 1e-6 * expect
+    # an existing directory is skipped unless resuming; resume restores counters, performance and weights
+    again = _NIP()
+    assert pipeline.train_nip_model(again, 'cam', n_epochs=3, data=data, patch_size=16, batch_size=4, out_directory_root=str(tmp_path)) == out
+    assert again.lrs == []
+    resumed = _NIP()
+    pipeline.train_nip_model(resumed, 'cam', n_epochs=9, lr_schedule=5e-4, validation_schedule=3, resume=True, patch_size=16, batch_size=4,
+                             data=data, out_directory_root=str(tmp_path))
+    assert resumed.loaded == out and len(resumed.lrs) == 2 * (9 - 6) and resumed.lrs[0] == 1e-4       # float schedule = {0: lr}: epoch 0 is past
+    assert len(resumed.performance['loss']['training']) == 7 + 3
+    with pytest.raises(FileNotFoundError):
+        pipeline.train_nip_model(_NIP(), 'other', resume=True, data=data, patch_size=16, batch_size=4, out_directory_root=str(tmp_path / 'x'))
+    # errors (training/pipeline.py:109-121)
+    with pytest.raises(ValueError, match='not to be loaded'):
+        pipeline.train_nip_model(_NIP(), 'cam', data=None)
+    with pytest.raises(ValueError, match='exceeds dataset size'):
+        pipeline.train_nip_model(_NIP(), 'cam', data=data, patch_size=16, batch_size=50, out_directory_root=str(tmp_path / 'y'))
+    with pytest.raises(ValueError, match='Data set error'):
+        pipeline.train_nip_model(_NIP(), 'cam', data=_Data(raw=False), patch_size=16, batch_size=4, out_directory_root=str(tmp_path / 'z'))
+    with pytest.raises(ValueError, match='Unsupported loss'):
+        pipeline.validate(model, data, out, loss_metric='L3')
+
+
+def test_train_nip_model_best_checkpoint_lr_drop_and_early_stop(tmp_path, numpy_ssim):
+    from neural_imaging_b200.training import pipeline
+    data = _Data()
+    # validation quality per validation round: improves, then gets >20 % worse (lr drop, no snapshot with save_best), then goes flat
+    q = [0.30, 0.40, 0.45, 0.45, 0.45, 0.45, 0.10, 0.45] + [0.45] * 12
+    model = _NIP(losses=q)
+    pipeline.train_nip_model(model, 'cam', n_epochs=40, lr_schedule={0: 1e-3}, validation_schedule=1, patch_size=16, batch_size=4, data=data,
+                             out_directory_root=str(tmp_path), save_best=True, validation_loss_threshold=1e-3)
+    v = model.performance['loss']['validation']
+    assert len(v) < 40                                           # stopped early on the flat validation loss
+    assert 6 not in model.saved and model.saved[0] == 2          # save_best: needs > 2 validations, never the deteriorated round
+    dropped = [lr for lr in model.lrs if lr < 1e-3]
+    assert dropped and abs(dropped[0] - 0.95e-3) < 1e-12         # one 0.95 drop after the deterioration (len > 5 and > 1.2 x best)
+
+
+class _DCN(TFModel):
+    model_code = 'FakeDCN/8c'
+
+    class _H:
+        scale_latent = False
+        train_codebook = False
+
+    def __init__(self, ssims):
+        super().__init__()
+        self.performance = self._reset_performance(['loss', 'entropy', 'ssim', 'psnr'])
+        self._h, self.lrs, self.saved, self.markers, self._ssims = self._H(), [], [], [], ssims
+
+    def training_step(self, x, lr):
+        self.lrs.append(lr)
+        self.markers.append(tuple(int(v) for v in np.argwhere(x[0, :, :, 0] == 1.0)[0]))
+        assert x.flags['C_CONTIGUOUS'] and x.dtype == np.float32
+        return {'loss': 4.0, 'ssim': 0.5, 'entropy': 2.0}
+
+    def compress(self, x):
+        class _T:
+            def numpy(_):
+                return np.round(np.linspace(-3, 3, len(x) * 16)).reshape(len(x), 4, 4, 1)
+        return _T()
+
+    def decompress(self, z):
+        n_val = len(self.performance['ssim']['validation'])
+        err = 1.0 - self._ssims[min(n_val, len(self._ssims) - 1)]
+
+        class _T:
+            def numpy(_):
+                return self._x - err
+        return _T()
+
+    def get_codebook(self):
+        return np.arange(-15, 17, dtype=np.float32)
+
+    def get_hyperparameters(self):
+        return {'n_features': 8}
+
+    def save_model(self, dirname, epoch=0, quiet=False):
+        self.saved.append(epoch)
+
+
+def test_train_dcn_loop(tmp_path, numpy_ssim, monkeypatch):
+    from neural_imaging_b200.training import compression
+    data = _Data(raw=False)
+    spec = {'n_epochs': 30, 'batch_size': 4, 'patch_size': 32, 'learning_rate': 1e-3, 'learning_rate_reduction_schedule': 2,
+            'learning_rate_reduction_factor': 0.5, 'validation_schedule': 1, 'convergence_threshold': 1e-4,
+            'augmentation_probs': {'resize': 0.0, 'flip_h': 1.0, 'flip_v': 0.0, 'gamma': 0.0}}
+    dcn = _DCN(ssims=[0.5, 0.6, 0.7, 0.8, 0.85, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9])
+    orig = data.next_validation_batch
+    monkeypatch.setattr(data, 'next_validation_batch', lambda b, n: setattr(dcn, '_x', orig(b, n)) or orig(b, n))
+    out = compression.train_dcn(dcn, spec, data, directory=str(tmp_path))
+    assert out == os.path.join(str(tmp_path), 'FakeDCN/8c', dcn.scoped_name) and os.path.isdir(out)
+    assert dcn.lrs[:2] == [1e-3, 1e-3] and dcn.lrs[4] == 0.5e-3 and dcn.lrs[8] == 0.25e-3           # 2 batches / epoch, halved every 2 epochs
+    assert all(m == (0, 31) for m in dcn.markers)                                                    # flip_h moved the marker to the last column
+    n_epochs_run = len(dcn.performance['loss']['training'])
+    assert 6 < n_epochs_run < 30 and dcn.saved == list(range(n_epochs_run))                          # early stop once the validation SSIM is flat
+    assert dcn.performance['loss']['training'][0] == 4.0 and dcn.performance['entropy']['training'][0] == 2.0
+    assert abs(dcn.performance['ssim']['validation'][0] - 0.5) < 1e-6 and spec['current_epoch'] == n_epochs_run - 1
+    log = json.load(open(os.path.join(out, 'progress.json')))
+    assert set(log) == {'training_spec', 'data', 'codec'} and set(log['codec']) == {'model', 'init', 'args', 'codebook', 'performance'}
+    assert log['codec']['model'] == '_DCN' and len(log['codec']['codebook']) == 32 and log['data'] == 'stand-in data'
+    assert 0 < log['codec']['performance']['entropy']['validation'][0] < 5
+    # existing directory: skipped unless overwrite; deterioration by more than 10 % stops the loop; unavailable augmentation raises
+    assert compression.train_dcn(_DCN([0.5]), spec, data, directory=str(tmp_path)) is None
+    bad = _DCN(ssims=[0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.2, 0.2])
+    monkeypatch.setattr(data, 'next_validation_batch', lambda b, n: setattr(bad, '_x', orig(b, n)) or orig(b, n))
+    compression.train_dcn(bad, dict(spec, convergence_threshold=0.0), data, directory=str(tmp_path), overwrite=True)
+    assert len(bad.performance['ssim']['validation']) == 7
+    with pytest.raises(NotImplementedError):
+        compression.train_dcn(_DCN([0.5]), dict(spec, augmentation_probs={'resize': 1.0, 'flip_h': 0, 'flip_v': 0, 'gamma': 0}), data,
+                              directory=str(tmp_path / 'r'))
+    assert abs(compression.latent_entropy(np.array([0.0, 0.0, 1.0, 1.0]), np.arange(-1, 3)) - (-(2 * 2 / 6 * np.log2(2 / 6) + 2 * 1 / 6 * np.log2(1 / 6)))) < 1e-12
