@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(32) l3ic_parse_kernel(const unsigned char* __r
     const int nl = in[3] | in[4] << 8;
     if (5 + nl > total) { flag(status, img, kStatusTruncated); return; }
     const unsigned char* tab = in + 5;
+    if (nl > 2 * c) { flag(status, img, kStatusLengths); return; }      // a coded table is always shorter than the raw one (bounds `lens`)
     if (nl != 2 * c) {
         const int got = fse::decompress(lens, (uint32_t)(10 * nl), tab, (uint32_t)nl, S);      // pyfse.decompress default capacity: 10 x input
         if (got < 2 * c) { flag(status, img, kStatusLengths); return; }
