@@ -13,3 +13,17 @@ extern "C" int fse_host_decompress(uint8_t* dst, uint32_t cap, const uint8_t* sr
     static fse::DecScratch S;
     return fse::decompress(dst, cap, src, n, S);
 }
+
+// Stages of the coder on their own, for direct comparison with FSE_normalizeCount / FSE_writeNCount / FSE_readNCount of the reference library
+// on inputs that FSE_compress itself rarely produces (fallback-normalisation branches, long zero runs in the header).
+extern "C" int fse_host_normalize(int16_t* norm, uint32_t table_log, const uint32_t* count, uint32_t total, uint32_t max_symbol) {
+    return fse::normalize(norm, table_log, count, total, max_symbol);
+}
+
+extern "C" int fse_host_write_ncount(uint8_t* out, uint32_t cap, const int16_t* norm, uint32_t max_symbol, uint32_t table_log) {
+    return fse::write_ncount(out, cap, norm, max_symbol, table_log);
+}
+
+extern "C" int fse_host_read_ncount(int16_t* norm, uint32_t* max_symbol, uint32_t* table_log, const uint8_t* hdr, uint32_t hdr_size) {
+    return fse::read_ncount(norm, max_symbol, table_log, hdr, hdr_size);
+}

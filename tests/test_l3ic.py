@@ -321,3 +321,94 @@ def test_large_batch_round_trip():
     assert total < 0.5 * z.numel()                       # ~2.4 bits per symbol of entropy: well under a byte per latent value
     for i in (0, 777, 1279):
         assert streams[i] == R.l3ic_compress(z[i:i + 1].numpy(), book)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the coder's stages on their own
+def _count_tables(seed, n_cases):
+    """Histograms FSE_compress itself rarely produces: they drive the fallback normalisation through all of its branches ("risk of rounding
+    to zero", "all values are pretty poor", "total == 0") and the header writer through long zero runs."""
+    rs = np.random.RandomState(seed)
+    for _ in range(n_cases):
+        m = int(rs.randint(1, 256))
+        kind = rs.randint(0, 8)
+        if kind == 0:
+            count = rs.randint(0, 50, m + 1)
+        elif kind == 1:
+            count = (rs.rand(m + 1) < 0.3) * rs.randint(1, 4, m + 1)
+        elif kind == 2:
+            count = np.ones(m + 1, np.int64)
+            count[rs.randint(0, m + 1)] = rs.randint(1, 100000)
+        elif kind == 3:
+            count = rs.geometric(0.01, m + 1) * (rs.rand(m + 1) < 0.5)
+        elif kind == 4:
+            count = np.full(m + 1, rs.randint(1, 5))
+        elif kind == 5:
+            count = (rs.zipf(1.3, m + 1) % 5000) * (rs.rand(m + 1) < 0.7)
+        else:
+            if kind == 7:
+                m = int(rs.randint(20, 256))
+            count = np.zeros(m + 1, np.int64)
+            idx = rs.permutation(m + 1)
+            k = rs.randint(8 if kind == 7 else 0, m + 1)
+            j = rs.randint(0, 3) if kind == 7 else rs.randint(0, max(1, m + 1 - k))
+            nb = 0 if kind == 7 else rs.randint(0, 4)
+            a = rs.randint(1, 3)
+            count[idx[:k]] = a
+            count[idx[k:k + j]] = a * rs.randint(1, 4)
+            count[idx[k + j:k + j + nb]] = rs.choice([50, 500, 5000, 50000, 1000000])
+        count = np.asarray(count, dtype=np.uint32)
+        if count[m] == 0:
+            count[m] = 1
+        if int(count.sum()) >= 2:
+            yield m, count, int(rs.randint(5, 10 if kind == 7 else 13))
+
+
+def test_normalisation_and_header_stages_match_reference_library(tmp_path):
+    lib = R.reference_library()
+    if lib is None:
+        pytest.skip('oracle/_ref not built (make -C oracle needs /root/reference)')
+    so = str(tmp_path / 'libfse_host.so')
+    subprocess.check_call(['g++', '-O2', '-fPIC', '-shared', '-o', so, os.path.join(ROOT, 'tests', 'fse_host_harness.cpp')])
+    host = ctypes.CDLL(so)
+    for fn in (lib.FSE_normalizeCount, lib.FSE_writeNCount, lib.FSE_readNCount):
+        fn.restype = ctypes.c_size_t
+    agree = rejected = 0
+    rs = np.random.RandomState(1)
+    for m, count, tl in _count_tables(17, 2500):
+        total = int(count.sum())
+        c = (ctypes.c_uint32 * 256)(*([int(v) for v in count] + [0] * (255 - m)))
+        n0, n1 = (ctypes.c_int16 * 256)(), (ctypes.c_int16 * 256)()
+        args = (ctypes.c_uint(tl), c, ctypes.c_size_t(total), ctypes.c_uint(m))
+        pid = os.fork()                  # the reference divides by zero on a few out-of-domain tables: probe each one in a child first
+        if pid == 0:
+            lib.FSE_normalizeCount(n0, *args)
+            os._exit(0)
+        if os.waitpid(pid, 0)[1] != 0:
+            continue
+        r0 = lib.FSE_normalizeCount(n0, *args)
+        r1 = host.fse_host_normalize(n1, tl, c, total, m)
+        failed = bool(lib.FSE_isError(ctypes.c_size_t(r0)))
+        assert failed == (r1 < 0), (tl, m, total)
+        if failed:
+            rejected += 1
+            continue
+        assert r0 == r1
+        if r0 == 0:
+            continue
+        assert list(n0)[:m + 1] == list(n1)[:m + 1], (tl, m, total)
+        agree += 1
+        b0, b1 = ctypes.create_string_buffer(600), ctypes.create_string_buffer(600)
+        w0 = lib.FSE_writeNCount(b0, ctypes.c_size_t(512), n0, ctypes.c_uint(m), ctypes.c_uint(tl))
+        w1 = host.fse_host_write_ncount(b1, 512, n1, m, tl)
+        assert not lib.FSE_isError(ctypes.c_size_t(w0)) and w0 == w1 and b0.raw[:w0] == b1.raw[:w1]
+        for cut in (w0, w0 + 5, max(1, w0 - 1), 3, 2):          # exact, padded with noise, truncated, shorter than the 4-byte minimum
+            hdr = b0.raw[:cut] if cut <= w0 else b0.raw[:w0] + bytes(rs.randint(0, 256, cut - w0).astype(np.uint8))
+            a0, a1 = (ctypes.c_int16 * 256)(), (ctypes.c_int16 * 256)()
+            ms0, tl0, ms1, tl1 = ctypes.c_uint(255), ctypes.c_uint(0), ctypes.c_uint32(255), ctypes.c_uint32(0)
+            q0 = lib.FSE_readNCount(a0, ctypes.byref(ms0), ctypes.byref(tl0), hdr, ctypes.c_size_t(len(hdr)))
+            q1 = host.fse_host_read_ncount(a1, ctypes.byref(ms1), ctypes.byref(tl1), hdr, len(hdr))
+            bad = bool(lib.FSE_isError(ctypes.c_size_t(q0)))
+            assert bad == (q1 < 0), (cut, w0)
+            if not bad:
+                assert q0 == q1 and ms0.value == ms1.value and tl0.value == tl1.value and list(a0) == list(a1)
+    assert agree > 1000 and rejected > 100
