@@ -328,6 +328,14 @@ def _count_tables(seed, n_cases):
     """Histograms FSE_compress itself rarely produces: they drive the fallback normalisation through all of its branches ("risk of rounding
     to zero", "all values are pretty poor", "total == 0") and the header writer through long zero runs."""
     rs = np.random.RandomState(seed)
+    ones = np.ones(43, dtype=np.uint32)
+    yield 42, ones, 6                                                   # 43 symbols seen once, 64 cells: every symbol is "poor"
+    for tl in (6, 7):
+        for n_once in (43, 50, 86, 100):
+            c = np.zeros(128, np.uint32)
+            c[:n_once] = 1
+            c[127] = 1                                                  # unused symbols in between: the "total == 0" hand-out loop
+            yield 127, c, tl
     for _ in range(n_cases):
         m = int(rs.randint(1, 256))
         kind = rs.randint(0, 8)
