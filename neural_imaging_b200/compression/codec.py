@@ -147,6 +147,7 @@ def compress_n_stats(batch_x, dcn):
     """Code every image of the batch through the byte stream and report ssim / psnr / entropy / bytes / bpp per image
     (codec.py:29-55; scalars instead of arrays for a batch of one)."""
     from ..helpers import metrics
+    from ..training.compression import latent_entropy
     x = batch_x.numpy() if hasattr(batch_x, 'numpy') and not isinstance(batch_x, np.ndarray) else np.asarray(batch_x)
     if x.ndim == 3:
         x = x[None]
@@ -156,11 +157,7 @@ def compress_n_stats(batch_x, dcn):
     code_book = np.asarray(dcn.get_codebook(), dtype=np.float64).reshape(-1)
     stats = {k: np.zeros((x.shape[0],)) for k in ('ssim', 'psnr', 'entropy', 'bytes', 'bpp')}
     for i in range(x.shape[0]):
-        # helpers/stats.py:119-131 on one image's latent: histogram over the code-book bins, empty bins counted once
-        edges = np.concatenate(([-2 * np.abs(code_book).max()], np.convolve(code_book, [0.5, 0.5], mode='valid'), [2 * np.abs(code_book).max()]))
-        counts = np.histogram(z[i].reshape(-1), bins=edges)[0].clip(min=1)
-        probs = counts / counts.sum()
-        stats['entropy'][i] = -np.sum(probs * np.log2(probs))
+        stats['entropy'][i] = latent_entropy(z[i], code_book)          # helpers/stats.py:119-131 on one image's latent
         stats['bytes'][i] = len(streams[i])
         stats['ssim'][i] = metrics.ssim(x[i], batch_y[i])
         stats['psnr'][i] = metrics.psnr(x[i], batch_y[i])

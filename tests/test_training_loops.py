@@ -207,3 +207,28 @@ def test_train_dcn_loop(tmp_path, numpy_ssim, monkeypatch):
         compression.train_dcn(_DCN([0.5]), dict(spec, augmentation_probs={'resize': 1.0, 'flip_h': 0, 'flip_v': 0, 'gamma': 0}), data,
                               directory=str(tmp_path / 'r'))
     assert abs(compression.latent_entropy(np.array([0.0, 0.0, 1.0, 1.0]), np.arange(-1, 3)) - (-(2 * 2 / 6 * np.log2(2 / 6) + 2 * 1 / 6 * np.log2(1 / 6)))) < 1e-12
+
+
+def test_codec_statistics_helpers_match_reference_execution():
+    """latent_entropy (helpers/stats.py:107-131, used by codec.compress_n_stats and train_dcn) and batch_gamma (helpers/image.py:22-28) against
+    tests/golden/codec_stats.npz, which tests/golden/make_codec_stats_golden.py produced by executing the reference's own functions."""
+    from conftest import GOLDEN
+    from neural_imaging_b200.training import compression
+    with np.load(os.path.join(GOLDEN, 'codec_stats.npz')) as d:
+        g = {k: d[k] for k in d.files}
+    n = 0
+    while 'z_%d_0' % n in g:
+        for j in range(3):
+            key = '%d_%d' % (n, j)
+            assert abs(compression.latent_entropy(g['z_' + key], g['cb_' + key]) - float(g['entropy_' + key])) < 1e-12
+        n += 1
+    assert n == 3
+    assert np.array_equal(compression.batch_gamma(g['gamma_in'], 2.0), g['gamma_out_2p0'])
+    assert np.array_equal(compression.batch_gamma(g['gamma_in'], g['gamma_vec']), g['gamma_out_vec'])
+    np.random.seed(3)
+    out = compression.batch_gamma(g['gamma_in'])
+    assert out.shape == g['gamma_in'].shape and out.dtype == np.float32 and 0 <= out.min() and out.max() <= 1
+    # the code path of codec.compress_n_stats imports the same function
+    import inspect
+    from neural_imaging_b200.compression import codec
+    assert 'latent_entropy' in inspect.getsource(codec.compress_n_stats)
