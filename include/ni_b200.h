@@ -2,7 +2,7 @@
  * ni_b200 — C-ABI of the B200-native neural-imaging hot path (libni_b200.so).
  *
  * The reference (pkorus/neural-imaging) has NO FFI on this path: every operator below is a chain of TensorFlow ops
- * issued from Python (models/*.py, helpers/tf_helpers.py, workflows/manipulation_classification.py). Each entry point
+ * issued from Python (models/ (all modules), helpers/tf_helpers.py, workflows/manipulation_classification.py). Each entry point
  * therefore cites the reference Python code it replaces; INTEGRATION.md shows the ctypes stub a maintainer adds.
  *
  * Conventions

@@ -166,3 +166,13 @@ def test_tfmodel_restore_host_logic(tmp_path, monkeypatch):
     assert isinstance(tfmodel.restore('32c', module, key='codec'), Dummy)
     with pytest.raises(ValueError, match='key not found in presets'):
         tfmodel.restore('64c', module)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/ni_b200.h must compile on its own as C and as C++ (no torch / CUDA types in the signatures)."""
+    header = os.path.join(ROOT, 'include', 'ni_b200.h')
+    for lang, cc in (('c', 'gcc'), ('c++', 'g++')):
+        out = subprocess.run([cc, '-fsyntax-only', '-Wall', '-Werror', '-x', lang, header], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    src = open(header).read()
+    assert 'torch' not in src and 'at::Tensor' not in src and '#include <cuda' not in src
