@@ -106,6 +106,7 @@ def train_manipulation_nip(flow, training, data, directories=None, overwrite=Fal
             if flow.is_trainable('nip') and data.is_raw_and_rgb():
                 for metric, values in zip(('ssim', 'psnr', 'loss'), validation.validate_nip(flow.nip, data, None, epoch=epoch, loss_type=flow.nip.loss_metric)):
                     flow.nip.log_metric(metric, 'validation', values)
+            validation.save_training_progress(summary, flow, save_dir, quiet=True)
             flow.fan.save_model(os.path.join(model_directory, flow.fan.scoped_name), epoch, quiet=True)
             if flow.is_trainable('nip'):
                 flow.nip.save_model(os.path.join(model_directory, flow.nip.scoped_name), epoch, quiet=True)

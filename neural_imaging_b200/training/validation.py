@@ -6,6 +6,10 @@ an n_classes^2 Python loop per batch; here the decisions stay one device->host r
 np.add.at. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does; SSIM
 (skimage structural_similarity in the reference, helpers/metrics.py:9-26) runs in the fused device kernel ni_ssim.
 """
+import json
+import os
+from collections import OrderedDict
+
 import numpy as np
 
 from ..helpers import metrics
@@ -86,3 +90,38 @@ def validate_dcn(dcn, data, save_dir=None, epoch=0, show_ref=False):
     psnr = np.atleast_1d(metrics.psnr(batch_x, out)).tolist()
     loss = float(dcn.loss(batch_x, batch_y, entropy).numpy())
     return {'ssim': float(np.mean(ssim)), 'psnr': float(np.mean(psnr)), 'loss': loss, 'entropy': entropy}
+
+
+def save_training_progress(training_summary, flow, root_dir, quiet=False):
+    """Write `<root_dir>/training.json`: summary, channel, classes and per-model (nip / forensics / codec) constructor + hyper-parameters +
+    performance logs — the file the reference's result analysis and resume logic read (reference training/validation.py:301-352)."""
+    training = OrderedDict()
+    training['summary'] = training_summary
+    training['distribution'] = flow._distribution
+    training['manipulations'] = flow._forensics_classes
+    training['nip'] = OrderedDict()
+    training['nip']['model'] = flow.nip.class_name
+    training['nip']['init'] = repr(flow.nip)
+    training['nip']['args'] = flow.nip._h.to_json() if hasattr(flow.nip, '_h') else {}
+    training['nip']['performance'] = flow.nip.performance
+    training['forensics'] = OrderedDict()
+    training['forensics']['model'] = flow.fan.class_name
+    training['forensics']['init'] = repr(flow.fan)
+    training['forensics']['args'] = flow.fan._h.to_json()
+    training['forensics']['performance'] = flow.fan.performance
+    codec = getattr(flow, 'codec', None)
+    if codec is not None:
+        training['codec'] = OrderedDict()
+        training['codec']['model'] = codec.class_name
+        training['codec']['init'] = repr(codec)
+        if hasattr(codec, '_h'):
+            training['codec']['args'] = codec._h.to_json()
+        if hasattr(codec, 'performance'):
+            training['codec']['performance'] = codec.performance
+    os.makedirs(root_dir, exist_ok=True)
+    filename = os.path.join(root_dir, 'training.json')
+    if not quiet:
+        print('> Training progress --> {}'.format(filename))
+    with open(filename, 'w') as f:
+        json.dump(training, f, indent=4, default=str)       # anything exotic in a user-supplied channel description is logged as text
+    return filename

@@ -232,3 +232,30 @@ def test_codec_statistics_helpers_match_reference_execution():
     import inspect
     from neural_imaging_b200.compression import codec
     assert 'latent_entropy' in inspect.getsource(codec.compress_n_stats)
+
+
+def test_save_training_progress_layout(tmp_path):
+    """training/validation.py:301-352: the training.json written at every validation epoch of the manipulation-classification loop."""
+    import types
+    from neural_imaging_b200.helpers import paramspec
+    from neural_imaging_b200.training import validation
+
+    def model(name, perf, with_h=True):
+        m = types.SimpleNamespace(class_name=name, performance=perf)
+        if with_h:
+            m._h = paramspec.ParamSpec({'n_filters': (32, int, (1, 1024)), 'activation': ('leaky_relu', str, {'leaky_relu', 'relu'})})
+        return m
+    flow = types.SimpleNamespace(
+        _distribution={'downsampling': 'pool:2', 'compression': 'jpeg', 'compression_params': {'quality': (50, 90), 'codec': 'soft', 'odd': np.float32(1.5)}},
+        _forensics_classes=['native', 'sharpen:1'],
+        nip=model('UNet', {'loss': {'training': [1.0, 0.5], 'validation': [0.7]}}, with_h=False),
+        fan=model('FAN', {'loss': {'training': [2.0], 'validation': []}, 'accuracy': {'training': [], 'validation': [0.4]}, 'confusion': [[1.0, 0.0], [0.5, 0.5]]}),
+        codec=model('JPEG', {'entropy': {'training': [], 'validation': [float('nan')]}}, with_h=False))
+    path = validation.save_training_progress({'Problem': 'toy', '# Epochs': 3}, flow, str(tmp_path / 'run' / '001'), quiet=True)
+    log = json.load(open(path))
+    assert os.path.basename(path) == 'training.json' and list(log) == ['summary', 'distribution', 'manipulations', 'nip', 'forensics', 'codec']
+    assert log['nip']['args'] == {} and log['forensics']['args'] == {'n_filters': 32, 'activation': 'leaky_relu'} and 'args' not in log['codec']
+    assert log['distribution']['compression_params']['quality'] == [50, 90] and log['forensics']['performance']['confusion'][1] == [0.5, 0.5]
+    assert log['manipulations'] == ['native', 'sharpen:1'] and log['summary']['# Epochs'] == 3
+    flow.codec = None
+    assert 'codec' not in json.load(open(validation.save_training_progress({}, flow, str(tmp_path / 'run' / '002'), quiet=True)))
