@@ -140,7 +140,7 @@ COLOR_I = np.array([[-1.402 * 128, 1, 0, 1.402], [1.058272 * 128, 1, -0.344136, 
 # ------------------------------------------------------------------------------------------------ quantisation
 def quantization(x, rounding):
     """models/layers.py:118-136 ('harmonic': taylor_terms receives 1 positionally, so only the first term is active)."""
-    c = torch.tensor(TWO_PI, dtype=torch.float32).to(x.dtype)     # TF casts the python scalar to the tensor dtype
+    c = torch.tensor(TWO_PI, dtype=x.dtype)     # TF casts the python scalar to the tensor dtype (float32 in the reference; exact in the float64 truth run)
     if rounding == 'round':
         return torch.round(x)
     if rounding == 'sin':
@@ -157,7 +157,7 @@ def quantization(x, rounding):
 
 def soft_quantization(x, alpha=255):
     """helpers/tf_helpers.py:271-277."""
-    c = torch.tensor(TWO_PI, dtype=torch.float32).to(x.dtype)
+    c = torch.tensor(TWO_PI, dtype=x.dtype)
     x = alpha * x
     x_ = x - torch.sin(c * x) / c
     return ((torch.round(x) - x_).detach() + x_) / alpha

@@ -1,0 +1,9 @@
+"""Import stub (tests/tf_shim): lets the reference modules import where this third-party package is absent. TEST INFRASTRUCTURE."""
+
+
+def imread(*a, **k):
+    raise NotImplementedError
+
+
+def imwrite(*a, **k):
+    raise NotImplementedError
