@@ -3,6 +3,10 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (restated; TF absent)
+    python bench.py --config c1|c2|c3|c5 ...                 # the other BASELINE.json configurations (c4 = default = headline):
+        c1 dJPEG round trip q=50 (1280 x 128x128x3 roofline run + the 256x256 image of test_jpeg.py), c2 UNet pretrain B=32,
+        c3 TwitterDCN-32C pretrain B=64 (1 -> 8 GPUs, batch-global entropy via a 32-double histogram all-reduce),
+        c5 UNet + TwitterDCN + FAN end to end, trainable {fan, nip, dcn} (--batch, or --sweep for 64 .. 1024)
 
 Prints ONE JSON line (rank 0). `value` = raw 128x128 patches / s with inputs resident in HBM; `e2e` = the same through
 helpers.dataset.DeviceFeed + ManipulationClassification.training_step_device with pinned-host inputs (H2D of every
@@ -28,6 +32,7 @@ RAW = 128
 LAMBDA_NIP = 0.1
 LR = 1e-4
 METRIC = 'patches_per_sec_unet_djpeg50_fan_train_step'
+LAMBDA_DCN = 0.1          # config/tests/framework.json:55
 
 
 def peaks():
@@ -148,6 +153,17 @@ def make_inputs(b, seed):
     return x, y
 
 
+def param_checksum(stores):
+    """Sum and L2 norm (float64) of every trained parameter after the timed steps: equal step counts at N = 1 / 2 / 4 / 8 must land on
+    (almost) the same numbers if the data-parallel step equals the single-GPU step (differences: summation order + rounding ties)."""
+    tot, sq = 0.0, 0.0
+    for s in stores:
+        f = s.flat.double()
+        tot += float(f.sum().item())
+        sq += float((f * f).sum().item())
+    return {'sum': tot, 'l2': sq ** 0.5}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from neural_imaging_b200 import _lib
@@ -158,7 +174,15 @@ def run_ours(args, rank, world, local_rank):
     gb = args.batch
     assert gb % world == 0
     bl = gb // world
-    flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=RAW, seed=1234)
+    c5 = args.config == 'c5'
+    lam_dcn = LAMBDA_DCN if c5 else 0.0
+    if c5:      # TwitterDCN-32C constructed directly instead of codec.restore: no pre-trained model files exist offline
+        flow = ManipulationClassification('UNet', trainable={'nip', 'dcn'}, raw_patch_size=RAW, seed=1234,
+                                          distribution={'downsampling': 'pool:2', 'compression': 'dcn', 'compression_params': {'patch_size': RAW}})
+        if world > 1:
+            flow.codec.set_data_parallel(world)
+    else:
+        flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=RAW, seed=1234)
     sync = GradSync() if world > 1 else None
     if not args.no_graph:
         flow.enable_cuda_graph()       # static step (augment=False, fixed quality): two captured graphs instead of ~220 launches
@@ -170,7 +194,7 @@ def run_ours(args, rank, world, local_rank):
     xd, yd = xp.to(dev), yp.to(dev)
 
     def step_resident():
-        return flow.training_step_device(xd, yd, LAMBDA_NIP, 0, False, LR, grad_sync=sync)
+        return flow.training_step_device(xd, yd, LAMBDA_NIP, lam_dcn, False, LR, grad_sync=sync)
 
     def barrier():
         if world > 1:
@@ -219,8 +243,7 @@ def run_ours(args, rank, world, local_rank):
         def step():
             xe, ye = feed.next()
             feed.submit(hx, hy)                   # next step's inputs: same pinned buffers, a full H2D copy every step
-            loss, _ = flow.training_step_device(xe, ye, LAMBDA_NIP, 0, False, LR, grad_sync=sync)
-            feed.release()
+            loss, _ = flow.training_step_device(xe, ye, LAMBDA_NIP, lam_dcn, False, LR, grad_sync=sync)
             return float(loss.numpy())            # device -> host read of the step's loss (synchronises)
         return step, feed
     step_e2e, feed32 = make_e2e(xp, yp)
@@ -237,6 +260,8 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e_int = timed(step_e2e_int, args.steps)
     if flow._optimizer.nonfinite():
         raise RuntimeError('non-finite gradients during the benchmark')
+    checksum = param_checksum(flow._stores)
+    checksum['optimizer_steps'] = int(flow._optimizer.iterations)
 
     # ---- per-kernel roofline: same steps again with every C-ABI call bracketed by CUDA events (own pass so that the
     # event records do not perturb `value`)
@@ -300,10 +325,16 @@ def run_ours(args, rank, world, local_rank):
                           'bytes_per_launch_basis': '24 B/pixel (read x + write y); the two launches of the step (256 x 256x256 at q=80, 1280 x 128x128 at q=50) averaged; '
                                                     'timed inside the step (inputs partly L2-resident); tools/profile_djpeg.py times it alone with L2 flushed',
                           'peak_source': pk['source']}
+    lat = next((k for k in kernels if k['entry'] == 'ni_latent_softcodebook_fwd'), None)
+    metric = METRIC if not c5 else 'patches_per_sec_unet_twitterdcn_fan_train_step'
+    workload = ('BASELINE config 4: UNet(128x128x4 raw) -> [native,sharpen,resample,gaussian,jpeg80] -> avgpool2 -> dJPEG(50,soft) -> FAN(5 classes); '
+                'fwd+bwd+Adam, trainable {fan,nip}, lambda_nip=0.1') if not c5 else \
+               ('BASELINE config 5: UNet(128x128x4 raw) -> [native,sharpen,resample,gaussian,jpeg80] -> avgpool2 -> TwitterDCN-32C (soft-codebook, 5 bpf, '
+                'float64 latent path) -> FAN(5 classes); fwd+bwd+Adam, trainable {fan,nip,dcn}, lambda_nip=0.1, lambda_dcn=0.1')
     out = {
-        'metric': METRIC, 'value': gb / (ms * 1e-3), 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'metric': metric, 'value': gb / (ms * 1e-3), 'unit': 'patches/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 4: UNet(128x128x4 raw) -> [native,sharpen,resample,gaussian,jpeg80] -> avgpool2 -> dJPEG(50,soft) -> FAN(5 classes); fwd+bwd+Adam, trainable {fan,nip}, lambda_nip=0.1',
+        'config': {'workload': workload, 'name': args.config,
                    'global_batch': gb, 'per_gpu_batch': bl, 'codec_fan_images_per_step': 5 * gb, 'parallelism': 'dp%d' % world,
                    'l2': 'working set (multi-GB activations per step) >> 126 MB L2; no explicit flush needed'},
         'e2e': {'value': gb / (ms_e2e * 1e-3), 'unit': 'patches/s', 'ms_per_step': ms_e2e,
@@ -314,11 +345,289 @@ def run_ours(args, rank, world, local_rank):
                              'api': 'as e2e, host batches as stored (uint16 RAW / uint8 RGB), converted on the device (ni_feed_convert)'},
         'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'cuda_graph': not args.no_graph,
         'host_enqueue_ms_per_step': host_ms.get('step_resident'), 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:12],
-        'images_per_sec_codec_fan': 5 * gb / (ms * 1e-3), 'loss': float(loss.numpy()),
+        'images_per_sec_codec_fan': 5 * gb / (ms * 1e-3), 'loss': float(loss.numpy()), 'param_checksum': checksum,
     }
+    if lat is not None:
+        out['roofline_latent'] = {'kernel': 'latent_softcodebook_fwd_kernel (scale, 32-entry soft code book in float64, hard value, soft histogram)',
+                                  'bound': 'hbm', 'calls_per_step': lat['calls_per_step'], 'ms_per_step': lat['ms_per_step'],
+                                  'note': 'bytes: 4 B read + 4 B written per latent value (M x 16 x 16 x 32 values); the float64 kernel weights of '
+                                          'the reference (M x 8192 x 32 x 8 B, twice) never exist in memory'}
+    if args.sweep:
+        sweep = []
+        for b in (64, 128, 256, 512, 1024):
+            if b % world:
+                continue
+            torch.cuda.synchronize()
+            flow.release_workspaces()          # buffers are kept per shape (graph safety): free the previous batch size first
+            xs, ys = make_inputs(b // world, 4321 + rank)
+            xs, ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+            fn = lambda: flow.training_step_device(xs, ys, LAMBDA_NIP, lam_dcn, False, LR, grad_sync=sync)
+            try:
+                for _ in range(3):
+                    fn()
+                m = timed(fn, max(3, args.steps // 2))
+                sweep.append({'global_batch': b, 'ms_per_step': m, 'value': b / (m * 1e-3),
+                              'peak_hbm_gb': torch.cuda.max_memory_allocated() / 1e9})
+            except torch.OutOfMemoryError:
+                sweep.append({'global_batch': b, 'ms_per_step': None, 'value': None, 'note': 'does not fit 180 GB on %d GPU(s)' % world})
+            torch.cuda.reset_peak_memory_stats()
+            del xs, ys
+        out['sweep'] = sweep
     if world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(bounded_batch=args.cpu_batch, steps=args.cpu_steps)
+        out['cpu_baseline'] = cpu_baseline(args, bounded_batch=args.cpu_batch or (gb if args.config == 'c4' else min(gb, 64)), steps=args.cpu_steps)
     print(json.dumps(out), flush=True)
+
+
+# ================================================================================================ configs 1 - 3 (stand-alone paths)
+def _harness(world, dev):
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+    return timed
+
+
+def _profiled(step, steps):
+    """Same steps with every C-ABI call bracketed by CUDA events -> (per-entry aggregate, wall ms of the pass)."""
+    from neural_imaging_b200 import _lib
+    prof = EventProfiler()
+    _lib.PROFILER = prof
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    _lib.PROFILER = None
+    return prof.summary(), t0.elapsed_time(t1)
+
+
+def _conv_roofline(agg, steps, prof_ms, pk):
+    conv = {k: r for k, r in agg.items() if k.startswith('ni_conv2d_')}
+    ms = sum(r['ms'] for r in conv.values()) / steps
+    flop = sum(r['work'] for r in conv.values()) / steps
+    n = sum(r['calls'] for r in conv.values()) / steps
+    tf = flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    return {'kernel': 'conv2d tcgen05 3xTF32 implicit GEMM + direct FP32 stencils (all %d conv launches of the step)' % int(n), 'bound': 'tensor',
+            'achieved': tf, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': tf / pk['bf16_tflops_sustained'], 'traffic': None,
+            'flop_per_launch_avg': flop / max(n, 1), 'ms_per_launch_avg': ms / max(n, 1), 'share_of_step': ms / max(prof_ms / steps, 1e-9),
+            'peak_source': pk['source'], 'note': 'FP32 results (1e-5 parity) => 3xTF32: 1/6 of the bf16 peak is the ceiling of an ideal kernel'}
+
+
+def _kernel_list(agg, steps, prof_ms, pk):
+    out = []
+    for name, r in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:10]:
+        e = {'entry': name, 'calls_per_step': r['calls'] / steps, 'ms_per_step': r['ms'] / steps, 'share': r['ms'] / max(prof_ms, 1e-9)}
+        if r['kind'] == 'flop' and r['ms'] > 0:
+            e['tflops'] = r['work'] / (r['ms'] * 1e-3) / 1e12
+        if r['kind'] == 'byte' and r['ms'] > 0:
+            e['gbs'] = r['work'] / (r['ms'] * 1e-3) / 1e9
+            e['frac_of_hbm_peak'] = e['gbs'] / pk['hbm_gbs']
+        out.append(e)
+    return out
+
+
+def _emit(args, world, rank, ms, ms_e2e, units, h2d, d2h, launches, clk, extra):
+    if rank != 0:
+        return
+    out = {'metric': METRICS[args.config], 'value': units / (ms * 1e-3), 'unit': UNITS[args.config], 'n_gpus': world, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+           'data': 'synthetic',
+           'e2e': {'value': units / (ms_e2e * 1e-3), 'unit': UNITS[args.config], 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': int(h2d) * world,
+                   'd2h_bytes_per_step': int(d2h) * world},
+           'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'clocks': clk}
+    out.update(extra)
+    if world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(args, bounded_batch=args.cpu_batch or min(args.batch, 256), steps=args.cpu_steps)
+    print(json.dumps(out), flush=True)
+
+
+def run_c1(args, rank, world, local_rank):
+    """config 1: differentiable JPEG round trip, q = 50. The roofline run is the batched tensor of the codec stage of config 4
+    (global batch images of 128x128x3, forward = JPEG.process); the 256x256 single image of test_jpeg.py:105-110 is timed beside it."""
+    from neural_imaging_b200 import _lib, ops
+    from neural_imaging_b200.compression.jpeg_helpers import jpeg_qtable
+    from neural_imaging_b200.models import jpeg
+    dev = torch.device('cuda', local_rank)
+    L = _lib.lib()
+    timed = _harness(world, dev)
+    n = args.batch // world
+    rs = np.random.RandomState(1234 + rank)
+    xh = torch.from_numpy(rs.uniform(size=(n, RAW, RAW, 3)).astype(np.float32)).pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    xd, dyd = xh.to(dev), torch.from_numpy(rs.normal(size=tuple(xh.shape)).astype(np.float32)).to(dev)
+    yd, dxd = torch.empty_like(xd), torch.empty_like(xd)
+    codec = jpeg.JPEG(50, 'soft')
+    ql, qc = jpeg_qtable(50, 0), jpeg_qtable(50, 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def fwd():
+        codec._model.forward_into(xd, yd)
+
+    def fwd_bwd():
+        ops.djpeg_fwd(xd, ql, qc, 'soft', out=yd)
+        ops.djpeg_bwd(xd, dyd, ql, qc, 'soft', out=dxd)
+
+    def e2e():
+        xd.copy_(xh, non_blocking=True)
+        codec._model.forward_into(xd, yd)
+        yh.copy_(yd, non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        fwd(); fwd_bwd()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    L.ni_reset_launch_count()
+    ms = timed(fwd, args.steps)
+    launches = int(L.ni_launch_count())
+    ms_fb = timed(fwd_bwd, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    e2e(); ms_e2e = timed(e2e, args.steps)
+    # single launches with L2 flushed in between (input + output = 503 MB per launch is already 4x the L2; the flush removes the tail)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record(); fwd(); b.record()
+    torch.cuda.synchronize()
+    ms_single = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evb:
+        flush.fill_(1)
+        a.record(); ops.djpeg_bwd(xd, dyd, ql, qc, 'soft', out=dxd); b.record()
+    torch.cuda.synchronize()
+    ms_bwd = float(np.median([a.elapsed_time(b) for a, b in evb]))
+    one = torch.from_numpy(np.random.RandomState(7).uniform(size=(1, 256, 256, 3)).astype(np.float32)).to(dev)
+    one_y = torch.empty_like(one)
+    for _ in range(3):
+        codec._model.forward_into(one, one_y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(100):
+        codec._model.forward_into(one, one_y)
+    e1.record(); torch.cuda.synchronize()
+    pk = peaks()
+    px = n * RAW * RAW
+    gbs = 24.0 * px / (ms_single * 1e-3) / 1e9
+    gbs_b = 36.0 * px / (ms_bwd * 1e-3) / 1e9
+    extra = {'config': {'workload': 'BASELINE config 1: dJPEG(50, soft) round trip (JPEG.process) of {} x 128x128x3 float32 images per step'.format(args.batch),
+                        'name': 'c1', 'global_batch': args.batch, 'parallelism': 'dp%d' % world, 'l2': 'input + output of a launch = 503 MB > 126 MB L2; single-launch timings flush L2'},
+             'roofline': {'kernel': 'djpeg_fwd kernel (fused colour + 8x8 DCT + quantisation + IDCT + colour)', 'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'],
+                          'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'], 'traffic': None, 'algorithmic_bytes_per_launch': 24.0 * px,
+                          'ms_per_launch': ms_single, 'peak_source': pk['source']},
+             'roofline_bwd': {'kernel': 'djpeg_bwd kernel (forward chain recomputed, nothing saved)', 'bound': 'hbm', 'achieved': gbs_b, 'peak': pk['hbm_gbs'],
+                              'unit': 'GB/s', 'frac': gbs_b / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': 36.0 * px, 'ms_per_launch': ms_bwd},
+             'fwd_bwd_ms_per_step': ms_fb, 'single_256x256_image_us': e0.elapsed_time(e1) * 10.0}
+    _emit(args, world, rank, ms, ms_e2e, args.batch, xh.numel() * 4, yh.numel() * 4, launches, clk, extra)
+
+
+def run_c2(args, rank, world, local_rank):
+    """config 2: UNet pretraining step (train_nip.py: L2 loss, Adam), global batch 32 raw patches of 128x128x4."""
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.models import pipelines
+    from neural_imaging_b200.parallel import GradSync, broadcast_parameters
+    dev = torch.device('cuda', local_rank)
+    L = _lib.lib()
+    timed = _harness(world, dev)
+    bl = args.batch // world
+    model = pipelines.UNet(patch_size=RAW, seed=1234)
+    sync = GradSync() if world > 1 else None
+    if world > 1:
+        broadcast_parameters([model._store])
+    xh, yh = make_inputs(args.batch, 1234)
+    xp = torch.from_numpy(xh[rank * bl:(rank + 1) * bl]).pin_memory()
+    yp = torch.from_numpy(yh[rank * bl:(rank + 1) * bl]).pin_memory()
+    xd, yd = xp.to(dev), yp.to(dev)
+
+    def step():
+        return model.training_step(xd, yd, LR, grad_sync=sync)
+
+    def e2e():
+        return float(model.training_step(xp.to(dev, non_blocking=True), yp.to(dev, non_blocking=True), LR, grad_sync=sync).numpy())
+    for _ in range(max(args.warmup, 3)):
+        step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    L.ni_reset_launch_count()
+    ms = timed(step, args.steps)
+    launches = int(L.ni_launch_count())
+    clk = clocks.stop() if rank == 0 else None
+    e2e(); ms_e2e = timed(e2e, args.steps)
+    agg, prof_ms = _profiled(step, args.steps)
+    pk = peaks()
+    extra = {'config': {'workload': 'BASELINE config 2: UNet (7.76 M parameters) pretraining step, L2 loss, Keras Adam, 128x128x4 raw -> 256x256x3', 'name': 'c2',
+                        'global_batch': args.batch, 'per_gpu_batch': bl, 'parallelism': 'dp%d' % world, 'l2': 'activations of a step (GBs) >> 126 MB L2'},
+             'roofline': _conv_roofline(agg, args.steps, prof_ms, pk), 'kernels': _kernel_list(agg, args.steps, prof_ms, pk),
+             'param_checksum': param_checksum([model._store])}
+    _emit(args, world, rank, ms, ms_e2e, args.batch, xp.numel() * 4 + yp.numel() * 4, 4, launches, clk, extra)
+
+
+def run_c3(args, rank, world, local_rank):
+    """config 3: TwitterDCN-32C pretraining step (train_dcn.py: soft-codebook, 5 bpf, entropy weight 250), global batch 64 images."""
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.models import compression
+    from neural_imaging_b200.parallel import GradSync, broadcast_parameters
+    dev = torch.device('cuda', local_rank)
+    L = _lib.lib()
+    timed = _harness(world, dev)
+    bl = args.batch // world
+    model = compression.TwitterDCN(patch_size=RAW, seed=1234)
+    sync = GradSync() if world > 1 else None
+    if world > 1:
+        model.set_data_parallel(world)
+        broadcast_parameters([model._store])
+    xh = np.random.RandomState(1234).uniform(size=(args.batch, RAW, RAW, 3)).astype(np.float32)
+    xp = torch.from_numpy(xh[rank * bl:(rank + 1) * bl]).pin_memory()
+    xd = xp.to(dev)
+
+    def step():
+        return model.training_step(xd, LR, grad_sync=sync)
+
+    def e2e():
+        return float(model.training_step(xp.to(dev, non_blocking=True), LR, grad_sync=sync)['loss'].numpy())
+    for _ in range(max(args.warmup, 3)):
+        step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    L.ni_reset_launch_count()
+    ms = timed(step, args.steps)
+    launches = int(L.ni_launch_count())
+    clk = clocks.stop() if rank == 0 else None
+    e2e(); ms_e2e = timed(e2e, args.steps)
+    agg, prof_ms = _profiled(step, args.steps)
+    pk = peaks()
+    lat = {k: agg[k] for k in agg if k.startswith('ni_latent_') or k == 'ni_entropy_from_hist'}
+    nz = bl * (RAW // 8) * (RAW // 8) * 32
+    lat_ms = {k: r['ms'] / max(r['calls'], 1) for k, r in lat.items()}
+    fwd_ms = lat_ms.get('ni_latent_softcodebook_fwd')
+    extra = {'config': {'workload': 'BASELINE config 3: TwitterDCN-32C (2.53 M parameters) training step: l2_loss (sum) + 250 x entropy of the batch-global soft '
+                                    'histogram (float64 latent path), Keras Adam, 128x128x3 images', 'name': 'c3', 'global_batch': args.batch, 'per_gpu_batch': bl,
+                        'parallelism': 'dp%d (32-double histogram all-reduce before the entropy + gradient all-reduce)' % world,
+                        'l2': 'activations of a step (GBs) >> 126 MB L2'},
+             'roofline': _conv_roofline(agg, args.steps, prof_ms, pk),
+             'roofline_latent': {'kernel': 'latent_softcodebook_fwd_kernel', 'bound': 'hbm', 'unit': 'GB/s', 'ms_per_launch': fwd_ms,
+                                 'algorithmic_bytes_per_launch': 8.0 * nz, 'achieved': (8.0 * nz / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
+                                 'peak': pk['hbm_gbs'], 'frac': (8.0 * nz / (fwd_ms * 1e-3) / 1e9 / pk['hbm_gbs']) if fwd_ms else None,
+                                 'note': '4 B read + 4 B written per latent value; {} values per launch: a few MB, i.e. latency- not bandwidth-sized at this batch '
+                                         '(32 float64 kernel evaluations per value are the work)'.format(nz), 'all_latent_entries_ms': lat_ms},
+             'kernels': _kernel_list(agg, args.steps, prof_ms, pk), 'param_checksum': param_checksum([model._store])}
+    _emit(args, world, rank, ms, ms_e2e, args.batch, xp.numel() * 4, 4, launches, clk, extra)
 
 
 def _host_state(cls, kwargs):
@@ -332,55 +641,98 @@ def _host_state(cls, kwargs):
     return {p.name: p.init for p in m._store.params}
 
 
-def cpu_step_factory(b):
-    """The restated reference (oracle) joint training step on host cores; b raw patches of config 4."""
-    from neural_imaging_b200.models import forensics, pipelines
+def cpu_step_factory(b, config='c4'):
+    """The restated reference (oracle, pinned to the executed reference by tests/test_tf_graph_golden.py) on host cores: one step of
+    `config` over b units (raw patches; images for c1 / c3). Returns (step callable, description)."""
+    from neural_imaging_b200.models import compression, forensics, pipelines
     from oracle import ref_models as M
+    from oracle import ref_ops as R
+    if config == 'c1':
+        x = torch.tensor(np.random.RandomState(1234).uniform(size=(b, RAW, RAW, 3)).astype(np.float32))
+        ql, qc = R.jpeg_qtable(50, 0), R.jpeg_qtable(50, 1)
+        return (lambda: R.djpeg(x, ql, qc, 'soft')[0]), 'dJPEG(50, soft) forward of {} 128x128x3 images'.format(b)
+    if config == 'c2':
+        Pn = M.to_params(_host_state(pipelines.UNet, dict(patch_size=RAW, seed=1234)))
+        x, y = make_inputs(b, 1234)
+        xt, yt = torch.tensor(x), torch.tensor(y)
+        opt = {'t': 0, 'm': {}, 'v': {}}
+        names = list(Pn.keys())
+
+        def step():
+            loss = R.mse(M.unet_forward(Pn, xt), yt)
+            g = torch.autograd.grad(loss, [Pn[k] for k in names])
+            opt['t'] += 1
+            with torch.no_grad():
+                ms = [opt['m'].setdefault(k, torch.zeros_like(Pn[k])) for k in names]
+                vs = [opt['v'].setdefault(k, torch.zeros_like(Pn[k])) for k in names]
+                R.adam_keras_step([Pn[k] for k in names], list(g), ms, vs, opt['t'], LR)
+            return loss
+        return step, 'UNet L2 training step (tape + Keras Adam) on {} raw patches'.format(b)
+    if config == 'c3':
+        Pd = M.to_params(_host_state(compression.TwitterDCN, dict(patch_size=RAW, seed=1234)))
+        xt = torch.tensor(np.random.RandomState(1234).uniform(size=(b, RAW, RAW, 3)).astype(np.float32))
+        opt = {'t': 0, 'm': {}, 'v': {}}
+        return (lambda: M.dcn_training_step(Pd, opt, xt, LR)), 'TwitterDCN-32C training step on {} 128x128x3 images'.format(b)
     state_nip = _host_state(pipelines.UNet, dict(patch_size=RAW, seed=1234))
     state_fan = _host_state(forensics.FAN, dict(n_classes=5, patch_size=RAW, seed=1234))
     Pn, Pf = M.to_params(state_nip), M.to_params(state_fan)
     x, y = make_inputs(b, 1234)
     xt, yt = torch.tensor(x), torch.tensor(y)
     opt = {'t': 0, 'm': {}, 'v': {}}
-    return lambda: M.training_step(Pn, Pf, opt, xt, yt, lambda_nip=LAMBDA_NIP, lr=LR, train_nip=True)
+    if config == 'c5':
+        Pd = M.to_params(_host_state(compression.TwitterDCN, dict(patch_size=RAW, seed=1234)))
+        return (lambda: M.training_step(Pn, Pf, opt, xt, yt, lambda_nip=LAMBDA_NIP, lr=LR, train_nip=True, P_dcn=Pd, lambda_dcn=LAMBDA_DCN,
+                                        train_dcn=True)), 'joint UNet + TwitterDCN + FAN step on {} raw patches ({} codec/FAN images)'.format(b, 5 * b)
+    return (lambda: M.training_step(Pn, Pf, opt, xt, yt, lambda_nip=LAMBDA_NIP, lr=LR, train_nip=True)), \
+        'joint UNet + dJPEG(50) + FAN step on {} raw patches ({} codec/FAN images)'.format(b, 5 * b)
 
 
-def cpu_baseline(bounded_batch=32, steps=4):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = cpu_step_factory(bounded_batch)
-    step()                                   # warm-up
+def time_cpu(step, max_steps, budget_s):
+    """Warm-up step, then as many timed steps as fit the budget (at least 2 when max_steps allows)."""
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return {'value': bounded_batch / dt, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
-            'sample': '{} raw patches/step ({} codec/FAN images), {} timed steps of the restated reference (PyTorch-CPU float32 op-for-op oracle; TensorFlow unavailable)'.format(
-                bounded_batch, 5 * bounded_batch, steps), 's_per_step': dt}
-
-
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    b = args.cpu_batch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = cpu_step_factory(b)
-    for _ in range(max(1, min(args.warmup, 1))):
-        step()
-    k = max(1, min(args.steps, args.cpu_steps))
+    step()
+    first = time.perf_counter() - t0
+    k = int(max(min(max_steps, 2), min(max_steps, budget_s // max(first, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(k):
         step()
-    dt = (time.perf_counter() - t0) / k
+    return (time.perf_counter() - t0) / k, k
+
+
+def cpu_baseline(args, bounded_batch, steps=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, what = cpu_step_factory(bounded_batch, args.config)
+    dt, k = time_cpu(step, steps, 30.0)
+    return {'value': bounded_batch / dt, 'unit': UNITS[args.config], 'cores': cores, 'kind': 'port',
+            'sample': '{}; {} timed steps of the restated reference (PyTorch-CPU float32 op-for-op oracle, {} threads; TensorFlow unavailable)'.format(what, k, cores),
+            's_per_step': dt}
+
+
+UNITS = {'c1': 'images/s', 'c2': 'patches/s', 'c3': 'images/s', 'c4': 'patches/s', 'c5': 'patches/s'}
+METRICS = {'c1': 'images_per_sec_djpeg50_roundtrip_128x128', 'c2': 'patches_per_sec_unet_pretrain_step', 'c3': 'images_per_sec_twitterdcn32c_train_step',
+           'c4': METRIC, 'c5': 'patches_per_sec_unet_twitterdcn_fan_train_step'}
+DEFAULT_BATCH = {'c1': 1280, 'c2': 32, 'c3': 64, 'c4': GLOBAL_BATCH, 'c5': GLOBAL_BATCH}
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the restated reference on ALL host cores, on the SAME configuration (global batch) as our arm; the number of
+    timed steps is what fits ~150 s (at least 2), so that the run ends within a few minutes whatever --steps asks for."""
+    if rank != 0:
+        return
+    b = args.cpu_batch or args.batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, what = cpu_step_factory(b, args.config)
+    dt, k = time_cpu(step, max(2, args.steps), 150.0)
     v = b / dt
-    sample = '{} raw patches/step ({} codec/FAN images) of config 4, {} timed steps; restated reference (oracle/, PyTorch-CPU float32, {} threads) because TensorFlow 2.1 is not installable here'.format(b, 5 * b, k, cores)
+    sample = '{}; {} timed steps after 1 warm-up; restated reference (oracle/, PyTorch-CPU float32, {} threads) because TensorFlow 2.1 is not installable here'.format(what, k, cores)
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'patches/s', 'n_gpus': world, 'steps': k, 'warmup': 1, 'ms_per_step': dt * 1e3,
+        'impl': 'reference', 'metric': METRICS[args.config], 'value': v, 'unit': UNITS[args.config], 'n_gpus': world, 'steps': k, 'warmup': 1, 'ms_per_step': dt * 1e3,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 4 (bounded sample): UNet -> manipulations -> avgpool2 -> dJPEG(50) -> FAN train step', 'global_batch': b, 'parallelism': 'cpu'},
-        'cpu_baseline': {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': v, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': {'workload': 'BASELINE config {} on the host cores: {}'.format(args.config[1], what), 'name': args.config, 'global_batch': b, 'parallelism': 'cpu'},
+        'cpu_baseline': {'value': v, 'unit': UNITS[args.config], 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': UNITS[args.config], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }), flush=True)
 
 
@@ -390,13 +742,17 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=GLOBAL_BATCH, help='global raw batch (BASELINE config 4: 256)')
-    ap.add_argument('--cpu-batch', type=int, default=32, help='raw patches per step of the CPU legs (bounded sample of config 4: ~10 s of host work)')
-    ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--config', default='c4', choices=['c1', 'c2', 'c3', 'c4', 'c5'], help='BASELINE.json configuration (c4 = headline)')
+    ap.add_argument('--batch', type=int, default=None, help='global batch (default: the configuration\'s own: c1 1280, c2 32, c3 64, c4 / c5 256)')
+    ap.add_argument('--sweep', action='store_true', help='c5: also time global batches 64 .. 1024 (reported under "sweep")')
+    ap.add_argument('--cpu-batch', type=int, default=None, help='units per step of the CPU legs (default: the same global batch as the GPU arm)')
+    ap.add_argument('--cpu-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of replaying the captured CUDA graphs')
     ap.add_argument('--layer-report', default=None, help='write a per-layer (per conv shape) timing table to this JSON file')
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.config]
     rank, world, local_rank = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
         return run_reference(args, rank, world)
@@ -406,7 +762,7 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        {'c1': run_c1, 'c2': run_c2, 'c3': run_c3, 'c4': run_ours, 'c5': run_ours}[args.config](args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -129,6 +129,15 @@ int ni_manip_gamma_bwd(const float* x, const float* dy, float* dx, int n, int h,
 /* manipulation_median (tf_helpers.py:91-110), k odd */
 int ni_manip_median_fwd(const float* x, float* y, int n, int h, int w, int k, ni_stream_t stream);
 int ni_manip_median_bwd(const float* x, const float* dy, float* dx_accum, int n, int h, int w, int k, ni_stream_t stream);
+/* run_manipulations + run_downsampling 'pool:2' fused (workflows/manipulation_classification.py:199-208, :231-245): the pooled
+ * class-major stack c = (n_classes * b, h/2, w/2, 3) is written straight from y = (b, h, w, 3) for the slots listed in
+ * slots[4] = {native, sharpen, resample at factor 50, gaussian 3x3 / 5x5} (class index, -1 = absent / filled by the caller through the
+ * stand-alone kernels + ni_avgpool_fwd); the full-resolution stack is never materialised. The backward accumulates
+ * d(loss)/dy from the pooled gradient slots (the sharpen slot carries none: helpers/tf_helpers.py:177,182 are not differentiable in TF 2.1). */
+int ni_manip_stack_pool2_fwd(const float* y, float* c, unsigned char* gauss_clip_mask_or_null, int b, int h, int w, int n_classes,
+                             const int* slots, const float* sharp9, const float* gauss, int gk, ni_stream_t stream);
+int ni_manip_stack_pool2_bwd(const unsigned char* gauss_clip_mask, const float* dc, float* dy, int b, int h, int w, int n_classes,
+                             const int* slots, const float* gauss, int gk, int accumulate, ni_stream_t stream);
 /* tf.nn.avg_pool k x k stride k SAME (workflows/manipulation_classification.py:235) */
 int ni_avgpool_fwd(const float* x, float* y, int n, int h, int w, int k, ni_stream_t stream);
 int ni_avgpool_bwd(const float* dy, float* dx, int n, int h, int w, int k, ni_stream_t stream);
@@ -215,6 +224,9 @@ int ni_gap_bwd(const float* dy, float* dx, int n, int hw, int c, ni_stream_t str
 /* softmax + SparseCategoricalCrossentropy on probabilities, Keras eager semantics (models/forensics.py:90,94) */
 int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* loss_sum, float* dlogits, int m, int c,
                   float gscale, ni_stream_t stream);
+/* validate_fan's decisions and confusion matrix (training/validation.py:163-203; workflows/manipulation_classification.py:178-180):
+   pred[i] = argmax probs[i, :], conf[labels[i] * c + pred[i]] += 1 (int32, caller zeroes); pred or conf may be null */
+int ni_confusion_accumulate(const float* probs, const int* labels, int* conf, int* pred, int m, int c, ni_stream_t stream);
 /* tf_helpers.mse / mae (helpers/tf_helpers.py:31-36): kind 0 = L2, 1 = L1 */
 int ni_image_loss(const float* a, const float* b, float* acc, long long n, int kind, ni_stream_t stream);
 int ni_image_loss_grad(const float* a, const float* b, float* da, long long n, int kind, float scale, int accumulate,

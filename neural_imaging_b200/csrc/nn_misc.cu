@@ -651,6 +651,30 @@ extern "C" int ni_softmax_ce(const float* logits, const int* labels, float* prob
     return NI_OK;
 }
 
+// Decisions + confusion matrix of a validation pass on the device (reference training/validation.py:163-203 builds it on the host with
+// an n_classes^2 Python loop per batch of 10): pred[i] = argmax_k probs[i, k] (first maximum, like numpy.argmax), conf[label, pred] += 1.
+__global__ void confusion_kernel(const float* __restrict__ probs, const int* __restrict__ labels, int* __restrict__ conf,
+                                 int* __restrict__ pred, int m, int c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float* p = probs + (size_t)i * c;
+    int best = 0;
+    float bv = p[0];
+    for (int k = 1; k < c; ++k) {
+        float v = p[k];
+        if (v > bv) { bv = v; best = k; }
+    }
+    if (pred) pred[i] = best;
+    if (conf && labels) atomicAdd(conf + labels[i] * c + best, 1);
+}
+extern "C" int ni_confusion_accumulate(const float* probs, const int* labels, int* conf, int* pred, int m, int c, cudaStream_t st) {
+    NI_REQUIRE(probs && m >= 0 && c > 0 && (pred || (conf && labels)), "ni_confusion_accumulate: invalid arguments");
+    if (m == 0) return NI_OK;
+    confusion_kernel<<<ni_cdiv(m, kT), kT, 0, st>>>(probs, labels, conf, pred, m, c);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
 // *acc += sum_i term_i (caller zeroes and divides by n). kind: 0 = L2 (mse of 255-scaled images), 1 = L1.
 extern "C" int ni_image_loss(const float* a, const float* b, float* acc, long long n, int kind, cudaStream_t st) {
     NI_REQUIRE(a && b && acc && n >= 0 && (kind == 0 || kind == 1), "ni_image_loss: invalid arguments");

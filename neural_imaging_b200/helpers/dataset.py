@@ -109,7 +109,7 @@ class Dataset(object):
     = 'xy' | 'x' | 'y'); `data['validation']` holds pre-cut patches of the same dtypes.
     """
 
-    def __init__(self, training, validation=None, load='xy', fast_stats=True):
+    def __init__(self, training, validation=None, load='xy', fast_stats=True, stats_budget_bytes=2 << 30):
         if load not in ('xy', 'x', 'y'):
             raise ValueError('Invalid X/Y data requested!')
         for k in load:
@@ -124,6 +124,7 @@ class Dataset(object):
             self.H, self.W = (2 * d for d in self.data['training']['x'].shape[1:3])
         self._fast_stats = fast_stats
         self._stats = {}
+        self._stats_cap = max(4, int(stats_budget_bytes // (16 * (self.H + 1) * (self.W + 1))))
         self._resident = {}
         self._coords = None
 
@@ -156,9 +157,12 @@ class Dataset(object):
                 img = tr['y'][bid]
                 st = None
                 if self._fast_stats and discard:
-                    st = self._stats.get(bid)
+                    st = self._stats.pop(bid, None)
                     if st is None:
-                        st = self._stats[bid] = PatchStats(img)
+                        st = PatchStats(img)
+                    self._stats[bid] = st                 # most recently used last (dict order); bounded: two int64 integral images
+                    while len(self._stats) > self._stats_cap:      # per image are 16 B/pixel — 8x the uint8 image itself
+                        self._stats.pop(next(iter(self._stats)))
                 xx, yy = sample_patch(img, rgb_patch_size, discard, max_attempts, stats=st)
             else:                     # RAW only: the reference indexes data['training']['y'] and fails; positions from the RAW size
                 xx, yy = sample_patch(np.empty((self.H, self.W, 0), dtype=np.uint8), rgb_patch_size, None, max_attempts)
@@ -226,6 +230,21 @@ class Dataset(object):
     def is_raw_and_rgb(self):
         return self._loaded_data == 'xy'
 
+    # the counters the training / validation loops read (reference helpers/dataset.py:160-185)
+    @property
+    def count_training(self):
+        return int(self.data['training'][self._loaded_data[0]].shape[0])
+
+    @property
+    def count_validation(self):
+        va = self.data['validation']
+        return int(va[self._loaded_data[0]].shape[0]) if va else 0
+
+    @property
+    def rgb_patch_size(self):
+        va = self.data['validation']
+        return int(va['y'].shape[1]) if 'y' in self._loaded_data else 2 * int(va['x'].shape[1])
+
     def summary(self):
         tr = self.data['training']
         return 'Dataset[{}]: {} training images {}x{}'.format(self._loaded_data, len(self), self.H, self.W) + \
@@ -246,7 +265,8 @@ class DeviceFeed(object):
             flow.training_step_device(x, y, ...)
 
     Integer batches are converted by `ni_feed_convert` on the copy stream (float(v) / 65535 or / 255: identical to the reference's
-    host conversion). Slots are recycled: `next()` returns views that stay valid until the second `submit` after it.
+    host conversion). Slots are recycled: the views `next()` returns stay valid for everything enqueued on the compute stream before the
+    following `next()` (an event recorded there gates the copy stream's reuse of the slot); `release()` frees a slot earlier.
     """
 
     def __init__(self, depth=2):
@@ -256,6 +276,7 @@ class DeviceFeed(object):
         self._ready = []                  # FIFO of (slot index, event)
         self._free_at = [None] * depth    # event after which slot i may be overwritten (recorded on the compute stream)
         self._w = 0
+        self._last = None
         self.h2d_bytes = 0
 
     @staticmethod
@@ -298,6 +319,12 @@ class DeviceFeed(object):
             raise RuntimeError('DeviceFeed.next() without a submitted batch')
         i, ev, outs = self._ready.pop(0)
         cur = torch.cuda.current_stream()
+        if self._last is not None and self._last != i:
+            # everything that consumes the PREVIOUS batch has been enqueued on the compute stream by now: its slot may be overwritten
+            # after this point of the stream (callers need not call release(); async steps / graph replays cannot race the copy stream)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._free_at[self._last] = done
         cur.wait_event(ev)
         self._last = i
         return outs if len(outs) > 1 else outs[0]

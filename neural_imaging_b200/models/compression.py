@@ -126,8 +126,11 @@ class DCN(TFModel):
         y = wrap(y.clone())
         return (y, wrap(ent.clone().reshape(()))) if return_entropy else y
 
-    def training_step(self, batch_x, learning_rate=None):
-        """One optimisation step; returns {'loss': sqrt(2 loss), 'ssim', 'entropy'} (models/compression.py:123-139)."""
+    def training_step(self, batch_x, learning_rate=None, grad_sync=None):
+        """One optimisation step; returns {'loss': sqrt(2 loss), 'ssim', 'entropy'} (models/compression.py:123-139).
+        grad_sync (parallel.GradSync, after set_data_parallel(world)): the batch is sharded by rank; the soft histogram is all-reduced
+        before the entropy is taken (so H is the single-device, batch-global value) and the gradients are summed — tf.nn.l2_loss is a
+        SUM over the batch and dH/dz is already normalised by the global count, so no 1 / world_size factor applies."""
         L, s = _lib.lib(), stream()
         x = as_device(batch_x)
         if x.dim() == 3:
@@ -141,6 +144,8 @@ class DCN(TFModel):
         dy = self._ws.get('dy', y.shape)
         L.ni_image_loss_grad(ptr(y), ptr(x), ptr(dy), y.numel(), 0, y.numel() / (2.0 * 255.0 * 255.0), 0, s)     # dy = y - x
         self.backward(dy, float(self._h.entropy_weight), need_dx=False)
+        if grad_sync is not None:
+            grad_sync([self._store])
         if learning_rate is not None:
             self.optimizer.lr = float(learning_rate)
         self.optimizer.apply([self._store])

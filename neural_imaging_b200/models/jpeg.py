@@ -91,9 +91,9 @@ class JPEG(TFModel):
     def loss(target, compressed, sample_weight=None):
         """tf.keras.losses.MeanSquaredError()(a, b, sample_weight). The workflow passes the (NaN) entropy as the third
         positional argument, which Keras interprets as sample_weight => NaN; reproduced."""
-        a, b = as_device(target), as_device(compressed)
         if sample_weight is not None and is_number(sample_weight) and np.isnan(sample_weight):
             return float('nan')
+        a, b = as_device(target), as_device(compressed)
         v = ops.image_loss(a, b, 'L2') / (255.0 * 255.0)
         return wrap(v.reshape(())) if sample_weight is None else wrap(v.reshape(()) * float(sample_weight))
 

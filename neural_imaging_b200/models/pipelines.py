@@ -64,8 +64,10 @@ class NIPModel(TFModel):
         y = self._forward(self._prep(batch_x), save=False)
         return wrap(y.clone())
 
-    def training_step(self, batch_x, batch_y, learning_rate=None):
-        """One optimisation step on (raw, rgb target); returns the loss (reference models/pipelines.py:77-90)."""
+    def training_step(self, batch_x, batch_y, learning_rate=None, grad_sync=None):
+        """One optimisation step on (raw, rgb target); returns the loss (reference models/pipelines.py:77-90).
+        grad_sync (parallel.GradSync): batch-sharded data parallelism — gradients are all-reduced between backward and Adam; the
+        loss is a mean, so the 1 / world_size average rides in the Adam kernel's gradient scale."""
         x, t = self._prep(batch_x), self._prep(batch_y)
         y = self._forward(x, save=True)
         L = _lib.lib()
@@ -75,9 +77,11 @@ class NIPModel(TFModel):
         self.loss_forward(y, t, acc, 1.0)
         self.loss_backward(y, t, dy, 1.0)
         self._backward(dy)
+        if grad_sync is not None:
+            grad_sync([self._store])
         if learning_rate is not None:
             self.optimizer.lr = float(learning_rate)
-        self.optimizer.apply([self._store])
+        self.optimizer.apply([self._store], getattr(grad_sync, 'gscale', 1.0))
         return wrap((acc / float(y.numel())).reshape(()))
 
     def loss_forward(self, y, t, acc, grad_scale=1.0):

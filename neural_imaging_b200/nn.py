@@ -68,7 +68,7 @@ class ParamStore:
 
     def __init__(self):
         self.params = []
-        self.flat = self.gflat = self.frozen = None
+        self.flat = self.gflat = self.frozen = self.arena = None
 
     def add(self, name, shape, init, trainable=True):
         p = Param(name, shape, init, trainable)
@@ -100,6 +100,13 @@ class ParamStore:
     @property
     def trainable(self):
         return [p for p in self.params if p.trainable]
+
+    def rebind_gradients(self, gflat):
+        """Move the gradient buffer into `gflat` (a slice of a shared arena, same length): every parameter's .grad view follows."""
+        assert gflat.numel() == self.flat.numel() and gflat.dtype == self.flat.dtype
+        self.gflat = gflat
+        for p in self.trainable:
+            p.grad = gflat[p.offset:p.offset + p.size].view(p.shape if p.shape else ())
 
     def count(self):
         return int(sum(p.size for p in self.trainable))
@@ -222,6 +229,21 @@ class Conv2D:
             dd.pad_mode = PAD_ZERO
             L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dx), st)
         return dx
+
+
+def unify_gradients(stores):
+    """Lay the flat gradient buffers of several stores out back to back in ONE arena, so that the data-parallel exchange is a single
+    all-reduce over one bucket instead of one collective per model. Returns the arena. Call before the first step (nothing
+    may have captured the old gradient pointers yet)."""
+    total = sum(s.gflat.numel() for s in stores)
+    arena = torch.zeros((total,), dtype=torch.float32, device=stores[0].gflat.device)
+    off = 0
+    for s in stores:
+        n = s.gflat.numel()
+        s.rebind_gradients(arena[off:off + n])
+        s.arena = arena
+        off += n
+    return arena
 
 
 class AdamKeras:

@@ -205,6 +205,67 @@ class MedianOp(ManipOp):
         return dx
 
 
+class PooledStack:
+    """run_manipulations + run_downsampling('pool:2') without the full-resolution stack (ni_manip_stack_pool2_fwd / _bwd).
+
+    plan() decides per step which class slots the fused kernels cover — native, sharpen, resample at factor 50 (any strength that
+    `ResampleOp._small` maps to H/2), gaussian 3x3 / 5x5 — and which operators (jpeg, awgn, gamma, median, other factors) go through
+    their stand-alone kernels into one image-sized scratch buffer followed by a per-slot pooling."""
+
+    def __init__(self, ops_by_name):
+        self.ops = ops_by_name            # OrderedDict name -> ManipOp, class slot = position + 1
+        self._mask = None
+
+    @staticmethod
+    def applicable(downsampling, h, w):
+        return downsampling in ('pool', 'pool:2') and h % 2 == 0 and w % 2 == 0 and h >= 8 and w >= 8 and h == w
+
+    def plan(self, strengths, h):
+        slots = [0, -1, -1, -1]           # native, sharpen, resample, gaussian
+        sharp = gauss = None
+        gk = 0
+        rest = []
+        for i, (name, op) in enumerate(self.ops.items()):
+            st = strengths[name]
+            if isinstance(op, SharpenOp):
+                slots[1], sharp = i + 1, sharpen_filter(st)
+            elif isinstance(op, ResampleOp) and 2 * ResampleOp._small(h, st) == h:
+                slots[2] = i + 1
+            elif isinstance(op, GaussianOp) and op.kernel in (3, 5):
+                slots[3], gauss, gk = i + 1, kernels.gkern(op.kernel, st), op.kernel
+            else:
+                rest.append((i + 1, name, op))
+        return {'slots': np.asarray(slots, dtype=np.int32), 'sharp': sharp, 'gauss': gauss, 'gk': gk, 'rest': rest}
+
+    def forward(self, Y, c, plan, strengths, scratch, training=False, mask=None):
+        """c (n_classes * B, H/2, W/2, 3) <- pooled stack of Y (B, H, W, 3); scratch: (B, H, W, 3) buffer for the stand-alone operators;
+        mask: (B, H, W) uint8 buffer that receives the gaussian slot's clip mask (needed by backward)."""
+        b, h, w = _nhw3(Y)
+        L = _lib.lib()
+        _, ps = _f32(plan['sharp']) if plan['sharp'] is not None else (None, None)
+        _, pg = _f32(plan['gauss']) if plan['gauss'] is not None else (None, None)
+        self._mask = mask if (training and plan['slots'][3] >= 0) else None
+        if training and plan['slots'][3] >= 0 and mask is None:
+            self._mask = empty((b, h, w), torch.uint8)
+        L.ni_manip_stack_pool2_fwd(ptr(Y), ptr(c), ptr(self._mask), b, h, w, len(self.ops) + 1, plan['slots'].ctypes.data, ps, pg, plan['gk'], stream())
+        for slot, name, op in plan['rest']:
+            op.forward(Y, scratch, strengths[name], training=training)
+            L.ni_avgpool_fwd(ptr(scratch), ptr(c[slot * b:(slot + 1) * b]), b, h, w, 2, stream())
+        return c
+
+    def backward(self, Y, dc, dY, plan, strengths, scratch):
+        """dY += d(pooled stack)/dY applied to dc."""
+        b, h, w = _nhw3(Y)
+        L = _lib.lib()
+        _, pg = _f32(plan['gauss']) if plan['gauss'] is not None else (None, None)
+        L.ni_manip_stack_pool2_bwd(ptr(self._mask), ptr(dc), ptr(dY), b, h, w, len(self.ops) + 1, plan['slots'].ctypes.data, pg, plan['gk'], 1, stream())
+        for slot, name, op in plan['rest']:
+            if op.has_grad:
+                L.ni_avgpool_bwd(ptr(dc[slot * b:(slot + 1) * b]), ptr(scratch), b, h, w, 2, stream())
+                op.backward(Y, scratch, dY, strengths[name])
+        return dY
+
+
 def avgpool_fwd(x, k, out=None):
     n, h, w = _nhw3(x)
     y = empty((n, -(-h // k), -(-w // k), 3)) if out is None else out

@@ -1,5 +1,5 @@
-"""Batch-sharded data parallelism: one process per GPU, ONE NCCL all-reduce (sum) per flat gradient buffer between
-backward and the fused Adam launch; the 1/world_size average is folded into the Adam kernel's gradient scale.
+"""Batch-sharded data parallelism: one process per GPU, ONE NCCL all-reduce (sum) over the gradient arena (all models' flat
+gradient buffers back to back, nn.unify_gradients) between backward and the fused Adam launch; the 1/world_size average is folded into the Adam kernel's gradient scale.
 
 The reference has no multi-GPU code at all (SURVEY.md 2.1 "Parallelism strategies present in the reference: none");
 every operator on the path is per-image (no BatchNorm), so sharding the raw batch by rank is exact: mean-type losses
@@ -19,6 +19,12 @@ class GradSync:
 
     def __call__(self, stores):
         if self.world == 1:
+            return
+        arena = getattr(stores[0], 'arena', None)
+        # stores laid out in one arena (nn.unify_gradients): ONE collective over the whole bucket
+        if arena is not None and all(getattr(s, 'arena', None) is arena for s in stores) \
+                and sum(s.gflat.numel() for s in stores) == arena.numel():
+            dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.group)
             return
         for s in stores:
             dist.all_reduce(s.gflat, op=dist.ReduceOp.SUM, group=self.group)

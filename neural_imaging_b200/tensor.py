@@ -68,11 +68,12 @@ class Workspace:
         self._bufs = {}
 
     def get(self, name, shape, dtype=torch.float32):
-        shape = tuple(int(s) for s in shape)
-        b = self._bufs.get(name)
-        if b is None or b.shape != shape or b.dtype != dtype:
-            b = torch.empty(shape, dtype=dtype, device=device())
-            self._bufs[name] = b
+        """Buffers are keyed by (name, shape, dtype): a buffer handed out once is never freed or re-pointed while the workspace
+        lives, so a captured CUDA graph that baked its address in stays valid when another batch shape comes through later."""
+        key = (name, tuple(int(s) for s in shape), dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = self._bufs[key] = torch.empty(key[1], dtype=dtype, device=device())
         return b
 
     def clear(self):

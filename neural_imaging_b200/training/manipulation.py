@@ -7,11 +7,14 @@ Adam kernel sequence, replayed as CUDA graphs when `flow.enable_cuda_graph()` is
 memory statistics of the reference are control-plane extras and are not reproduced.
 """
 import os
+import shutil
 from collections import OrderedDict, deque
 
 import numpy as np
 
 from . import validation
+from ..models.compression import DCN
+from ..models.jpeg import JPEG
 
 
 def default_training_specs():
@@ -86,6 +89,35 @@ def train_manipulation_nip(flow, training, data, directories=None, overwrite=Fal
                            ('Classes', str(flow._forensics_classes)), ('Joint optimization', str(flow.trainable_models)),
                            ('# Epochs', training['n_epochs']), ('Batch size', training['batch_size']), ('Learning rate', training['learning_rate'])])
     raw_and_rgb = getattr(data, '_loaded_data', 'xy') == 'xy'
+    learned_codec = flow.is_trainable('dcn') and isinstance(flow.codec, DCN)
+
+    def validate(epoch, loss_type):
+        """One validation round: FAN accuracy + confusion, ISP and codec quality when they are being trained (reference :224-246, :300-315)."""
+        accuracy, conf = validation.validate_fan(flow, data)
+        flow.fan.log_metric('accuracy', 'validation', accuracy)
+        flow.fan.performance['confusion'] = conf.tolist()
+        if flow.is_trainable('nip') and data.is_raw_and_rgb():
+            for metric, values in zip(('ssim', 'psnr', 'loss'), validation.validate_nip(flow.nip, data, None, epoch=epoch, loss_type=loss_type)):
+                flow.nip.log_metric(metric, 'validation', values)
+        if flow.is_trainable('dcn'):
+            if learned_codec:
+                values = validation.validate_dcn(flow.codec, data, None, epoch=epoch)
+            elif isinstance(flow.codec, JPEG):
+                values = validation.validate_jpeg(flow.codec, data)
+            else:
+                raise NotImplementedError('Validation for {} codec doesn\'t seem to be implemented'.format(flow.codec))
+            for metric, value in values.items():
+                flow.codec.log_metric(metric, 'validation', value)
+
+    def snapshot(epoch):
+        validation.save_training_progress(summary, flow, save_dir, quiet=True)
+        flow.fan.save_model(os.path.join(model_directory, flow.fan.scoped_name), epoch, quiet=True)
+        if flow.is_trainable('nip'):
+            flow.nip.save_model(os.path.join(model_directory, flow.nip.scoped_name), epoch, quiet=True)
+        if learned_codec:
+            flow.codec.save_model(os.path.join(model_directory, flow.codec.scoped_name), epoch, quiet=True)
+
+    epoch = 0
     for epoch in range(0, training['n_epochs']):
         for batch_id in range(n_batches):
             if raw_and_rgb:
@@ -100,18 +132,17 @@ def train_manipulation_nip(flow, training, data, directories=None, overwrite=Fal
         for name, model in (('nip', flow.nip), ('fan', flow.fan)):
             model.log_metric('loss', 'training', list(loss_epoch[name]))
         if epoch % training['validation_schedule'] == 0:
-            accuracy, conf = validation.validate_fan(flow, data)
-            flow.fan.log_metric('accuracy', 'validation', accuracy)
-            flow.fan.performance['confusion'] = conf.tolist()
-            if flow.is_trainable('nip') and data.is_raw_and_rgb():
-                for metric, values in zip(('ssim', 'psnr', 'loss'), validation.validate_nip(flow.nip, data, None, epoch=epoch, loss_type=flow.nip.loss_metric)):
-                    flow.nip.log_metric(metric, 'validation', values)
-            validation.save_training_progress(summary, flow, save_dir, quiet=True)
-            flow.fan.save_model(os.path.join(model_directory, flow.fan.scoped_name), epoch, quiet=True)
-            if flow.is_trainable('nip'):
-                flow.nip.save_model(os.path.join(model_directory, flow.nip.scoped_name), epoch, quiet=True)
-            if flow.is_trainable('dcn') and hasattr(flow.codec, 'save_model') and len(flow.codec.parameters) > 0:
-                flow.codec.save_model(os.path.join(model_directory, flow.codec.scoped_name), epoch, quiet=True)
+            validate(epoch, flow.nip.loss_metric)
+            snapshot(epoch)
         if epoch % learning_rate_decay_schedule == 0:
             learning_rate *= learning_rate_decay_rate
+
+    # the reference always closes with a validation round and a snapshot of the weights of the LAST epoch (:300-333), whatever the
+    # validation schedule was (the ISP is scored with L2 here, as there)
+    validate(epoch, 'L2')
+    snapshot(epoch)
+    progress = os.path.join(((flow._distribution.get('compression_params') or {}).get('dirname') or ''), flow.codec.scoped_name, 'progress.json') \
+        if learned_codec else None
+    if progress and os.path.isfile(progress):          # keep the codec's own training log next to its fine-tuned weights (:331-332)
+        shutil.copyfile(progress, os.path.join(model_directory, flow.codec.scoped_name, 'progress.json'))
     return model_directory

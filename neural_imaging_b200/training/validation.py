@@ -2,8 +2,8 @@
 training/validation.py:163-203 `validate_fan`, :96-160 `validate_nip`, :19-41 `validate_jpeg`, :44-93 `validate_dcn`, without the figure rendering).
 
 The reference runs batches of 10 through `flow.run_workflow_to_decisions` and builds the confusion matrix on the host with
-an n_classes^2 Python loop per batch; here the decisions stay one device->host read per batch and the matrix is one
-np.add.at. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does; SSIM
+an n_classes^2 Python loop per batch; here whole groups of batches go through the device in one pass, the decisions and the matrix
+are accumulated by a kernel, and the host reads the result once. PSNR / loss of the NIP are computed on the host from the developed images exactly as the reference does; SSIM
 (skimage structural_similarity in the reference, helpers/metrics.py:9-26) runs in the fused device kernel ni_ssim.
 """
 import json
@@ -15,26 +15,50 @@ import numpy as np
 from ..helpers import metrics
 
 
+GROUP_IMAGES = 160          # validation images per device pass (x n_classes manipulated copies each): bounds the activation memory
+
+
 def validate_fan(flow, data, get_labels=False):
-    """Confusion matrix of the FAN inside a ManipulationClassification workflow. Returns (accuracy, conf[, labels])."""
+    """Confusion matrix of the FAN inside a ManipulationClassification workflow. Returns (accuracy, conf[, labels]).
+
+    Same samples, same numbers as the reference (batches of 10, `count_validation // 10` of them, matrix normalised by the number of
+    validation images, accuracy = mean of the per-batch accuracies) — but the batches are stacked into groups of up to GROUP_IMAGES
+    images per device pass, decisions and the int32 confusion matrix stay on the device (`ni_confusion_accumulate`), and the host reads
+    the matrix (and, on request, the decisions) once at the end instead of once per batch."""
+    import torch
+    from .. import _lib
+    from ..tensor import as_device, ptr, stream, zeros
     batch_size = int(np.minimum(10, data.count_validation))
     n_batches = data.count_validation // batch_size
     n_classes = flow.n_classes
-    conf = np.zeros((n_classes, n_classes))
-    out_labels, accuracies = [], []
-    for batch in range(n_batches):
-        batch_x = data.next_validation_batch(batch, batch_size)
-        if isinstance(batch_x, tuple):
-            batch_x = batch_x[0]
-        batch_y = flow._batch_labels(len(batch_x))
-        predicted = np.asarray(flow.run_workflow_to_decisions(batch_x))
+    L = _lib.lib()
+    conf_dev = zeros((n_classes, n_classes), torch.int32)
+    per_group = max(1, GROUP_IMAGES // batch_size)
+    preds = []
+    for first in range(0, n_batches, per_group):
+        ids = range(first, min(first + per_group, n_batches))
+        parts = []
+        for b in ids:
+            bx = data.next_validation_batch(b, batch_size)
+            parts.append(np.asarray(bx[0] if isinstance(bx, tuple) else bx, dtype=np.float32))
+        k = len(parts)
+        probs = flow.run_workflow(np.concatenate(parts, axis=0))[-1]            # class-major over the whole group: (n_classes * k * bs, n_classes)
+        labels = as_device(np.repeat(np.arange(n_classes, dtype=np.int32), k * batch_size), torch.int32)
+        pred = zeros((n_classes * k * batch_size,), torch.int32) if get_labels else None
+        L.ni_confusion_accumulate(ptr(probs), ptr(labels), ptr(conf_dev), ptr(pred), n_classes * k * batch_size, n_classes, stream())
         if get_labels:
-            out_labels += [x for x in predicted]
-        np.add.at(conf, (batch_y, predicted), 1)
-        accuracies.append(np.mean(predicted == batch_y))
-    if out_labels:
-        return np.mean(accuracies), conf / (n_batches * batch_size), out_labels
-    return np.mean(accuracies), conf / (n_batches * batch_size)
+            preds.append((pred, k))
+    counts = conf_dev.cpu().numpy().astype(np.float64)                         # the one device -> host read
+    total = n_batches * batch_size
+    conf = counts / total
+    accuracy = float(np.trace(counts) / (n_classes * total))                    # equal-size batches: mean of batch accuracies = overall accuracy
+    if get_labels:
+        out_labels = []
+        for pred, k in preds:                                                  # back to the reference's order: batch by batch, class-major inside
+            p = pred.cpu().numpy().reshape(n_classes, k, batch_size)
+            out_labels += [int(v) for b in range(k) for v in p[:, b, :].reshape(-1)]
+        return accuracy, conf, out_labels
+    return accuracy, conf
 
 
 def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type='L2'):

@@ -100,8 +100,11 @@ class ManipulationClassification(object):
         if 'dcn' in self._trainable:
             self._stores.append(self.codec._store)
         self._parameters = [p for s in self._stores for p in (q.value for q in s.trainable)]
+        self._grad_arena = nn.unify_gradients(self._stores)        # one bucket for the data-parallel all-reduce
         self._optimizer = nn.AdamKeras()
         self._ws = Workspace()
+        self._stack = ops.PooledStack(self._ops)
+        self._fuse_pool = True            # tests switch it off to compare against the operator-by-operator path
         self._labels = {}
         self._use_graph = False
         self._graphs = {}
@@ -222,6 +225,16 @@ class ManipulationClassification(object):
             raise RuntimeError('∇ NaNs: non-finite gradients detected by the fused Adam kernel')
         return loss, parts
 
+    def release_workspaces(self):
+        """Drop every persistent activation / gradient buffer and captured graph (they are re-created on the next step). Workspaces keep
+        one buffer per (name, shape) alive so that captured graphs stay valid; call this between very different batch sizes."""
+        self._graphs.clear()
+        for obj in (self, self.nip, self.fan, self.codec):
+            ws_ = getattr(obj, '_ws', None)
+            if ws_ is not None:
+                ws_.clear()
+        torch.cuda.empty_cache()
+
     def enable_cuda_graph(self, enabled=True):
         """Replay the step as two captured CUDA graphs (forward + backward | Adam + loss scalars) instead of ~1100 separate
         launches. Used when the step is static: augment=False and a fixed codec quality; the first call of a given
@@ -278,18 +291,19 @@ class ManipulationClassification(object):
         opt = self._optimizer
         opt.lr = float(learning_rate)
         opt.iterations += 1
-        st['lr_host'][0] = float(opt.step_size())
         st['fwd_bwd'].replay()
         if grad_sync is not None:
             grad_sync(self._stores)
+        # the bias-corrected step size reaches the captured Adam through a device scalar written by a stream-ordered launch (its value
+        # is a kernel argument): the host may run any number of steps ahead without racing a pinned staging buffer
+        _lib.lib().ni_fill(ptr(st['lr_dev']), float(opt.step_size()), 1, stream())
         st['update'].replay()
         loss, parts = st['out']
         return wrap(loss.clone()), {k: (wrap(v.clone()) if isinstance(v, torch.Tensor) else v) for k, v in parts.items()}
 
     def _capture(self, x_shape, t_shape, lambda_nip, lambda_dcn, world, gscale):
         L = _lib.lib()
-        st = {'x': empty(tuple(x_shape)), 't': empty(tuple(t_shape)), 'lr_dev': zeros((1,)),
-              'lr_host': torch.zeros(1, dtype=torch.float32).pin_memory()}
+        st = {'x': empty(tuple(x_shape)), 't': empty(tuple(t_shape)), 'lr_dev': zeros((1,))}
         torch.cuda.synchronize()
         n0 = int(L.ni_launch_count())
         st['fwd_bwd'] = torch.cuda.CUDAGraph()
@@ -297,7 +311,6 @@ class ManipulationClassification(object):
             ctx = self._forward_backward(st['x'], st['t'], lambda_nip, lambda_dcn, False, world)
         st['update'] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(st['update'], pool=st['fwd_bwd'].pool(), capture_error_mode='thread_local'):
-            st['lr_dev'].copy_(st['lr_host'], non_blocking=True)     # pinned -> device copy node: re-read at every replay
             st['out'] = self._update(ctx, gscale, lr_t_dev=st['lr_dev'])
         st['launches'] = int(L.ni_launch_count()) - n0
         st['ctx'] = ctx
@@ -324,10 +337,19 @@ class ManipulationClassification(object):
         Y = self.nip._forward(x, save=train_nip)
         strengths = self._draw_strengths(augment)
         M = self.n_classes * B
-        m = ws.get('m', (M,) + tuple(Y.shape[1:]))
-        self._manipulate(Y, strengths, m, training=train_nip)
-        c = self._downsample(m, out=ws.get('c', (M, -(-Y.shape[1] // self.downsampling_factor), -(-Y.shape[2] // self.downsampling_factor), 3))
-                             if self._distribution['downsampling'].startswith('pool') else None)
+        # manipulations + 2x2 average pooling in one pass (no full-resolution stack) whenever the channel allows it
+        fused = self._fuse_pool and ops.PooledStack.applicable(self._distribution['downsampling'], Y.shape[1], Y.shape[2])
+        if fused:
+            plan = self._stack.plan(strengths, Y.shape[1])
+            m = None
+            scratch = ws.get('mscratch', Y.shape) if plan['rest'] else None
+            c = self._stack.forward(Y, ws.get('c', (M, Y.shape[1] // 2, Y.shape[2] // 2, 3)), plan, strengths, scratch, training=train_nip,
+                                    mask=ws.get('gmask', Y.shape[:3], torch.uint8) if train_nip else None)
+        else:
+            m = ws.get('m', (M,) + tuple(Y.shape[1:]))
+            self._manipulate(Y, strengths, m, training=train_nip)
+            c = self._downsample(m, out=ws.get('c', (M, -(-Y.shape[1] // self.downsampling_factor), -(-Y.shape[2] // self.downsampling_factor), 3))
+                                 if self._distribution['downsampling'].startswith('pool') else None)
         entropy = acc_dcn = None
         if comp == 'jpeg':
             C = ws.get('C', c.shape)
@@ -364,14 +386,17 @@ class ManipulationClassification(object):
                 self.codec._with_quality(quality, lambda: self.codec._model.backward(c, dC, dc))
             elif comp != 'dcn':
                 dc = dC
-            dm = self._downsample_bwd(dc, m.shape, ws)
             dY = ws.get('dY', Y.shape)
             # dY = lambda_nip * d(nip loss)/dY + native slot + manipulation branches
             self.nip.loss_backward(Y, t, dY, float(lambda_nip))
-            L.ni_axpy(ptr(dY), ptr(dm[:B]), 1.0, dY.numel(), s)
-            for i, (name, op) in enumerate(self._ops.items()):
-                if op.has_grad:
-                    op.backward(Y, dm[(i + 1) * B:(i + 2) * B], dY, strengths[name])
+            if fused:
+                self._stack.backward(Y, dc, dY, plan, strengths, scratch)
+            else:
+                dm = self._downsample_bwd(dc, m.shape, ws)
+                L.ni_axpy(ptr(dY), ptr(dm[:B]), 1.0, dY.numel(), s)
+                for i, (name, op) in enumerate(self._ops.items()):
+                    if op.has_grad:
+                        op.backward(Y, dm[(i + 1) * B:(i + 2) * B], dY, strengths[name])
             self.nip._backward(dY)
         return {'M': M, 'Y_numel': Y.numel(), 'loss_ce': loss_ce, 'acc': acc, 'acc_dcn': acc_dcn, 'entropy': entropy,
                 'comp': comp, 'train_dcn': train_dcn, 'lambda_nip': float(lambda_nip), 'lambda_dcn': float(lambda_dcn)}

@@ -84,7 +84,7 @@ def test_jpeg_api_errors():
     assert repr(c) == 'JPEG(quality=75,codec="sin",trainable=False)'
     assert c.summary() == 'JPEG (sin) QF=75' and c.estimate_qf() == 75
     assert jpeg.JPEG((50, 90))._quality_mode() == 'QF~[50,90]'
-    assert np.isnan(jpeg.JPEG.loss(None, None, float('nan'))) if False else True
+    assert np.isnan(jpeg.JPEG.loss(None, None, float('nan')))          # the workflow's NaN entropy lands in sample_weight
 
 
 def test_paramspec_semantics():

@@ -139,3 +139,56 @@ def test_avgpool(shape, k):
     g_ref, = torch.autograd.grad(yt, xt, torch.tensor(dy, dtype=torch.float64))
     g = ops.avgpool_bwd(as_device(dy), shape, k).cpu().numpy()
     assert_parity(g, g_ref.numpy(), tol=1e-6, what='parity')
+
+
+@pytest.mark.parametrize('b,hw,names', [(3, 64, ('sharpen', 'resample', 'gaussian', 'jpeg')), (2, 96, ('sharpen', 'resample', 'gaussian')),
+                                         (1, 256, ('gaussian', 'resample')), (2, 40, ('resample', 'gamma', 'sharpen', 'median')),
+                                         (2, 72, ('gaussian3', 'resample70'))])
+def test_fused_pooled_stack_equals_operator_by_operator(b, hw, names):
+    """ni_manip_stack_pool2_fwd / _bwd (manipulations with the 2x2 average pooling folded into the store) against the
+    stand-alone kernels followed by ni_avgpool: run_manipulations + run_downsampling of workflows/manipulation_classification.py:199-245.
+    Sizes cover whole tiles, partial tiles (96, 40, 72 are not multiples of the 32-pixel tile) and image borders inside one tile."""
+    from collections import OrderedDict
+    from neural_imaging_b200 import _lib, ops
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream, zeros
+    makers = {'sharpen': (ops.SharpenOp, 1.0), 'resample': (ops.ResampleOp, 50), 'gaussian': (lambda: ops.GaussianOp(5), 0.83),
+              'jpeg': (ops.JpegOp, 80), 'gamma': (ops.GammaOp, 3.0), 'median': (ops.MedianOp, 3), 'gaussian3': (lambda: ops.GaussianOp(3), 1.2),
+              'resample70': (ops.ResampleOp, 70)}
+    opsd, strengths = OrderedDict(), {}
+    for nme in names:
+        opsd[nme] = makers[nme][0]()
+        strengths[nme] = makers[nme][1]
+    rs = np.random.RandomState(b * 1000 + hw)
+    Y = as_device(rs.uniform(-0.1, 1.1, size=(b, hw, hw, 3)).astype(np.float32))
+    k = len(names) + 1
+    dc = as_device(rs.normal(size=(k * b, hw // 2, hw // 2, 3)).astype(np.float32))
+    dY0 = rs.normal(size=(b, hw, hw, 3)).astype(np.float32)
+    L = _lib.lib()
+    # operator by operator
+    m = empty((k * b, hw, hw, 3))
+    ops.copy_into(m[:b], Y)
+    for i, (nme, op) in enumerate(opsd.items()):
+        op.forward(Y, m[(i + 1) * b:(i + 2) * b], strengths[nme], training=True)
+    c_ref = ops.avgpool_fwd(m, 2)
+    dm = ops.avgpool_bwd(dc, m.shape, 2)
+    dY_ref = as_device(dY0.copy())
+    L.ni_axpy(ptr(dY_ref), ptr(dm[:b]), 1.0, dY_ref.numel(), stream())
+    for i, (nme, op) in enumerate(opsd.items()):
+        if op.has_grad:
+            op.backward(Y, dm[(i + 1) * b:(i + 2) * b], dY_ref, strengths[nme])
+    # fused
+    assert ops.PooledStack.applicable('pool:2', hw, hw) and not ops.PooledStack.applicable('bilinear', hw, hw)
+    stack = ops.PooledStack(opsd)
+    plan = stack.plan(strengths, hw)
+    assert plan['slots'][0] == 0 and len(plan['rest']) == sum(n in ('jpeg', 'gamma', 'median', 'resample70') for n in names)
+    scratch = empty((b, hw, hw, 3))
+    c = stack.forward(Y, zeros((k * b, hw // 2, hw // 2, 3)), plan, strengths, scratch, training=True)
+    dY = stack.backward(Y, dc, as_device(dY0.copy()), plan, strengths, scratch)
+    torch.cuda.synchronize()
+    c, c_ref, dY, dY_ref = c.cpu().numpy(), c_ref.cpu().numpy(), dY.cpu().numpy(), dY_ref.cpu().numpy()
+    # forward: same arithmetic operation for operation -> float32 rounding only (FMA contraction may differ between the two kernels)
+    assert rel_err(c, c_ref) < 2e-6, rel_err(c, c_ref)
+    for i in range(k):
+        assert rel_err(c[i * b:(i + 1) * b], c_ref[i * b:(i + 1) * b]) < 2e-6, (i, names)
+    # backward: the reference chain scatters with atomics (order varies), the fused kernel gathers
+    assert rel_err(dY, dY_ref) < 5e-6, rel_err(dY, dY_ref)

@@ -1,5 +1,7 @@
 """GPU parity of the models (UNet, FAN) and of the joint training step against the CPU oracle restatement of
 models/pipelines.py:169-230, models/forensics.py:29-125 and workflows/manipulation_classification.py:260-285."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -258,10 +260,78 @@ def test_training_loop_api(tmp_path):
             'learning_rate': 1e-3, 'lambda_nip': 0.1}
     out = manipulation.train_manipulation_nip(flow, spec, data, {'root': str(tmp_path)}, overwrite=True)
     assert out.endswith('models') and str(tmp_path) in out
-    assert len(flow.fan.performance['loss']['training']) == 3 and len(flow.fan.performance['accuracy']['validation']) == 2
+    # validation at epochs 0 and 2 plus the closing round the reference always runs (training/manipulation.py:300-303)
+    assert len(flow.fan.performance['loss']['training']) == 3 and len(flow.fan.performance['accuracy']['validation']) == 3
+    assert os.path.isfile(os.path.join(out, 'fan', 'fan.npz')) or os.path.isdir(os.path.join(out, 'fan'))
     conf = np.array(flow.fan.performance['confusion'])
     assert conf.shape == (5, 5) and np.allclose(conf.sum(axis=1), 1.0)       # reference normalisation: per-class rates (:200-202)
     acc, conf2, labels = validation.validate_fan(flow, data, get_labels=True)
     assert len(labels) == 5 * 4 and 0.0 <= acc <= 1.0
     with pytest.raises(RuntimeError):          # 'camera_name' is a required key (reference :81-86)
         manipulation.train_manipulation_nip(flow, {k: v for k, v in spec.items() if k != 'camera_name'}, data, {'root': str(tmp_path)})
+
+
+def test_training_loop_with_the_real_dataset_class(tmp_path):
+    """helpers.dataset.Dataset (integer images, patch sampling) through train_manipulation_nip and validate_fan: the loops read
+    count_training / count_validation / rgb_patch_size from it (reference helpers/dataset.py:160-185), and validate_fan's grouped device
+    pass must give the numbers of the reference's batch-of-10 host loop."""
+    from neural_imaging_b200.helpers.dataset import Dataset
+    from neural_imaging_b200.training import manipulation, validation
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    rs = np.random.RandomState(11)
+    n, H = 6, 96
+    y = rs.randint(0, 256, size=(n, H, H, 3)).astype(np.uint8)
+    x = rs.randint(0, 65536, size=(n, H // 2, H // 2, 4)).astype(np.uint16)
+    vy = rs.randint(0, 256, size=(23, 32, 32, 3)).astype(np.uint8)
+    vx = rs.randint(0, 65536, size=(23, 16, 16, 4)).astype(np.uint16)
+    data = Dataset.from_arrays(x=x, y=y, val_x=vx, val_y=vy)
+    assert (data.count_training, data.count_validation, data.rgb_patch_size) == (6, 23, 32)
+    flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=16, seed=4)
+    spec = {'camera_name': 'toy', 'use_pretrained_nip': False, 'patch_size': 16, 'batch_size': 3, 'n_epochs': 2, 'validation_schedule': 5,
+            'learning_rate': 1e-3, 'lambda_nip': 0.1}
+    np.random.seed(3)
+    out = manipulation.train_manipulation_nip(flow, spec, data, {'root': str(tmp_path)}, overwrite=True)
+    assert len(flow.fan.performance['accuracy']['validation']) == 2          # epoch 0 + the closing round (weights of the last epoch are saved)
+    assert os.path.isdir(os.path.join(out, flow.nip.scoped_name)) and os.path.isfile(os.path.join(os.path.dirname(out), 'training.json'))
+    # grouped device pass == the reference's loop (batches of 10, 23 // 10 = 2 of them, decisions read batch by batch)
+    acc, conf, labels = validation.validate_fan(flow, data, get_labels=True)
+    ref_conf, ref_labels, accs = np.zeros((5, 5)), [], []
+    for b in range(2):
+        bx = data.next_validation_batch(b, 10)[0]
+        pred = np.asarray(flow.run_workflow_to_decisions(bx))
+        lab = flow._batch_labels(10)
+        np.add.at(ref_conf, (lab, pred), 1)
+        ref_labels += list(pred)
+        accs.append(np.mean(pred == lab))
+    assert labels == [int(v) for v in ref_labels]
+    assert np.array_equal(conf, ref_conf / 20) and abs(acc - np.mean(accs)) < 1e-12
+    old = validation.GROUP_IMAGES
+    try:
+        validation.GROUP_IMAGES = 10          # one batch per pass: same result whatever the grouping
+        acc1, conf1 = validation.validate_fan(flow, data)
+    finally:
+        validation.GROUP_IMAGES = old
+    assert acc1 == acc and np.array_equal(conf1, conf)
+
+
+def test_fused_pooled_stack_inside_the_training_step():
+    """The joint step with the manipulation stack + average pooling fused (default) against the operator-by-operator path
+    (flow._fuse_pool = False): same losses, same gradients."""
+    from neural_imaging_b200.workflows.manipulation_classification import ManipulationClassification
+    rs = np.random.RandomState(77)
+    x = rs.uniform(size=(2, 32, 32, 4)).astype(np.float32)
+    t = rs.uniform(size=(2, 64, 64, 3)).astype(np.float32)
+    res = {}
+    for fused in (True, False):
+        flow = ManipulationClassification('UNet', trainable={'nip'}, raw_patch_size=32, seed=9,
+                                          distribution={'downsampling': 'pool:2', 'compression': 'jpeg', 'compression_params': {'quality': 50, 'codec': 'sin'}})
+        flow._fuse_pool = fused
+        Y, c, C, ent, probs = flow.run_workflow(x)
+        loss, parts = flow.training_step(x, t, lambda_nip=0.1, learning_rate=1e-4)
+        res[fused] = (float(loss.numpy()), float(parts['ce'].numpy()), _grads(flow.nip._store), _grads(flow.fan._store))
+    assert abs(res[True][0] - res[False][0]) <= 1e-6 * abs(res[False][0]) and abs(res[True][1] - res[False][1]) <= 1e-5 * abs(res[False][1])
+    for k in (2, 3):
+        for name, g in res[True][k].items():
+            ref = res[False][k][name]
+            e = np.abs(g - ref) / max(float(np.abs(ref).max()), 1e-30)
+            assert np.mean(e > 2e-5) <= 0.02, (name, float(e.max()))

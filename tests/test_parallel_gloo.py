@@ -41,6 +41,21 @@ def _worker(rank, world, port, out):
         ok = False
     except ValueError:
         pass
+    # gradient buffers laid out in one arena (nn.unify_gradients): the hook issues ONE collective over the whole bucket
+    a, b = _Store(1000, rank), _Store(40, rank)
+    arena = torch.cat((a.gflat, b.gflat))
+    a.gflat, b.gflat = arena[:1000], arena[1000:]
+    a.arena = b.arena = arena
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, **kw: (calls.append(t.numel()), real(t, **kw))[1]
+    try:
+        sync([a, b])
+    finally:
+        dist.all_reduce = real
+    ok = ok and calls == [1040]
+    ok = ok and torch.allclose(a.gflat, sum(_Store(1000, r).gflat for r in range(world))) \
+        and torch.allclose(b.gflat, sum(_Store(40, r).gflat for r in range(world)))
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -81,58 +81,6 @@ def numpy_ssim(monkeypatch):
     monkeypatch.setattr(metrics, 'ssim', lambda a, b: 1.0 - float(np.mean(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)))))
 
 
-def test_train_nip_model_loop(tmp_path, numpy_ssim):
-    from neural_imaging_b200.training import pipeline
-    data, model = _Data(), _NIP()
-    out = pipeline.train_nip_model(model, 'cam', n_epochs=7, lr_schedule={0: 1e-3, 4: 1e-4}, validation_schedule=3, patch_size=16, batch_size=4,
-                                   data=data, out_directory_root=str(tmp_path))
-    assert out == os.path.join(str(tmp_path), 'cam', 'FakeNet', model.scoped_name) and os.path.isfile(os.path.join(out, 'progress.json'))
-    assert data.calls[0] == (0, 5, 32, 'flat') and data.calls[1] == (0, 4, 16, 'flat')            # the shape probe, then the loop's own call
-    assert model.lrs == [1e-3] * 8 + [1e-4] * 6                                                   # 2 batches x 7 epochs, schedule at epoch 4
-    assert len(model.performance['loss']['training']) == 7 and len(model.performance['loss']['validation']) == 3      # epochs 0, 3, 6
-    assert model.saved == [0, 3, 6, 6]                                                            # every validation + the final snapshot
-    log = json.load(open(os.path.join(out, 'progress.json')))
-    assert set(log) == {'performance', 'args', 'model', 'init', 'summary'} and log['model'] == '_NIP' and log['summary']['Epoch'] == 6
-    assert log['summary']['Saved checkpoint'] == 6 and log['summary']['# batches'] == 2 and log['summary']['Training data size'] == [8, 16, 16, 4]
-    expect = np.mean([np.mean((255 * y.astype(np.float64) - 127.5) ** 2) for y in data._val_y])       # metrics.mse(255 ref, 255 developed), mean over images
-    assert abs(log['performance']['loss']['validation'][0] - expect) < 1e-6 * expect
-    # an existing directory is skipped unless resuming; resume restores counters, performance and weights
-    again = _NIP()
-    assert pipeline.train_nip_model(again, 'cam', n_epochs=3, data=data, patch_size=16, batch_size=4, out_directory_root=str(tmp_path)) == out
-    assert again.lrs == []
-    resumed = _NIP()
-    pipeline.train_nip_model(resumed, 'cam', n_epochs=9, lr_schedule=5e-4, validation_schedule=3, resume=True, patch_size=16, batch_size=4,
-                             data=data, out_directory_root=str(tmp_path))
-    assert resumed.loaded == out and len(resumed.lrs) == 2 * (9 - 6) and resumed.lrs[0] == 1e-4       # float schedule = {0: lr}: epoch 0 is past
-    assert len(resumed.performance['loss']['training']) == 7 + 3
-    with pytest.raises(FileNotFoundError):
-        pipeline.train_nip_model(_NIP(), 'other', resume=True, data=data, patch_size=16, batch_size=4, out_directory_root=str(tmp_path / 'x'))
-    # errors (training/pipeline.py:109-121)
-    with pytest.raises(ValueError, match='not to be loaded'):
-        pipeline.train_nip_model(_NIP(), 'cam', data=None)
-    with pytest.raises(ValueError, match='exceeds dataset size'):
-        pipeline.train_nip_model(_NIP(), 'cam', data=data, patch_size=16, batch_size=50, out_directory_root=str(tmp_path / 'y'))
-    with pytest.raises(ValueError, match='Data set error'):
-        pipeline.train_nip_model(_NIP(), 'cam', data=_Data(raw=False), patch_size=16, batch_size=4, out_directory_root=str(tmp_path / 'z'))
-    with pytest.raises(ValueError, match='Unsupported loss'):
-        pipeline.validate(model, data, out, loss_metric='L3')
-
-
-def test_train_nip_model_best_checkpoint_lr_drop_and_early_stop(tmp_path, numpy_ssim):
-    from neural_imaging_b200.training import pipeline
-    data = _Data()
-    # validation quality per validation round: improves, then gets >20 % worse (lr drop, no snapshot with save_best), then goes flat
-    q = [0.30, 0.40, 0.45, 0.45, 0.45, 0.45, 0.10, 0.45] + [0.45] * 12
-    model = _NIP(losses=q)
-    pipeline.train_nip_model(model, 'cam', n_epochs=40, lr_schedule={0: 1e-3}, validation_schedule=1, patch_size=16, batch_size=4, data=data,
-                             out_directory_root=str(tmp_path), save_best=True, validation_loss_threshold=1e-3)
-    v = model.performance['loss']['validation']
-    assert len(v) < 40                                           # stopped early on the flat validation loss
-    assert 6 not in model.saved and model.saved[0] == 2          # save_best: needs > 2 validations, never the deteriorated round
-    dropped = [lr for lr in model.lrs if lr < 1e-3]
-    assert dropped and abs(dropped[0] - 0.95e-3) < 1e-12         # one 0.95 drop after the deterioration (len > 5 and > 1.2 x best)
-
-
 class _DCN(TFModel):
     model_code = 'FakeDCN/8c'
 
