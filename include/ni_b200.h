@@ -224,6 +224,11 @@ int ni_gap_bwd(const float* dy, float* dx, int n, int hw, int c, ni_stream_t str
 /* softmax + SparseCategoricalCrossentropy on probabilities, Keras eager semantics (models/forensics.py:90,94) */
 int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* loss_sum, float* dlogits, int m, int c,
                   float gscale, ni_stream_t stream);
+/* ConstrainedConv2D.call (models/layers.py:45-57) on the normalised filter nf (5, 5, 3, 3): SYMMETRIC pad 2 + VALID conv, no bias; its
+   input gradient with the transpose of the mirrored pad folded in; its filter gradient (dnf is zeroed first). x, y, dy, dx: (n, h, w, 3) */
+int ni_cconv5_fwd(const float* x, const float* nf, float* y, int n, int h, int w, ni_stream_t stream);
+int ni_cconv5_bwd_data(const float* dy, const float* nf, float* dx, int n, int h, int w, int accumulate, ni_stream_t stream);
+int ni_cconv5_bwd_filter(const float* x, const float* dy, float* dnf, int n, int h, int w, ni_stream_t stream);
 /* validate_fan's decisions and confusion matrix (training/validation.py:163-203; workflows/manipulation_classification.py:178-180):
    pred[i] = argmax probs[i, :], conf[labels[i] * c + pred[i]] += 1 (int32, caller zeroes); pred or conf may be null */
 int ni_confusion_accumulate(const float* probs, const int* labels, int* conf, int* pred, int m, int c, ni_stream_t stream);

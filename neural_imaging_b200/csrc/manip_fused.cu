@@ -12,6 +12,7 @@
 // The arithmetic of every operator follows the stand-alone kernels of manip.cu operation for operation (same tap order, same
 // interpolation formulas), so the fused result equals avg_pool(manipulation(x)) to float32 rounding.
 #include "ni_common.cuh"
+#include "tile3.cuh"
 
 namespace {
 
@@ -61,32 +62,6 @@ __device__ __forceinline__ void hsv2rgb(float h, float s, float v, float& r, flo
     b = (one_s + s * db) * v;
 }
 
-// Image tile in shared memory: rows y0 - HALO .. y0 + 31 + HALO, columns x0 - XOFF .. x0 - XOFF + COLS - 1 (XOFF, COLS multiples of 4 so
-// that interior row segments are 16-byte aligned), interleaved RGB. Out-of-image positions hold the REFLECT-mirrored pixel (tf.pad).
-template <int HALO, int XOFF, int COLS>
-__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ img, int H, int W, int y0, int x0) {
-    constexpr int ROWS = kTS + 2 * HALO;
-    constexpr int RS = COLS * 3;
-    const bool fast = (x0 - XOFF >= 0) && (x0 - XOFF + COLS <= W) && ((W & 3) == 0);
-    if (fast) {
-        constexpr int V = RS / 4;
-        for (int t = threadIdx.x; t < ROWS * V; t += kThreads) {
-            const int r = t / V, v = t - r * V;
-            const int gy = reflect_i(y0 - HALO + r, H);
-            const float4 val = ni_ldg4(img + ((size_t)gy * W + (x0 - XOFF)) * 3 + v * 4);
-            *reinterpret_cast<float4*>(tile + r * RS + v * 4) = val;
-        }
-    } else {
-        for (int t = threadIdx.x; t < ROWS * RS; t += kThreads) {
-            const int r = t / RS, q = t - r * RS;
-            const int col = q / 3, ch = q - col * 3;
-            const int gy = reflect_i(y0 - HALO + r, H);
-            const int gx = clamp_i(reflect_i(x0 - XOFF + col, W), W);     // columns further out than the halo are never read
-            tile[t] = __ldg(img + ((size_t)gy * W + gx) * 3 + ch);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------ forward
 constexpr int kFH = 2, kFX = 4, kFC = 40;                     // forward tile: halo 2, 40 columns
 constexpr int kFRS = kFC * 3;
@@ -101,7 +76,7 @@ manip_stack_pool2_fwd_kernel(const float* __restrict__ Y, float* __restrict__ c,
     __shared__ float small[kSmN * kSmN * 3];
     const int n = blockIdx.z, y0 = blockIdx.y * kTS, x0 = blockIdx.x * kTS;
     const float* img = Y + (size_t)n * H * W * 3;
-    load_tile<kFH, kFX, kFC>(tile, img, H, W, y0, x0);
+    load_tile3<kTS, kFH, kFX, kFC, TILE_REFLECT, kThreads>(tile, img, H, W, y0, x0);      // REFLECT halo (gaussian); sharpen / resample map their own
     __syncthreads();
     const int H2 = H >> 1, W2 = W >> 1;
     // HSV of the tile + halo 1 under SYMMETRIC padding (the source pixel of a padded position lies inside the image, hence inside the tile)

@@ -86,7 +86,8 @@ class FAN(TFModel):
         L.ni_constrained_filter_fwd(ptr(self._cconv.w.value), ptr(self._nf), 5, 3, self.filter_strength, s)
         acts = {'x': x}
         d0 = self._cconv.desc(m, h, w)
-        r = self._cconv.fprop(x, ws.get('r', (m, h, w, 3)), d0, weight=self._nf)
+        r = ws.get('r', (m, h, w, 3))
+        L.ni_cconv5_fwd(ptr(x), ptr(self._nf), ptr(r), m, h, w, s)
         acts['r'], descs = r, {'cconv': d0}
         cur, ch, cw = r, h, w
         for i, conv in enumerate(self._convs):
@@ -181,17 +182,11 @@ class FAN(TFModel):
         # constrained conv: filter gradient through the normalisation; input gradient through the mirrored pad
         d0 = descs['cconv']
         dx = None
-        L.ni_conv2d_wgrad(ctypes.byref(d0), ptr(acts['x']), ptr(dp), ptr(self._dnf), s)
+        L.ni_cconv5_bwd_filter(ptr(acts['x']), ptr(dp), ptr(self._dnf), m, h, w, s)
         L.ni_constrained_filter_bwd(ptr(self._cconv.w.value), ptr(self._dnf), ptr(self._cconv.w.grad), 5, 3, self.filter_strength, s)
         if need_dx:
-            pad = 2
-            dpad = ws.get('dpad', (m, h + 2 * pad, w + 2 * pad, 3))
-            dd = self._cconv.desc(m, h + 2 * pad, w + 2 * pad)   # VALID conv on the padded domain
-            dd.pad_t = dd.pad_l = 0
-            dd.oh, dd.ow, dd.pad_mode = h, w, PAD_ZERO
-            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dp), ptr(self._nf), ptr(dpad), s)
             dx = ws.get('dx', (m, h, w, 3))
-            L.ni_pad_fold(ptr(dpad), ptr(dx), m, h, w, 3, pad, PAD_SYMMETRIC, 0, s)
+            L.ni_cconv5_bwd_data(ptr(dp), ptr(self._nf), ptr(dx), m, h, w, 0, s)       # transpose of (SYMMETRIC pad + VALID conv) in one kernel
         return dx
 
     def loss(self, labels, probabilities):

@@ -47,7 +47,7 @@ class ConstrainedConv2D(object):
             raise ValueError('ConstrainedConv2D expects 3-channel images')
         self.normalized_kernel()
         y = empty((n, h, w, 3))
-        self._conv.fprop(x, y, self._conv.desc(n, h, w), weight=self._nf)
+        _lib.lib().ni_cconv5_fwd(ptr(x.contiguous()), ptr(self._nf), ptr(y), n, h, w, stream())
         return wrap(y)
 
     call = __call__

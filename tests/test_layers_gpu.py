@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import rel_err
 from oracle import ref_models as M
 from oracle import ref_ops as R
 
@@ -64,3 +65,31 @@ def test_constrained_conv2d():
     assert np.max(np.abs(layer.normalized_kernel().numpy() - nf.numpy())) < 1e-4
     with pytest.raises(ValueError):
         layer(np.zeros((1, 8, 8, 4), np.float32))
+
+
+@pytest.mark.parametrize('n,h,w', [(2, 32, 32), (1, 128, 128), (3, 40, 72), (2, 12, 20)])
+def test_constrained_conv_kernels_forward_data_and_filter_gradient(n, h, w):
+    """ni_cconv5_fwd / _bwd_data / _bwd_filter (SYMMETRIC pad 2 + VALID 5x5 conv 3 -> 3 with the pad's transpose folded into the input
+    gradient) against autograd on the float64 oracle (models/layers.py:45-57); sizes with partial tiles and borders inside one tile."""
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream
+    rs = np.random.RandomState(n * 100 + h)
+    x = rs.uniform(size=(n, h, w, 3)).astype(np.float32)
+    f = rs.normal(size=(5, 5, 3, 3)).astype(np.float32)
+    dy = rs.normal(size=(n, h, w, 3)).astype(np.float32)
+    L = _lib.lib()
+    xd, fd, dyd = as_device(x), as_device(f), as_device(dy)
+    y, dx, df = empty((n, h, w, 3)), empty((n, h, w, 3)), empty((5, 5, 3, 3))
+    L.ni_cconv5_fwd(ptr(xd), ptr(fd), ptr(y), n, h, w, stream())
+    L.ni_cconv5_bwd_data(ptr(dyd), ptr(fd), ptr(dx), n, h, w, 0, stream())
+    L.ni_cconv5_bwd_filter(ptr(xd), ptr(dyd), ptr(df), n, h, w, stream())
+    dx2 = as_device(x.copy())
+    L.ni_cconv5_bwd_data(ptr(dyd), ptr(fd), ptr(dx2), n, h, w, 1, stream())          # accumulate
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    ft = torch.tensor(f, dtype=torch.float64, requires_grad=True)
+    yt = R.conv2d(R.tf_pad(xt, 2, 'SYMMETRIC'), ft, padding='VALID')
+    gx, gf = torch.autograd.grad(yt, [xt, ft], torch.tensor(dy, dtype=torch.float64))
+    assert rel_err(y.cpu().numpy(), yt.detach().numpy()) < 1e-5
+    assert rel_err(dx.cpu().numpy(), gx.numpy()) < 1e-5
+    assert rel_err(dx2.cpu().numpy() - x, gx.numpy()) < 1e-5
+    assert rel_err(df.cpu().numpy(), gf.numpy()) < 2e-5
