@@ -171,6 +171,12 @@ typedef struct ni_conv_desc {
 /* Dispatchers: tcgen05 implicit GEMM where the layer is a dense contraction, FP32 SIMT otherwise. */
 int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w /* HWIO, same tensor as fprop */, float* dx, ni_stream_t stream);
+/* dgrad fused with the activation backward + bias gradient of the layer BELOW (the tape's LeakyReluGrad / BiasAddGrad of the producing
+ * Conv2D, models/pipelines.py:190-214): dx <- dgrad(dy) * act'(y_prev) (+= when d->accumulate), dbias_prev[c] += sum over pixels. y_prev is
+ * that layer's forward output, addressed like dx with its own channel pitch / offset. tcgen05 path only: query _supported first. */
+int ni_conv2d_dgrad_act_supported(const ni_conv_desc* d, int y_pitch, int y_coff);
+int ni_conv2d_dgrad_act_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, const float* y_prev, int y_pitch, int y_coff,
+                           int act_prev, float alpha_prev, float* dbias_prev, int bias_mod_prev, ni_stream_t stream);
 int ni_conv2d_wgrad(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
 /* The tcgen05 (3xTF32, FP32-accurate) implementations; ni_conv2d_tc_supported(d, op) op: 0 fprop, 1 dgrad, 2 wgrad. */
 int ni_conv2d_tc_supported(const ni_conv_desc* d, int op);

@@ -86,7 +86,7 @@ class _Lib:
         if name not in protos:
             raise AttributeError(name)
         fn = getattr(self._dll, name)
-        if protos[name][0] is not ctypes.c_int or name in ('ni_version', 'ni_device_arch', 'ni_conv2d_tc_supported', 'ni_conv2d_small_supported', 'ni_conv2d_direct_supported', 'ni_tma_probe'):
+        if protos[name][0] is not ctypes.c_int or name.endswith('_supported') or name in ('ni_version', 'ni_device_arch', 'ni_tma_probe'):
             return fn
 
         def checked(*args):

@@ -164,8 +164,14 @@ int set_dyn_smem(K kern, size_t bytes) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Activation backward of the layer BELOW fused into a dgrad (see GemmParams::dact_y)
+struct FusedAct {
+    const float* y = nullptr; int pitch = 0, coff = 0, act = NI_ACT_NONE; float alpha = 0.f; float* dbias = nullptr; int bias_mod = 0;
+};
+
 // Shared launcher for fprop (dgrad = false) and dgrad (dgrad = true).
-int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float* w, const float* bias, float* dst, cudaStream_t st) {
+int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float* w, const float* bias, float* dst, cudaStream_t st,
+                const FusedAct& fa = FusedAct()) {
     const int K = dgrad ? d->cout : d->cin, N = dgrad ? d->cin : d->cout;
     const int sh = dgrad ? d->oh : d->h, sw = dgrad ? d->ow : d->w;           // source dims
     const int th = dgrad ? d->h : d->oh, tw = dgrad ? d->w : d->ow;           // target dims
@@ -202,6 +208,8 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     p.out_pitch = dpitch; p.out_coff = dcoff; p.out_mode = dmode;
     p.bias_mod = dgrad ? 0 : d->bias_mod; p.act = dgrad ? NI_ACT_NONE : d->act; p.accumulate = d->accumulate; p.alpha = d->act_alpha;
     p.bias = dgrad ? nullptr : bias; p.out = dst;
+    p.dact_y = fa.y; p.dact_pitch = fa.pitch; p.dact_coff = fa.coff; p.dact = fa.act; p.dact_alpha = fa.alpha;
+    p.dbias = fa.dbias; p.dbias_mod = fa.bias_mod;
     const int ktot = taps * K;
     const int want_nacc = ktot > 2304 ? 3 : (ktot > 1024 ? 2 : 1);
     static const bool use_v2 = getenv("NI_TC_GEMM_V2") != nullptr;
@@ -345,6 +353,29 @@ extern "C" int ni_conv2d_dgrad_tc(const ni_conv_desc* d, const float* dy, const 
     NI_REQUIRE(ni_conv2d_tc_supported(d, 1), "ni_conv2d_dgrad_tc: problem not supported by the tcgen05 path");
     NI_REQUIRE(dy && w && dx && aligned16(dy) && aligned16(dx), "ni_conv2d_dgrad_tc: null or unaligned pointer");
     return launch_gemm(d, true, dy, w, nullptr, dx, st);
+}
+
+// dgrad whose epilogue also applies the activation derivative of the layer that produced this layer's input and accumulates that layer's
+// bias gradient: dx <- (dgrad result) * act'(y_prev), dbias_prev += column sums. y_prev is addressed like dx (plain NHWC, own pitch / offset).
+extern "C" int ni_conv2d_dgrad_act_supported(const ni_conv_desc* d, int y_pitch, int y_coff) {
+    if (!ni_conv2d_tc_supported(d, 1)) return 0;
+    if (d->in_mode != NI_MODE_PLAIN) return 0;                          // dx (and y_prev) plain NHWC
+    if ((y_pitch & 3) || (y_coff & 3)) return 0;
+    static const bool use_v2 = getenv("NI_TC_GEMM_V2") != nullptr;      // the fused epilogue exists in the generation-3 kernel only
+    return use_v2 ? 0 : 1;
+}
+extern "C" int ni_conv2d_dgrad_act_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, const float* y_prev, int y_pitch,
+                                      int y_coff, int act_prev, float alpha_prev, float* dbias_prev, int bias_mod_prev, cudaStream_t st) {
+    NI_REQUIRE(ni_conv2d_dgrad_act_supported(d, y_pitch, y_coff), "ni_conv2d_dgrad_act_tc: problem not supported by the fused tcgen05 path");
+    NI_REQUIRE(dy && w && dx && aligned16(dy) && aligned16(dx) && (y_prev == nullptr || aligned16(y_prev)), "ni_conv2d_dgrad_act_tc: null or unaligned pointer");
+    NI_REQUIRE(act_prev == NI_ACT_NONE || act_prev == NI_ACT_LEAKY_RELU || act_prev == NI_ACT_RELU || act_prev == NI_ACT_TANH ||
+               act_prev == NI_ACT_SIGMOID, "ni_conv2d_dgrad_act_tc: activation %d has no derivative in terms of its output", act_prev);
+    NI_REQUIRE(y_prev != nullptr || act_prev == NI_ACT_NONE, "ni_conv2d_dgrad_act_tc: activation backward needs the forward output");
+    FusedAct fa;
+    fa.y = y_prev; fa.pitch = y_pitch; fa.coff = y_coff; fa.act = act_prev; fa.alpha = alpha_prev; fa.dbias = dbias_prev; fa.bias_mod = bias_mod_prev;
+    if (fa.y == nullptr && fa.dbias == nullptr) return launch_gemm(d, true, dy, w, nullptr, dx, st);
+    if (fa.dbias) NI_CUDA(cudaMemsetAsync(fa.dbias, 0, sizeof(float) * (size_t)(bias_mod_prev > 0 ? bias_mod_prev : d->cin), st));   // the epilogue accumulates
+    return launch_gemm(d, true, dy, w, nullptr, dx, st, fa);
 }
 
 extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {

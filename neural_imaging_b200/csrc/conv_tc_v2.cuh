@@ -39,6 +39,14 @@ struct GemmParams {
     float* out;
     int src_block2_f;              // > 0: the source is read through depth_to_space(2) of an (n, 2h, 2w, F) buffer (5-D tensor map
                                    // (F, 2, w, 2, h*n); only for 1x1 filters = the transposed convolutions), F = src_block2_f
+    // dgrad fused with the PRODUCING layer's activation backward (generation 3 only): the result is d(loss)/d(output y of the layer below);
+    // the epilogue multiplies it by act'(y) and accumulates that layer's bias gradient (column sums), so that no separate elementwise pass
+    // (ni_act_bwd_bias: read y, read + write dy) is needed. dact_y = nullptr: off.
+    const float* dact_y;
+    int dact_pitch, dact_coff, dact;
+    float dact_alpha;
+    float* dbias;
+    int dbias_mod;
 };
 
 __device__ __forceinline__ float act_apply(float v, int act, float alpha) {

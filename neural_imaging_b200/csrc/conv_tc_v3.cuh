@@ -312,6 +312,21 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         const int qd = warp & 3, row = qd * 32 + lane;
         const int lw = row % p.bw, lh = (row / p.bw) % p.bh, ln = row / (p.bw * p.bh);
         int tcount = 0;
+        // fused activation backward: per-lane partial bias gradients (lane = channel within a 32-channel chunk), kept in registers across
+        // the tiles of this persistent CTA and flushed with one atomicAdd per channel when the n-tile changes / at the end
+        const bool fuse_act = p.dact_y != nullptr || p.dbias != nullptr;
+        float bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
+        int bs_nt = -1;
+        auto flush_bias = [&]() {
+            if (p.dbias == nullptr || bs_nt < 0) return;
+            const float bsv[4] = {bs0, bs1, bs2, bs3};
+#pragma unroll
+            for (int cc = 0; cc < BNT / 32; ++cc) {
+                const int co = bs_nt * BNT + cc * 32 + lane;
+                atomicAdd(p.dbias + (p.dbias_mod > 0 ? co % p.dbias_mod : co), bsv[cc]);
+            }
+            bs0 = bs1 = bs2 = bs3 = 0.f;
+        };
 #ifdef NI_TC_PROFILE
         long long tcp_t = 0; const bool tcp_on = blockIdx.x == 0 && threadIdx.x == 384;
 #endif
@@ -321,6 +336,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
             tile_origin(tile, x0, y0, n0, nt);
             const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;
             const bool valid = on < p.n && oy < p.oh && ox < p.ow;
+            if (fuse_act && nt != bs_nt) { flush_bias(); bs_nt = nt; }
             TCP_START();
             mbar_wait(&bar_accfull[aset], use & 1, 4);
             TCP_ADD(10);
@@ -340,8 +356,53 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     tcgen05_fence_before();
                     mbar_arrive(&bar_accfree[aset]);
                 }
-                if (!valid) continue;
+                if (!valid && !fuse_act) continue;
                 const int co0 = nt * BNT + c * 32;
+                if (fuse_act) {
+                    // v <- v * act'(y) with y = the forward output of the layer whose output gradient this is (same pixel, same channels)
+                    if (p.dact_y != nullptr && valid && p.dact != NI_ACT_NONE) {
+                        const float4* y4 = reinterpret_cast<const float4*>(
+                            p.dact_y + (((long long)on * p.oh + oy) * p.ow + ox) * p.dact_pitch + p.dact_coff + co0);
+                        float4 yv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) yv[j] = y4[j];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float ye[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float yy = ye[e];
+                                float dd;
+                                switch (p.dact) {
+                                    case NI_ACT_LEAKY_RELU: dd = yy > 0.f ? 1.f : p.dact_alpha; break;
+                                    case NI_ACT_RELU: dd = yy > 0.f ? 1.f : 0.f; break;
+                                    case NI_ACT_TANH: dd = 1.f - yy * yy; break;
+                                    case NI_ACT_SIGMOID: dd = yy * (1.f - yy); break;
+                                    default: dd = 1.f; break;
+                                }
+                                v[4 * j + e] *= dd;
+                            }
+                        }
+                    }
+                    if (p.dbias != nullptr) {
+                        // column sums over the 32 pixels of this warp: butterfly, lane l ends up with the sum of channel co0 + l
+                        float r[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = valid ? v[j] : 0.f;
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool upper = (lane & off) != 0;
+#pragma unroll
+                            for (int j = 0; j < off; ++j) {
+                                const float send = upper ? r[j] : r[j + off];
+                                const float keep = upper ? r[j + off] : r[j];
+                                r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        if (c == 0) bs0 += r[0]; else if (c == 1) bs1 += r[0]; else if (c == 2) bs2 += r[0]; else bs3 += r[0];
+                    }
+                    if (!valid) continue;
+                }
                 float* o;
                 if (p.out_mode == NI_MODE_PLAIN) {
                     o = p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff + co0;
@@ -386,6 +447,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
             }
             TCP_ADD(11);
         }
+        if (fuse_act) flush_bias();
     }
     tcgen05_fence_before();
     __syncthreads();

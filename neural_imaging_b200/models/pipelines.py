@@ -229,20 +229,23 @@ class UNet(NIPModel):
         dcur = ws.get('d_dc%d2' % (S - 1), last.shape)
         self._final.bprop(last, None, dy, dcur, descs['final'])
         dcats = {}
+        done = False           # the gradient in `dcur` already carries act'(y) and the bias gradient of its layer has been accumulated
         for n in reversed(range(1, S)):
             up, c1, c2 = self._dec[n - 1]
             c = c1.cout
             d1, d2, du = descs['dc%d1' % n], descs['dc%d2' % n], descs['dct%d' % n]
             da1 = ws.get('d_dc%d1' % n, acts['dc%d1' % n].shape)
-            c2.bprop(acts['dc%d1' % n], acts['dc%d2' % n], dcur, da1, d2)
+            # the dgrad of each convolution also applies the activation backward + bias gradient of the layer below it (tcgen05 epilogue)
+            c2.bprop(acts['dc%d1' % n], acts['dc%d2' % n], dcur, da1, d2, act_bias_done=done, fuse_prev=c1.fuse_info(acts['dc%d1' % n]))
             dcat = ws.get('d_cat%d' % n, acts['cat%d' % n].shape)
-            c1.bprop(acts['cat%d' % n], acts['dc%d1' % n], da1, dcat, d1)
+            c1.bprop(acts['cat%d' % n], acts['dc%d1' % n], da1, dcat, d1, act_bias_done=c2.fused_prev)
             dcats[n] = dcat
             # transposed conv: dy = first half of dcat seen through depth_to_space addressing
             src = acts['dc%d2' % (n - 1)] if n > 1 else acts['dc02']
+            below = self._dec[n - 2][2] if n > 1 else self._enc[S - 1][1]      # the layer that produced `src`
             dsrc = ws.get('d_dc%d2' % (n - 1), src.shape)
-            up.bprop(src, None, dcat, dsrc, du, dy_addr=(2 * c, 0, MODE_BLOCK2))
-            dcur = dsrc
+            up.bprop(src, None, dcat, dsrc, du, dy_addr=(2 * c, 0, MODE_BLOCK2), fuse_prev=below.fuse_info(src))
+            dcur, done = dsrc, up.fused_prev
         # encoder
         ch, cw = h // 2 ** (S - 1), w // 2 ** (S - 1)
         for n in reversed(range(1, S + 1)):
@@ -260,17 +263,17 @@ class UNet(NIPModel):
                                            2 * c, c, c, 0, d2.act, d2.act_alpha, s)
                 y2, fused = cat, True
             else:
-                dec2, y2, fused = dcur, acts['dc02'], False
+                dec2, y2, fused = dcur, acts['dc02'], done
             da1 = ws.get('d_ec%d1' % n, a1.shape)
-            c2.bprop(a1, y2, dec2, da1, d2, dy_addr=(c, 0, MODE_PLAIN), act_bias_done=fused)
+            c2.bprop(a1, y2, dec2, da1, d2, dy_addr=(c, 0, MODE_PLAIN), act_bias_done=fused, fuse_prev=c1.fuse_info(a1))
             src = acts['ep%d' % (n - 1)]
             if n > 1:
                 dsrc = ws.get('d_ep%d' % (n - 1), src.shape)
-                c1.bprop(src, a1, da1, dsrc, d1)
+                c1.bprop(src, a1, da1, dsrc, d1, act_bias_done=c2.fused_prev)
                 dcur = dsrc
                 ch, cw = ch * 2, cw * 2
             else:
-                c1.bprop(src, a1, da1, None, d1, need_dx=False)
+                c1.bprop(src, a1, da1, None, d1, need_dx=False, act_bias_done=c2.fused_prev)
         return None
 
 

@@ -186,8 +186,13 @@ class Conv2D:
     def bias_grad_ptr(self, need_dw=True):
         return ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
 
+    def fuse_info(self, y, pitch=None, coff=0, need_dw=True):
+        """What the layer ABOVE needs to fold this layer's activation backward + bias gradient into its dgrad epilogue
+        (`bprop(fuse_prev=...)`): forward output y (plain NHWC, channel pitch / offset), activation, bias-gradient pointer."""
+        return (y, self.cout if pitch is None else int(pitch), int(coff), self.act, self.alpha, self.bias_grad_ptr(need_dw), self.bias_mod)
+
     def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
-              dx_accumulate=False, need_dw=True, dpad=None, act_bias_done=False):
+              dx_accumulate=False, need_dw=True, dpad=None, act_bias_done=False, fuse_prev=None):
         """Backward of fprop(x -> y) described by the forward descriptor `d`.
 
         For mirrored padding (REFLECT / SYMMETRIC + VALID conv) the input gradient is computed on the padded domain into
@@ -196,7 +201,10 @@ class Conv2D:
         dy is modified in place (multiplied by the activation derivative). dW / db go to the flat gradient buffer
         (or `dweight`). dy_addr / dx_addr = (pitch, coff, mode) of the gradient buffers when they are laid out
         differently from y / x (default: same addressing as the forward tensors). act_bias_done: dy already carries the
-        activation derivative and the bias gradient has been written (ni_maxpool2_act_bwd_bias)."""
+        activation derivative and the bias gradient has been written (ni_maxpool2_act_bwd_bias, or the fused dgrad of the layer above).
+        fuse_prev = producer.fuse_info(...): when the tcgen05 path takes this dgrad, its epilogue multiplies dx by the producing layer's
+        act'(y) and accumulates that layer's bias gradient; `self.fused_prev` then tells the caller to pass act_bias_done=True below."""
+        self.fused_prev = False
         L = _lib.lib()
         st = stream()
         dyp, dyo, dym = dy_addr if dy_addr is not None else (d.out_pitch, d.out_coff, d.out_mode)
@@ -227,6 +235,13 @@ class Conv2D:
                 dd.in_pitch, dd.in_coff, dd.in_mode = dx_addr
             dd.accumulate = int(dx_accumulate)
             dd.pad_mode = PAD_ZERO
+            if fuse_prev is not None and not dx_accumulate:
+                yp, ypitch, ycoff, actp, alphap, dbp, bmodp = fuse_prev
+                if actp in (ACT_NONE, ACT_LEAKY_RELU, ACT_RELU, ACT_TANH, ACT_SIGMOID) and \
+                        L.ni_conv2d_dgrad_act_supported(ctypes.byref(dd), ypitch, ycoff):
+                    L.ni_conv2d_dgrad_act_tc(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dx), ptr(yp), ypitch, ycoff, actp, alphap, dbp, bmodp, st)
+                    self.fused_prev = True
+                    return dx
             L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(wv), ptr(dx), st)
         return dx
 
