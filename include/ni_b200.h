@@ -194,16 +194,8 @@ int ni_conv2d_small_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_small(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_small(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
 int ni_conv2d_wgrad_small(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
-int ni_tc_selftest(const float* a /*128x32*/, const float* b /*64x32*/, float* d /*128x64*/, int mn_major, ni_stream_t stream);
-/* measurement probe: TMA box streaming rate vs channel pitch / boxes in flight; returns the grid size (> 0) or an error (< 0) */
-int ni_tma_probe(const float* x, int n, int h, int w, int c, int stages, int boxes_per_cta, long long* cycles_out, int max_grid, ni_stream_t stream);
-/* measurement probes (tools/): tcgen05.mma issue / execution rate; 1-D bulk-copy (weight stream) ingest rate per SM */
-int ni_mma_probe(int n, int ts, int rounds, int nacc, long long* cycles_out, int grid, ni_stream_t stream);
-int ni_bulk_probe(const void* src, long long src_bytes, int bytes, int depth, int copies, int same, int warps, long long* cycles_out, int grid,
-                  ni_stream_t stream);
-/* debug: per-role clock64 spans of the persistent tcgen05 gemm [0,32) and of the wgrad kernel [32,64) (zeros unless built with -DNI_TC_PROFILE) */
-int ni_tc_prof_read(long long* out64, int reset);
-void ni_conv2d_set_force_simt(int on);   /* -1 environment (NI_CONV_FORCE_SIMT), 0 dispatch normally, 1 always SIMT */
+/* test hook: 1 = run every convolution on the FP32 SIMT kernels (tests compare the tcgen05 path against them on the device), 0 = dispatch normally */
+void ni_conv2d_set_force_simt(int on);
 /* The SIMT implementations, callable directly (tests compare the two paths on the device). */
 int ni_conv2d_fprop_simt(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_simt(const ni_conv_desc* d, const float* dy, const float* w_t, float* dx, ni_stream_t stream);

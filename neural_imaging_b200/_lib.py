@@ -75,6 +75,9 @@ class _Lib:
                               '__graft_entry__.build() — there is no CPU/PyTorch fallback'.format(LIB_PATH))
         self._dll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
+        dev_header = os.path.join(os.path.dirname(HEADER), 'ni_b200_dev.h')
+        if os.environ.get('NI_B200_LIB') and os.path.isfile(dev_header):       # development variant: probes / profiler of csrc/dev
+            self.protos.update({k: v for k, v in parse_header(dev_header).items() if hasattr(self._dll, k)})
         for name, (ret, argtypes, _) in self.protos.items():
             fn = getattr(self._dll, name)   # AttributeError if the header declares a symbol the library lacks
             fn.restype = ret

@@ -10,12 +10,17 @@ TAG = os.environ.get('NI_BUILD_TAG', '')          # development variants (tools/
 OBJ = os.path.join(HERE, 'build' + ('_' + TAG if TAG else ''))
 LIB = os.path.join(HERE, 'libni_b200' + ('_' + TAG if TAG else '') + '.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+# a tagged build is a DEVELOPMENT variant: -DNI_DEV compiles in the environment switches, the generation-2 tcgen05 kernels and the
+# hardware probes of csrc/dev/ (declared in include/ni_b200_dev.h). The shipping libni_b200.so has none of them.
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
-         '--expt-relaxed-constexpr'] + os.environ.get('NI_NVCC_EXTRA', '').split()      # e.g. -DNI_TC_PROFILE (tools/gpu_tcprof.sh)
+         '--expt-relaxed-constexpr', '-I', CSRC] + (['-DNI_DEV'] if TAG else []) + os.environ.get('NI_NVCC_EXTRA', '').split()      # e.g. -DNI_TC_PROFILE
 
 
 def _sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+    src = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+    if TAG:
+        src += sorted(os.path.join('dev', f) for f in os.listdir(os.path.join(CSRC, 'dev')) if f.endswith('.cu'))
+    return src
 
 
 def _stale(target, deps):
@@ -32,7 +37,7 @@ def build(force=False, verbose=False):
     objs = []
     for src in _sources():
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src[:-3] + '.o')
+        o = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append([NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o])

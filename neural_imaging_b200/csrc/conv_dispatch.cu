@@ -1,6 +1,7 @@
 // Dispatch between the tcgen05 implicit-GEMM path (dense contractions) and the FP32 SIMT path (everything else:
 // 3/4-channel layers, strided / mirrored-pad / space-to-depth addressing). Both run on the GPU; there is no CPU path.
-// NI_CONV_FORCE_SIMT=1 in the environment forces the SIMT path (used by tests to compare the two on the device).
+// ni_conv2d_set_force_simt(1) forces the SIMT path (tests compare the two on the device); development builds (-DNI_DEV) also read
+// NI_CONV_FORCE_SIMT=1 from the environment.
 #include <stdlib.h>
 
 #include "conv_desc.h"
@@ -27,8 +28,12 @@ int ni_get_scratch2(size_t bytes, float** out);
 static bool force_simt() {
     static int v = -1;
     if (v < 0) {
+#ifdef NI_DEV
         const char* e = getenv("NI_CONV_FORCE_SIMT");
         v = (e && e[0] == '1') ? 1 : 0;
+#else
+        v = 0;
+#endif
     }
     return v == 1;
 }

@@ -27,6 +27,17 @@
 #include "ni_common.cuh"
 #include "tc_common.cuh"
 
+// Tuning switches read from the environment exist in DEVELOPMENT builds only (NI_BUILD_TAG=dev -> -DNI_DEV, libni_b200_dev.so);
+// the shipping library has one fixed configuration.
+static inline const char* dev_env(const char* name) {
+#ifdef NI_DEV
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
 namespace {
 
 // w (taps, cin, cout) HWIO -> tiles for the gemm kernel: block ((nt * K/32 + kc) * taps + tap) = [hi | lo], each a
@@ -146,7 +157,7 @@ bool pick_tile(int h, int w, int pixels, int& bw, int& bh, int& bn) {
 
 int bnt_cap() {
     static int cap = 0;
-    if (!cap) { const char* e = getenv("NI_TC_BNT_MAX"); cap = e ? atoi(e) : 128; if (cap != 32 && cap != 64) cap = 128; }
+    if (!cap) { const char* e = dev_env("NI_TC_BNT_MAX"); cap = e ? atoi(e) : 128; if (cap != 32 && cap != 64) cap = 128; }
     return cap;
 }
 int pick_bnt(int n) {
@@ -212,7 +223,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     p.dbias = fa.dbias; p.dbias_mod = fa.bias_mod;
     const int ktot = taps * K;
     const int want_nacc = ktot > 2304 ? 3 : (ktot > 1024 ? 2 : 1);
-    static const bool use_v2 = getenv("NI_TC_GEMM_V2") != nullptr;
+    static const bool use_v2 = dev_env("NI_TC_GEMM_V2") != nullptr;
     const int mtiles = p.tiles_w * p.tiles_h * tiles_n;
     if (!use_v2) {
         // generation 3: persistent CTAs (one per SM), see conv_tc_v3.cuh
@@ -228,13 +239,13 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         const int budget = 226 * 1024 - 1024;
         if (p.sa * p.a_stage + tcv3::kGroupBytes > budget) p.sa = 1;
         const int room = (budget - p.sa * p.a_stage) / tcv3::kGroupBytes;       // 32 KB groups that fit beside the A stages
-        static const int resident_on = getenv("NI_TC_B_RESIDENT") ? atoi(getenv("NI_TC_B_RESIDENT")) : 1;
+        static const int resident_on = dev_env("NI_TC_B_RESIDENT") ? atoi(dev_env("NI_TC_B_RESIDENT")) : 1;
         q.b_resident = (resident_on && N == bnt && ngroups <= room && ngroups <= tcv3::kMaxGroups && q.total_tiles >= 2 * grid_ctas) ? 1 : 0;
         if (q.b_resident) { q.sb = ngroups; q.log_sb = 0; }
         else if (room >= 4) { q.sb = 4; q.log_sb = 2; }
         else if (room >= 2) { q.sb = 2; q.log_sb = 1; }
         else { q.sb = room >= 1 ? 1 : 0; q.log_sb = 0; }
-        static const int defer_env = getenv("NI_TC_DEFER") ? atoi(getenv("NI_TC_DEFER")) : -1;
+        static const int defer_env = dev_env("NI_TC_DEFER") ? atoi(dev_env("NI_TC_DEFER")) : -1;
         q.defer_st = defer_env >= 0 ? (defer_env >> (bnt == 128 ? 2 : (bnt == 64 ? 1 : 0))) & 1 : 1;      // bit 0: N = 32, bit 1: N = 64, bit 2: N = 128
         const int bstage = tcv3::kGroupBytes;
         // TMEM budget (tcv3::Cfg): N = 128 -> one set of (nacc + 1) accumulators + 2 A slots; N <= 64 -> fixed 4 accumulators per set
@@ -250,7 +261,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     {                                                                                                          \
         rc = set_dyn_smem(tcv3::conv_tc3_gemm_kernel<B, SL>, smem);                                            \
         if (rc) return rc;                                                                                     \
-        if (getenv("NI_TC_DEBUG")) {                                                                           \
+        if (dev_env("NI_TC_DEBUG")) {                                                                           \
             cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, tcv3::conv_tc3_gemm_kernel<B, SL>);              \
             fprintf(stderr, "tc gemm3<%d,%d>: grid %d, tiles %d, iters %d, smem %zu, regs %d, local %zu, sb %d%s, sa %d, nacc %d\n", B, SL, grid,  \
                     q.total_tiles, taps * (K / 32), smem, fa.numRegs, fa.localSizeBytes, q.sb, q.b_resident ? " (resident)" : "", p.sa, p.nacc);  \
@@ -263,6 +274,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         NI_COUNT_LAUNCH(2);
         return NI_OK;
     }
+#ifdef NI_DEV
     {
         // generation 2 (one CTA per tile): accumulator rotation bounded by the 512 TMEM columns
         int nacc = want_nacc;
@@ -283,10 +295,15 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     NI_LAUNCH_CHECK();
     NI_COUNT_LAUNCH(2);
     return NI_OK;
+#else
+    ni_set_error("conv_tc: the generation-2 gemm exists in development builds only");
+    return NI_ERR_UNSUPPORTED;
+#endif
 }
 
 }  // namespace
 
+#ifdef NI_DEV
 // In-kernel timing counters of the persistent gemm [0,32) and of wgrad [32,64) (all zero unless the library was built with -DNI_TC_PROFILE)
 extern "C" int ni_tc_prof_read(long long* out64, int reset) {
     NI_REQUIRE(out64, "ni_tc_prof_read: null pointer");
@@ -299,6 +316,8 @@ extern "C" int ni_tc_prof_read(long long* out64, int reset) {
 #endif
     return NI_OK;
 }
+
+#endif
 
 // Second internal scratch (transposed / flipped weights of the SIMT and direct dgrad paths), same grow-on-demand policy.
 int ni_get_scratch2(size_t bytes, float** out) {
@@ -332,12 +351,12 @@ extern "C" int ni_conv2d_tc_supported(const ni_conv_desc* d, int op) {
     }
     if (op == 1) {
         // dy is the TMA source: depth_to_space addressing only for 1x1 filters (the transposed convolutions) on whole 32-channel chunks
-        if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && getenv("NI_TC_NO_BLOCK2") == nullptr)) return 0;
+        if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && dev_env("NI_TC_NO_BLOCK2") == nullptr)) return 0;
         if (d->in_mode == NI_MODE_BLOCK2 && ((d->cin / 4) % 32)) return 0;
         return gemm_geometry(d->h, d->w, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
     if (d->in_mode != NI_MODE_PLAIN) return 0;
-    if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && getenv("NI_TC_NO_BLOCK2") == nullptr)) return 0;
+    if (d->out_mode != NI_MODE_PLAIN && !(d->kh == 1 && d->kw == 1 && ((d->cout / 4) % 32) == 0 && dev_env("NI_TC_NO_BLOCK2") == nullptr)) return 0;
     if (!pick_tile(d->oh, d->ow, 32, bw, bh, bn)) return 0;
     return (d->n % bn) == 0 ? 1 : 0;
 }
@@ -361,7 +380,7 @@ extern "C" int ni_conv2d_dgrad_act_supported(const ni_conv_desc* d, int y_pitch,
     if (!ni_conv2d_tc_supported(d, 1)) return 0;
     if (d->in_mode != NI_MODE_PLAIN) return 0;                          // dx (and y_prev) plain NHWC
     if ((y_pitch & 3) || (y_coff & 3)) return 0;
-    static const bool use_v2 = getenv("NI_TC_GEMM_V2") != nullptr;      // the fused epilogue exists in the generation-3 kernel only
+    static const bool use_v2 = dev_env("NI_TC_GEMM_V2") != nullptr;      // the fused epilogue exists in the generation-3 kernel only
     return use_v2 ? 0 : 1;
 }
 extern "C" int ni_conv2d_dgrad_act_tc(const ni_conv_desc* d, const float* dy, const float* w, float* dx, const float* y_prev, int y_pitch,
@@ -406,7 +425,7 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     // (16 KB of A + BNT x 128 B of B per 32 pixels ~ 3.5 TB/s over 148 SMs), measured 1.4 - 1.8 us for every tile width. The old rule (always
     // ~4 waves) made the 1x1 transposed-conv layers reduction-bound: 592 CTAs x 16 K atomics for 28 iterations of work each.
     // Chains are capped at 2048 steps (65 K pixels) to bound the truncation bias of the in-TMEM accumulation.
-    static const bool wgrad_v2 = getenv("NI_TC_WGRAD_V2") != nullptr;      // generation 2 kernel (one producer thread, two CTAs per SM for N <= 64)
+    static const bool wgrad_v2 = dev_env("NI_TC_WGRAD_V2") != nullptr;      // generation 2 kernel (one producer thread, two CTAs per SM for N <= 64)
     const int tiles = mtiles * ntiles, sms = ni_num_sms() * ((bnt == 128 || !wgrad_v2) ? 1 : 2);   // resident CTAs
     const double t_iter = wgrad_v2 ? 1.5 : 0.7;                             // us per 32-pixel step of one CTA
     const int min_splits = (p.steps_total + 2047) / 2048;
@@ -425,7 +444,7 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     p.steps_per_split = (p.steps_total + splits - 1) / splits;
     splits = (p.steps_total + p.steps_per_split - 1) / p.steps_per_split;
     dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
-    if (getenv("NI_TC_DEBUG"))
+    if (dev_env("NI_TC_DEBUG"))
         fprintf(stderr, "tc wgrad<%d>%s: grid (%d, %d, %d), steps %d total, %d per split, atoms %d\n", bnt, wgrad_v2 ? " v2" : "", mtiles, ntiles, splits,
                 p.steps_total, p.steps_per_split, p.atoms);
     if (!wgrad_v2) {
@@ -439,9 +458,9 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     }
         // producer warps per tile width (measured, tools/profile_conv.py): the copy engine's row rate (one 128-byte box row per ~4.5
         // cycles) bounds a step, more issuing warps than needed to reach it only add polling
-        static const int np_env = getenv("NI_TC_WG_NP") ? atoi(getenv("NI_TC_WG_NP")) : 0;
+        static const int np_env = dev_env("NI_TC_WG_NP") ? atoi(dev_env("NI_TC_WG_NP")) : 0;
         const bool many = np_env > 4;        // measured: 4 producer warps are enough for every tile width (more only add polling)
-        static const int defer_env = getenv("NI_TC_WG_DEFER") ? atoi(getenv("NI_TC_WG_DEFER")) : -1;
+        static const int defer_env = dev_env("NI_TC_WG_DEFER") ? atoi(dev_env("NI_TC_WG_DEFER")) : -1;
         p.defer_st = defer_env > 0 ? 1 : 0;   // measured: deferring the converters' tcgen05.st completion delays the MMA warp more than it hides (-10 .. -25 %)
         if (bnt == 128) { if (many) NI_TC_WGRAD3(128, 8) else NI_TC_WGRAD3(128, 4) }
         else if (bnt == 64) { if (many) NI_TC_WGRAD3(64, 6) else NI_TC_WGRAD3(64, 4) }
@@ -451,6 +470,7 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
         NI_COUNT_LAUNCH(1);
         return NI_OK;
     }
+#ifdef NI_DEV
 #define NI_TC_WGRAD(B)                                                                                         \
     {                                                                                                          \
         const size_t smem = (size_t)tcv2::WgCfg<B>::STAGES * (tcv2::kAraw + 3 * B * 128) + 1024;                      \
@@ -463,4 +483,8 @@ extern "C" int ni_conv2d_wgrad_tc(const ni_conv_desc* d, const float* x, const f
     NI_LAUNCH_CHECK();
     NI_COUNT_LAUNCH(1);
     return NI_OK;
+#else
+    ni_set_error("conv_tc: the generation-2 wgrad exists in development builds only");
+    return NI_ERR_UNSUPPORTED;
+#endif
 }
