@@ -43,6 +43,9 @@ int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h, int w, co
                  int mode, ni_stream_t stream);
 int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, int h, int w, const float* q_luma,
                  const float* q_chroma, int mode, ni_stream_t stream);
+/* gradient w.r.t. the two 8x8 quantisation tables of DifferentiableJPEG(trainable=True) (models/jpeg.py:58-62): dq = [luma 64 | chroma 64] */
+int ni_djpeg_bwd_tables(const float* x, const float* dy, float* dq, int n, int h, int w, const float* q_luma, const float* q_chroma,
+                        int mode, ni_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ training-data feed
  * Replaces the host-side batch assembly of Dataset.next_training_batch (helpers/dataset.py:89-131): crop, astype(float) / 65535
@@ -227,6 +230,8 @@ int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* l
 int ni_cconv5_fwd(const float* x, const float* nf, float* y, int n, int h, int w, ni_stream_t stream);
 int ni_cconv5_bwd_data(const float* dy, const float* nf, float* dx, int n, int h, int w, int accumulate, ni_stream_t stream);
 int ni_cconv5_bwd_filter(const float* x, const float* dy, float* dnf, int n, int h, int w, ni_stream_t stream);
+/* tf.keras.layers.Dropout(rate) in training mode (models/forensics.py:88; FAN.process(x, training=True)): inverted dropout, own generator */
+int ni_dropout(const float* x, float* y, long long n, float rate, unsigned long long seed, ni_stream_t stream);
 /* validate_fan's decisions and confusion matrix (training/validation.py:163-203; workflows/manipulation_classification.py:178-180):
    pred[i] = argmax probs[i, :], conf[labels[i] * c + pred[i]] += 1 (int32, caller zeroes); pred or conf may be null */
 int ni_confusion_accumulate(const float* probs, const int* labels, int* conf, int* pred, int m, int c, ni_stream_t stream);
@@ -255,6 +260,13 @@ int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* 
                                int ncodes, double nu, double gamma, ni_stream_t stream);
 int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
                                const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, ni_stream_t stream);
+/* the same with the latent quantiser selectable (DCN's `rounding`, models/compression.py:66 -> models/layers.py:118-170):
+ * rounding 0 'soft-codebook', 1 'sin', 2 'soft' (round forward, sine gradient), 3 'identity'; the entropy term is unchanged */
+int ni_latent_quantise_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc, long long n,
+                           int ncodes, double nu, double gamma, int rounding, ni_stream_t stream);
+int ni_latent_quantise_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
+                           const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, int rounding,
+                           ni_stream_t stream);
 /* Quantization layer, scalar modes (models/layers.py:118-136): 0 'round', 1 'sin', 2 'soft', 3 'harmonic', 4 'identity' (forward values) */
 int ni_quantize_scalar(const float* x, float* y, long long n, int mode, int taylor_terms, ni_stream_t stream);
 /* entropy estimate from the accumulated soft histogram (helpers/tf_helpers.py:326-331) and its gradient w.r.t. the histogram */

@@ -386,6 +386,107 @@ djpeg_bwd3_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- table gradient (trainable Q)
+// DifferentiableJPEG(trainable=True) (models/jpeg.py:58-62): the two 8x8 quantisation tables are model weights. With Z = D / Q,
+// X = q(Z) * Q:  dX/dQ = q(Z) - Z q'(Z)  ('soft': forward value round(Z), gradient 1 - cos 2 pi Z), so
+//   dL/dQ[k][l] = sum over the blocks that use the table of G[k][l] * (q(Z) - Z q'(Z)),   G = F g_xi F^T = dL/dX.
+// Same tile / thread mapping as the backward kernel (warp = channel, lane = block); the per-block terms are summed over the warp's
+// 32 blocks with a butterfly (lane l ends with entries l and 32 + l) and added to the 2 x 64 output with atomics. Not a hot path.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+djpeg_dq_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dq, int H, int W, int nblk,
+                const __grid_constant__ DjpegTables tab) {
+    extern __shared__ __align__(16) float smem[];
+    float* tx = smem;
+    float* tg = smem + kTileFloats;
+    long long* base = reinterpret_cast<long long*>(smem + 2 * kTileFloats);
+    const int nbw = W / 8, nbh = H / 8, rowf = W * 3;
+    const int g0 = blockIdx.x * kTileBlocks;
+    const int c = threadIdx.x >> 5, blk = threadIdx.x & 31;
+    if (c == 0) {
+        const int g = g0 + blk;
+        base[blk] = g < nblk ? block_base_offset(g, nbw, nbh, W) : -1;
+    }
+    for (int i = threadIdx.x; i < 2 * kTileFloats; i += kThreads) smem[i] = 0.f;     // blocks past the end contribute exactly zero
+    __syncthreads();
+    tile_load(tx, x, base, rowf);
+    tile_load(tg, dy, base, rowf);
+    cp_async_wait_all();
+    __syncthreads();
+
+    float* bp = tx + blk * kBlockFloats;
+    float v[8][8];
+    float coef[8][8];
+    load_channel(bp, c, v);
+    __syncthreads();
+    dct2d_fwd(v);
+    const int cc = c == 0 ? 0 : 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const float z = v[k][l] * tab.rq[cc][k * 8 + l];
+            const float qf = quant_fwd<MODE>(z);
+            coef[k][l] = qf - z * quant_grad_fast<MODE>(z);
+            v[k][l] = qf * tab.q[cc][k * 8 + l];
+        }
+    dct2d_inv(v);
+    store_plane(bp + c * 64, v);
+    __syncthreads();
+    // clip mask from the recomputed ypre, g_xi = C_I[:,1:]^T (mask * dy) / 255 (pixel pass 1 of the backward kernel)
+    for (int u = threadIdx.x; u < kTileBlocks * kUnitsPerBlock; u += kThreads) {
+        const int b = u >> 4, r = u & 15;
+        float4* p = reinterpret_cast<float4*>(tx + b * kBlockFloats + r * 4);
+        const float4* pg = reinterpret_cast<const float4*>(tg + b * kBlockFloats + (r >> 1) * 24 + (r & 1) * 12);
+        const float4 Y = p[0], B = p[16], R = p[32];
+        const float4 ga = pg[0], gb4 = pg[1], gc = pg[2];
+        const float yy[4] = {Y.x, Y.y, Y.z, Y.w}, cb[4] = {B.x, B.y, B.z, B.w}, cr[4] = {R.x, R.y, R.z, R.w};
+        const float g[12] = {ga.x, ga.y, ga.z, ga.w, gb4.x, gb4.y, gb4.z, gb4.w, gc.x, gc.y, gc.z, gc.w};
+        constexpr float s = 1.f / 255.f;
+        constexpr float kr = (127.f - 1.402f) * s, kg = (127.f + 1.058272f) * s, kb = (127.f - 1.772f) * s;
+        float oy[4], ob[4], orr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float pr = fmaf(cr[j], 1.402f * s, fmaf(yy[j], s, kr));
+            const float pgn = fmaf(cr[j], -0.714136f * s, fmaf(cb[j], -0.344136f * s, fmaf(yy[j], s, kg)));
+            const float pb = fmaf(cb[j], 1.772f * s, fmaf(yy[j], s, kb));
+            const float gr = (pr >= 0.f && pr <= 1.f) ? g[3 * j] * s : 0.f;
+            const float ggn = (pgn >= 0.f && pgn <= 1.f) ? g[3 * j + 1] * s : 0.f;
+            const float gbl = (pb >= 0.f && pb <= 1.f) ? g[3 * j + 2] * s : 0.f;
+            oy[j] = gr + ggn + gbl;
+            ob[j] = fmaf(-0.344136f, ggn, 1.772f * gbl);
+            orr[j] = fmaf(1.402f, gr, -0.714136f * ggn);
+        }
+        p[0] = make_float4(oy[0], oy[1], oy[2], oy[3]);
+        p[16] = make_float4(ob[0], ob[1], ob[2], ob[3]);
+        p[32] = make_float4(orr[0], orr[1], orr[2], orr[3]);
+    }
+    __syncthreads();
+    load_plane(bp + c * 64, v);
+    dct2d_fwd(v);                           // G = dL/dX
+    const bool live = base[blk] >= 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int e = half * 32 + j;
+            r[j] = live ? v[e >> 3][e & 7] * coef[e >> 3][e & 7] : 0.f;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (blk & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+                const float send = upper ? r[j] : r[j + off];
+                const float keep = upper ? r[j + off] : r[j];
+                r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        atomicAdd(dq + cc * 64 + half * 32 + blk, r[0]);
+    }
+}
+
 int fill_tables(DjpegTables& t, const float* q_luma, const float* q_chroma) {
     for (int i = 0; i < 64; ++i) {
         if (!(q_luma[i] > 0.f) || !(q_chroma[i] > 0.f)) return -1;
@@ -456,6 +557,34 @@ extern "C" int ni_djpeg_bwd(const float* x, const float* dy, float* dx, int n, i
     }
     if (mode == 0) NI_BWD(0) else if (mode == 1) NI_BWD(1) else NI_BWD(2)
 #undef NI_BWD
+    NI_LAUNCH_CHECK();
+    NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
+// dq: 2 x 64 floats (luma table, chroma table), overwritten. Gradient of the loss w.r.t. the quantisation tables of a trainable
+// DifferentiableJPEG (models/jpeg.py:58-62) given dy = dL/dy; everything is recomputed from x like ni_djpeg_bwd.
+extern "C" int ni_djpeg_bwd_tables(const float* x, const float* dy, float* dq, int n, int h, int w, const float* q_luma,
+                                   const float* q_chroma, int mode, cudaStream_t stream) {
+    NI_REQUIRE(x && dy && dq && q_luma && q_chroma, "ni_djpeg_bwd_tables: null pointer");
+    NI_REQUIRE(n >= 0 && h > 0 && w > 0 && h % 8 == 0 && w % 8 == 0,
+               "ni_djpeg_bwd_tables: H and W must be positive multiples of 8 (got %d x %d)", h, w);
+    NI_REQUIRE(mode >= 0 && mode <= 2, "ni_djpeg_bwd_tables: mode must be 0 (soft), 1 (sin) or 2 (harmonic), got %d", mode);
+    NI_CUDA(cudaMemsetAsync(dq, 0, sizeof(float) * 128, stream));
+    if (n == 0) return NI_OK;
+    DjpegTables tab;
+    NI_REQUIRE(fill_tables(tab, q_luma, q_chroma) == 0, "ni_djpeg_bwd_tables: quantisation tables must be positive");
+    const long long nblk = (long long)n * (h / 8) * (w / 8);
+    NI_REQUIRE(nblk < (1ll << 31) - 64 * kTileBlocks, "ni_djpeg_bwd_tables: tensor too large (%lld blocks)", nblk);
+    const int grid = ni_cdiv(nblk, kTileBlocks);
+#define NI_DQ(MODE)                                                                                  \
+    {                                                                                                  \
+        int rc = set_smem(djpeg_dq_kernel<MODE>, kBwd3Smem);                                           \
+        if (rc) return rc;                                                                             \
+        djpeg_dq_kernel<MODE><<<grid, kThreads, kBwd3Smem, stream>>>(x, dy, dq, h, w, (int)nblk, tab); \
+    }
+    if (mode == 0) NI_DQ(0) else if (mode == 1) NI_DQ(1) else NI_DQ(2)
+#undef NI_DQ
     NI_LAUNCH_CHECK();
     NI_COUNT_LAUNCH(1);
     return NI_OK;

@@ -20,7 +20,21 @@ struct LatentParams {
     long long n;
     int ncodes;
     double nu, gamma;
+    int rounding;      // 0 'soft-codebook', 1 'sin', 2 'soft' (round forward, sine gradient), 3 'identity' (models/layers.py:118-170)
 };
+
+// scalar rounding modes of the Quantization layer on the (float32) scaled latent; period-1 reduction keeps the SFU argument small
+__device__ __forceinline__ float scalar_round(float v, int mode) {
+    if (mode == 3) return v;
+    if (mode == 2) return rintf(v);
+    const float f = v - rintf(v);
+    return v - sinf(6.2831855f * f) * (1.f / 6.2831855f);
+}
+__device__ __forceinline__ double scalar_round_grad(float v, int mode) {
+    if (mode == 3) return 1.0;
+    const float f = v - rintf(v);
+    return 1.0 - (double)cosf(6.2831855f * f);         // d/dv [v - sin(2 pi v) / 2 pi], also the straight-through gradient of 'soft'
+}
 
 __device__ __forceinline__ double kernel_weight(double diff, double nu, double gamma, double& dlog) {
     // returns w and d(ln w)/dv (diff = v - c)
@@ -46,18 +60,23 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < p.n; i += (long long)gridDim.x * kT) {
         const float vf = x[i] * sc;                  // float32 multiply, as the reference (latent * scaling_factor)
         const double v = (double)vf;
-        double S = 0.0, soft = 0.0, best = -1.0;
-        int arg = 0;
-        for (int k = 0; k < p.ncodes; ++k) {
-            double dl;
-            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
-            S += w;
-            soft += w * (double)cb[k];
-            if (w > best) { best = w; arg = k; }
+        float q;
+        if (p.rounding == 0) {
+            double S = 0.0, soft = 0.0, best = -1.0;
+            int arg = 0;
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
+                S += w;
+                soft += w * (double)cb[k];
+                if (w > best) { best = w; arg = k; }
+            }
+            soft /= S;
+            const float softf = (float)soft, hard = cb[arg];
+            q = (hard - softf) + softf;
+        } else {
+            q = scalar_round(vf, p.rounding);
         }
-        soft /= S;
-        const float softf = (float)soft, hard = cb[arg];
-        const float q = (hard - softf) + softf;
         out[i] = q;
         if (hist_acc) {
             // the reference estimates the entropy of the QUANTISED latent (models/layers.py:200-201): weights at q
@@ -96,18 +115,22 @@ latent_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < p.n; i += (long long)gridDim.x * kT) {
         const float xf = x[i];
         const double v = (double)(xf * sc);
-        double S = 0.0, A = 0.0;            // S = sum (w+eps), A = sum w a   (a = dlnw/dv)
-        for (int k = 0; k < p.ncodes; ++k) {
-            double dl;
-            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
-            S += w + 1e-72;
-            A += w * dl;
-        }
         double dsoft = 0.0, dent = 0.0;
-        for (int k = 0; k < p.ncodes; ++k) {
-            double dl;
-            const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
-            dsoft += (double)cb[k] * ((w * dl) / S - (w + 1e-72) * A / (S * S));
+        if (p.rounding == 0) {
+            double S = 0.0, A = 0.0;            // S = sum (w+eps), A = sum w a   (a = dlnw/dv)
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
+                S += w + 1e-72;
+                A += w * dl;
+            }
+            for (int k = 0; k < p.ncodes; ++k) {
+                double dl;
+                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
+                dsoft += (double)cb[k] * ((w * dl) / S - (w + 1e-72) * A / (S * S));
+            }
+        } else {
+            dsoft = scalar_round_grad(xf * sc, p.rounding);      // dq/dv of the scalar rounding modes
         }
         if (gh) {
             const double vq = (double)q[i];
@@ -156,11 +179,14 @@ __global__ void lrelu_bwd_kernel(const float* __restrict__ x, const float* __res
 
 // out: quantised latent (n floats). hist_acc: 32 (ncodes) doubles, zeroed by the caller, receives sum_i wn_ik (may be NULL).
 // scale: device pointer to the trainable scaling factor (NULL = 1). codebook: ncodes floats on the device.
-extern "C" int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc,
-                                          long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
-    NI_REQUIRE(x && codebook && out && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes, "ni_latent_softcodebook_fwd: invalid arguments");
+// rounding: 0 'soft-codebook', 1 'sin', 2 'soft', 3 'identity' — the modes models/compression.py:66 accepts for the latent quantiser; the
+// entropy estimate (soft histogram of the QUANTISED latent over the code book) is the same for all of them.
+extern "C" int ni_latent_quantise_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc,
+                                      long long n, int ncodes, double nu, double gamma, int rounding, cudaStream_t st) {
+    NI_REQUIRE(x && codebook && out && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes && rounding >= 0 && rounding <= 3,
+               "ni_latent_quantise_fwd: invalid arguments");
     if (n == 0) return NI_OK;
-    LatentParams p{n, ncodes, nu, gamma};
+    LatentParams p{n, ncodes, nu, gamma, rounding};
     int grid = ni_cdiv(n, kT * 4);
     if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
     latent_fwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, out, hist_acc, p);
@@ -170,12 +196,17 @@ extern "C" int ni_latent_softcodebook_fwd(const float* x, const float* scale, co
 
 // q: the quantised latent written by the forward (needed when gh != NULL). g_out: gradient w.r.t. the quantised latent (NULL = 0). gh: ncodes doubles = d(loss)/d(hist_k) / n (NULL = no entropy term).
 // dscale_acc: one double, zeroed by the caller, receives d(loss)/d(scale) (may be NULL).
-extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
-                                          const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
-    NI_REQUIRE(x && codebook && dx && (q || !gh) && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes,
-               "ni_latent_softcodebook_bwd: invalid arguments");
+extern "C" int ni_latent_softcodebook_fwd(const float* x, const float* scale, const float* codebook, float* out, double* hist_acc,
+                                          long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
+    return ni_latent_quantise_fwd(x, scale, codebook, out, hist_acc, n, ncodes, nu, gamma, 0, st);
+}
+extern "C" int ni_latent_quantise_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
+                                      const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma,
+                                      int rounding, cudaStream_t st) {
+    NI_REQUIRE(x && codebook && dx && (q || !gh) && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes && rounding >= 0 && rounding <= 3,
+               "ni_latent_quantise_bwd: invalid arguments");
     if (n == 0) return NI_OK;
-    LatentParams p{n, ncodes, nu, gamma};
+    LatentParams p{n, ncodes, nu, gamma, rounding};
     int grid = ni_cdiv(n, kT * 4);
     if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
     latent_bwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, q, g_out, gh, dx, dscale_acc, p);
@@ -183,6 +214,10 @@ extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, co
     return NI_OK;
 }
 
+extern "C" int ni_latent_softcodebook_bwd(const float* x, const float* scale, const float* codebook, const float* q, const float* g_out,
+                                          const double* gh, float* dx, double* dscale_acc, long long n, int ncodes, double nu, double gamma, cudaStream_t st) {
+    return ni_latent_quantise_bwd(x, scale, codebook, q, g_out, gh, dx, dscale_acc, n, ncodes, nu, gamma, 0, st);
+}
 extern "C" int ni_leaky_relu_fwd(const float* x, float* y, long long n, float alpha, cudaStream_t st) {
     NI_REQUIRE(x && y && n >= 0, "ni_leaky_relu_fwd: invalid arguments");
     if (n == 0) return NI_OK;

@@ -651,6 +651,27 @@ extern "C" int ni_softmax_ce(const float* logits, const int* labels, float* prob
     return NI_OK;
 }
 
+// Keras Dropout(rate) in training mode (models/forensics.py:88: after each hidden dense layer when the model is CALLED with
+// training=True; the reference's training steps call it without, so the layer is inactive there): y = x * keep / (1 - rate), keep ~
+// Bernoulli(1 - rate) from a counter-based generator (splitmix64 of seed and element index; TensorFlow's stream cannot be reproduced).
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float rate, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.f / 16777216.f);        // uniform [0, 1)
+    y[i] = u >= rate ? x[i] / (1.f - rate) : 0.f;
+}
+extern "C" int ni_dropout(const float* x, float* y, long long n, float rate, unsigned long long seed, cudaStream_t st) {
+    NI_REQUIRE(x && y && n >= 0 && rate >= 0.f && rate < 1.f, "ni_dropout: invalid arguments");
+    if (n == 0) return NI_OK;
+    dropout_kernel<<<ni_cdiv(n, kT), kT, 0, st>>>(x, y, n, rate, seed);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
 // Decisions + confusion matrix of a validation pass on the device (reference training/validation.py:163-203 builds it on the host with
 // an n_classes^2 Python loop per batch of 10): pred[i] = argmax_k probs[i, k] (first maximum, like numpy.argmax), conf[label, pred] += 1.
 __global__ void confusion_kernel(const float* __restrict__ probs, const int* __restrict__ labels, int* __restrict__ conf,

@@ -44,8 +44,8 @@ class DCN(TFModel):
         })
         self._h.update(latent_bpf=latent_bpf, train_codebook=train_codebook, entropy_weight=entropy_weight,
                        scale_latent=scale_latent, use_batchnorm=use_batchnorm, loss_metric=loss_metric, rounding=rounding)
-        if self._h.rounding != 'soft-codebook':
-            raise NotImplementedError("only rounding='soft-codebook' (the toolbox default) is implemented on the B200 path")
+        # latent quantiser of DiscreteLatent(rounding) (models/layers.py:118-170); the entropy estimate is the same for every mode
+        self._rounding = {'soft-codebook': 0, 'sin': 1, 'soft': 2, 'identity': 3}[self._h.rounding]
         if self._h.train_codebook:
             raise NotImplementedError('train_codebook=True ("not tested" in the reference, models/compression.py:57) is not implemented')
         self.patch_size = patch_size
@@ -191,8 +191,8 @@ class DCN(TFModel):
         q = self._ws.get('q', z.shape)
         self._hist.zero_()
         scale = ptr(self._scale.value) if self._scale is not None else None
-        L.ni_latent_softcodebook_fwd(ptr(z), scale, ptr(self._codebook), ptr(q), ptr(self._hist), z.numel(), self._codebook.numel(),
-                                     _NU, _GAMMA, s)
+        L.ni_latent_quantise_fwd(ptr(z), scale, ptr(self._codebook), ptr(q), ptr(self._hist), z.numel(), self._codebook.numel(),
+                                 _NU, _GAMMA, self._rounding, s)
         n_total = z.numel()
         if self._world > 1:
             torch.distributed.all_reduce(self._hist)
@@ -213,9 +213,9 @@ class DCN(TFModel):
         want_ds = need_dw and self._scale is not None and self._scale.trainable
         if want_ds:
             self._dscale.zero_()
-        L.ni_latent_softcodebook_bwd(ptr(z), ptr(self._scale.value) if self._scale is not None else None, ptr(self._codebook), ptr(q),
-                                     ptr(dq), gh, ptr(dz), ptr(self._dscale) if want_ds else None, z.numel(), self._codebook.numel(),
-                                     _NU, _GAMMA, s)
+        L.ni_latent_quantise_bwd(ptr(z), ptr(self._scale.value) if self._scale is not None else None, ptr(self._codebook), ptr(q),
+                                 ptr(dq), gh, ptr(dz), ptr(self._dscale) if want_ds else None, z.numel(), self._codebook.numel(),
+                                 _NU, _GAMMA, self._rounding, s)
         if want_ds:
             self._scale.grad.copy_(self._dscale[0])
         return dz

@@ -44,6 +44,7 @@ class FAN(TFModel):
             raise ValueError('Flatten (use_gap=False) needs a fixed patch_size')
 
         rng = np.random.RandomState(seed)
+        self._seed, self._dropout_calls = int(seed or 0), 0
         st = self._store = nn.ParamStore()
         act = self._h.activation
         # constrained residual filter: trainable raw kernel (5,5,3,3), normalised on every call (models/layers.py:36-53)
@@ -79,7 +80,7 @@ class FAN(TFModel):
         self.performance = {'loss': {'training': [], 'validation': []}, 'accuracy': {'validation': []}, 'confusion': []}
 
     # ------------------------------------------------------------------------------------------------ forward
-    def _forward(self, x, save=False):
+    def _forward(self, x, save=False, training=False):
         """x: (M,H,W,3) device tensor. Returns logits (M, n_classes); keeps activations when save=True."""
         L, ws, s = _lib.lib(), self._ws, stream()
         m, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
@@ -111,6 +112,13 @@ class FAN(TFModel):
             d = dl.desc(m, 1, 1)
             cur = dl.fprop(cur, ws.get('d%d' % i, (m, dl.cout)), d)
             acts['d%d' % i], descs['d%d' % i] = cur, d
+            if training and self._h.dropout > 0:       # Dropout after every hidden dense layer (models/forensics.py:88), inference: identity
+                if save:
+                    raise NotImplementedError('back-propagation through an active Dropout layer (the reference never trains with it active)')
+                dropped = ws.get('drop%d' % i, (m, dl.cout))
+                self._dropout_calls += 1
+                L.ni_dropout(ptr(cur), ptr(dropped), cur.numel(), float(self._h.dropout), (self._seed << 20) + self._dropout_calls, s)
+                cur = dropped
         d = self._out.desc(m, 1, 1)
         logits = self._out.fprop(cur, ws.get('logits', (m, self.n_classes)), d)
         descs['out'] = d
@@ -123,7 +131,7 @@ class FAN(TFModel):
         x = as_device(batch_x)
         if x.dim() == 3:
             x = x.unsqueeze(0)
-        logits = self._forward(x)
+        logits = self._forward(x, training=bool(training))
         probs = empty(logits.shape)
         _lib.lib().ni_softmax_ce(ptr(logits), None, ptr(probs), None, None, logits.shape[0], self.n_classes, 1.0, stream())
         return wrap(probs)
@@ -198,8 +206,7 @@ class FAN(TFModel):
 
     def training_step(self, batch_x, target_labels, learning_rate=None):
         """One optimisation step on (images, class numbers); returns the loss (reference models/forensics.py:116-125)."""
-        if self._h.dropout > 0:
-            raise NotImplementedError('dropout > 0 is not implemented on the B200 path')
+        # (the reference calls self._model(batch_x) WITHOUT training=True here, so Dropout layers are inactive in its training step too)
         x = as_device(batch_x)
         labels = as_device(np.asarray(target_labels), torch.int32)
         probs, loss, dlogits = self.forward_loss(x, labels)

@@ -12,7 +12,7 @@ from .. import ops
 from ..compression import jpeg_helpers
 from ..compression.jpeg_helpers import jpeg_qf_estimation, jpeg_qtable
 from ..helpers.utils import is_number
-from ..tensor import as_device, wrap
+from ..tensor import as_device, empty, wrap
 from .tfmodel import TFModel
 
 _common_codec = None
@@ -45,18 +45,52 @@ class DifferentiableJPEG(object):
         if rounding_approximation is None:
             # the reference fails inside Quantization(None, ...) (models/layers.py:99-100)
             raise ValueError('Unsupported quantization: {}'.format(rounding_approximation))
-        if trainable:
-            raise NotImplementedError('trainable quantisation tables are "under development" in the reference '
-                                      '(models/jpeg.py:58-62) and not part of the B200 path yet')
         if is_number(quality):
-            self._q_mtx_luma, self._q_mtx_chroma = jpeg_qtable(quality, 0), jpeg_qtable(quality, 1)
+            ql, qc = jpeg_qtable(quality, 0), jpeg_qtable(quality, 1)
         else:
-            self._q_mtx_luma = np.ones((8, 8), dtype=np.float32)
-            self._q_mtx_chroma = np.ones((8, 8), dtype=np.float32)
+            ql, qc = np.ones((8, 8), dtype=np.float32), np.ones((8, 8), dtype=np.float32)
+        self._store = None
+        if trainable:
+            # the tables are model weights (self.add_weight('Q_mtx_luma', [8, 8]) ..., models/jpeg.py:58-62): kept in a flat parameter
+            # store like every other model; the kernels take the tables by value, so each call reads the current 128 floats back
+            from .. import nn
+            self._store = nn.ParamStore()
+            self._pl = self._store.add('Q_mtx_luma', (8, 8), np.asarray(ql, np.float32), True)
+            self._pc = self._store.add('Q_mtx_chroma', (8, 8), np.asarray(qc, np.float32), True)
+            self._store.finalize()
+            self._dq = None
+        self._ql_host, self._qc_host = np.asarray(ql, np.float32), np.asarray(qc, np.float32)
         self.quality = quality
         self.trainable = trainable
         self.rounding_approximation = rounding_approximation
         self.rounding_approximation_steps = rounding_approximation_steps
+
+    # the 8x8 tables: host arrays for a fixed codec, the current value of the weights for a trainable one
+    @property
+    def _q_mtx_luma(self):
+        return self._pl.value.detach().cpu().numpy() if self._store is not None else self._ql_host
+
+    @_q_mtx_luma.setter
+    def _q_mtx_luma(self, v):
+        if self._store is not None:
+            self._pl.value.copy_(as_device(np.asarray(v, np.float32)))
+        else:
+            self._ql_host = np.asarray(v, np.float32)
+
+    @property
+    def _q_mtx_chroma(self):
+        return self._pc.value.detach().cpu().numpy() if self._store is not None else self._qc_host
+
+    @_q_mtx_chroma.setter
+    def _q_mtx_chroma(self, v):
+        if self._store is not None:
+            self._pc.value.copy_(as_device(np.asarray(v, np.float32)))
+        else:
+            self._qc_host = np.asarray(v, np.float32)
+
+    @property
+    def trainable_weights(self):
+        return [wrap(self._pl.value), wrap(self._pc.value)] if self._store is not None else []
 
     def __call__(self, inputs, want_coeffs=True):
         x = as_device(inputs)
@@ -74,7 +108,20 @@ class DifferentiableJPEG(object):
         return ops.djpeg_fwd(x, self._q_mtx_luma, self._q_mtx_chroma, self.rounding_approximation, out=y)
 
     def backward(self, x, dy, dx=None):
-        return ops.djpeg_bwd(x, dy, self._q_mtx_luma, self._q_mtx_chroma, self.rounding_approximation, out=dx)
+        """dx = J^T dy; for a trainable codec the table gradients land in the parameter store (self._pl.grad, self._pc.grad)."""
+        ql, qc = self._q_mtx_luma, self._q_mtx_chroma
+        if self._store is not None:
+            from ..tensor import ptr, stream
+            if self._dq is None:
+                self._dq = empty((128,))
+            n, h, w = ops._nhw3(x)
+            _, pl = ops._f32(ql)
+            _, pc = ops._f32(qc)
+            from .. import _lib
+            _lib.lib().ni_djpeg_bwd_tables(ptr(x), ptr(dy), ptr(self._dq), n, h, w, pl, pc, ops.QUANT_MODES[self.rounding_approximation], stream())
+            self._pl.grad.copy_(self._dq[:64].view(8, 8))
+            self._pc.grad.copy_(self._dq[64:].view(8, 8))
+        return ops.djpeg_bwd(x, dy, ql, qc, self.rounding_approximation, out=dx)
 
 
 class JPEG(TFModel):
@@ -102,10 +149,10 @@ class JPEG(TFModel):
 
     @property
     def parameters(self):
-        return []
+        return [] if self._model is None else self._model.trainable_weights
 
     def count_parameters(self):
-        return 0
+        return int(sum(int(np.prod(p.shape)) for p in self.parameters))
 
     def _draw_quality(self, quality):
         quality = self.quality if quality is None else quality
@@ -157,6 +204,8 @@ class JPEG(TFModel):
 
     def _quality_mode(self, quality=None):
         quality = quality or self.quality
+        if self._model is not None and self._model.trainable:
+            return 'trainable QF~{}/{}'.format(jpeg_qf_estimation(self._model._q_mtx_luma, 0), jpeg_qf_estimation(self._model._q_mtx_chroma, 1))
         if is_number(quality):
             return 'QF={}'.format(quality)
         if hasattr(quality, '__getitem__') and len(quality) == 2:

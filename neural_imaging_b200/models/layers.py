@@ -91,8 +91,8 @@ class DiscreteLatent(object):
     soft-histogram entropy (`helpers/tf_helpers.py:290-333`) of the quantised values. Returns (latent, entropy)."""
 
     def __init__(self, rounding='soft', v=50, gamma=25, latent_bpf=4, trainable_codebook=False, trainable_scale=True):
-        if rounding not in ('soft-codebook', 'round'):
-            raise NotImplementedError("DiscreteLatent on the B200 path: rounding 'soft-codebook' (the toolbox default) or 'round'")
+        if rounding not in {'round', 'sin', 'soft', 'identity', 'harmonic', 'soft-codebook'}:
+            raise ValueError('Unsupported quantization: {}'.format(rounding))
         self.trainable_scale, self.rounding, self.v, self.gamma, self.latent_bpf = trainable_scale, rounding, v, gamma, latent_bpf
         self.trainable_codebook = trainable_codebook
         self.quantization = Quantization(rounding, v, gamma, latent_bpf, trainable_codebook)
@@ -103,9 +103,16 @@ class DiscreteLatent(object):
         L, st = _lib.lib(), stream()
         cb = self.quantization._cb()
         n = x.numel()
+        fused = {'soft-codebook': 0, 'sin': 1, 'soft': 2, 'identity': 3}
         if self.rounding == 'soft-codebook':
             hist = zeros((cb.numel(),), torch.float64)
             latent = self.quantization(x, scale=self.scaling_factor, hist=hist)
+        elif self.rounding in fused:       # scaling, scalar rounding and the soft histogram of the quantised values in one kernel
+            hist = zeros((cb.numel(),), torch.float64)
+            latent = torch.empty_like(x)
+            L.ni_latent_quantise_fwd(ptr(x), ptr(self.scaling_factor) if self.scaling_factor is not None else None, ptr(cb), ptr(latent), ptr(hist),
+                                     n, cb.numel(), float(self.v), float(self.gamma), fused[self.rounding], st)
+            latent = wrap(latent)
         else:
             latent = self.quantization(x * self.scaling_factor if self.scaling_factor is not None else x)
             # the entropy estimate always uses the soft histogram of the (quantised) values

@@ -6,6 +6,8 @@ workflows/manipulation_classification.py:180,187), so results are returned as :c
 ``torch.Tensor`` subclass whose ``numpy()`` copies to the host.
 """
 import numpy as np
+import os
+
 import torch
 
 
@@ -78,3 +80,26 @@ class Workspace:
 
     def clear(self):
         self._bufs.clear()
+
+
+class _Nvtx:
+    """NVTX range per pipeline stage (nsys / ncu --nvtx): `with nvtx('fan.backward'): ...`. Host-side markers only (no device work, safe
+    inside CUDA-graph capture); switched on with NI_NVTX=1, otherwise a no-op context."""
+    enabled = os.environ.get('NI_NVTX', '0') == '1'
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _Nvtx.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx(name):
+    return _Nvtx(name)

@@ -13,7 +13,7 @@ import torch
 
 from .. import _lib, nn, ops
 from ..models import forensics, jpeg, pipelines
-from ..tensor import Workspace, as_device, empty, ptr, stream, wrap, zeros
+from ..tensor import Workspace, as_device, empty, nvtx, ptr, stream, wrap, zeros
 
 
 class ManipulationClassification(object):
@@ -98,6 +98,12 @@ class ManipulationClassification(object):
         if 'nip' in self._trainable and self.nip._store.trainable:
             self._stores.append(self.nip._store)
         if 'dcn' in self._trainable:
+            if comp == 'jpeg':
+                # a JPEG codec with trainable tables passes the parameter check of the reference (:141-142), but its loss is
+                # MeanSquaredError()(c, C, sample_weight = NaN entropy): every gradient is NaN and the reference's first
+                # training step raises RuntimeError('∇ NaNs: ...') (:281-282). Same outcome here, reported where it is decided.
+                raise RuntimeError('∇ NaNs: a trainable JPEG codec cannot be optimised through this workflow — its loss term is NaN in the '
+                                   'reference (JPEG.loss receives the NaN entropy as sample_weight)')
             self._stores.append(self.codec._store)
         self._parameters = [p for s in self._stores for p in (q.value for q in s.trainable)]
         self._grad_arena = nn.unify_gradients(self._stores)        # one bucket for the data-parallel all-reduce
@@ -334,11 +340,13 @@ class ManipulationClassification(object):
         lam_dcn = float(lambda_dcn) * world if train_dcn else 0.0
 
         # ---- forward
-        Y = self.nip._forward(x, save=train_nip)
+        with nvtx('nip.forward'):
+            Y = self.nip._forward(x, save=train_nip)
         strengths = self._draw_strengths(augment)
         M = self.n_classes * B
         # manipulations + 2x2 average pooling in one pass (no full-resolution stack) whenever the channel allows it
         fused = self._fuse_pool and ops.PooledStack.applicable(self._distribution['downsampling'], Y.shape[1], Y.shape[2])
+        _r = nvtx('manipulations+downsample'); _r.__enter__()
         if fused:
             plan = self._stack.plan(strengths, Y.shape[1])
             m = None
@@ -350,7 +358,9 @@ class ManipulationClassification(object):
             self._manipulate(Y, strengths, m, training=train_nip)
             c = self._downsample(m, out=ws.get('c', (M, -(-Y.shape[1] // self.downsampling_factor), -(-Y.shape[2] // self.downsampling_factor), 3))
                                  if self._distribution['downsampling'].startswith('pool') else None)
+        _r.__exit__()
         entropy = acc_dcn = None
+        _r = nvtx('codec.forward'); _r.__enter__()
         if comp == 'jpeg':
             C = ws.get('C', c.shape)
             quality = self.codec._draw_quality(None)
@@ -364,15 +374,18 @@ class ManipulationClassification(object):
             L.ni_image_loss(ptr(c), ptr(C), ptr(acc_dcn), c.numel(), 0, s)
         else:
             C, quality = c, None
+        _r.__exit__()
         labels = self._device_labels(B)
-        probs, loss_ce, dlogits = self.fan.forward_loss(C, labels)
+        with nvtx('fan.forward+loss'):
+            probs, loss_ce, dlogits = self.fan.forward_loss(C, labels)
         acc = ws.get('loss_nip', (1,))
         L.ni_fill(ptr(acc), 0.0, 1, s)
         self.nip.loss_forward(Y, t, acc, float(lambda_nip))
 
         # ---- backward
         codec_bwd = comp == 'dcn' and (train_nip or train_dcn)
-        dC = self.fan.backward(dlogits, need_dx=train_nip or codec_bwd)
+        with nvtx('fan.backward'):
+            dC = self.fan.backward(dlogits, need_dx=train_nip or codec_bwd)
         if codec_bwd:
             # d/dC of lambda_dcn * (l2_loss(c - C) + w * H); the entropy enters through the latent inside codec.backward
             if lam_dcn:
@@ -397,13 +410,15 @@ class ManipulationClassification(object):
                 for i, (name, op) in enumerate(self._ops.items()):
                     if op.has_grad:
                         op.backward(Y, dm[(i + 1) * B:(i + 2) * B], dY, strengths[name])
-            self.nip._backward(dY)
+            with nvtx('nip.backward'):
+                self.nip._backward(dY)
         return {'M': M, 'Y_numel': Y.numel(), 'loss_ce': loss_ce, 'acc': acc, 'acc_dcn': acc_dcn, 'entropy': entropy,
                 'comp': comp, 'train_dcn': train_dcn, 'lambda_nip': float(lambda_nip), 'lambda_dcn': float(lambda_dcn)}
 
     def _update(self, ctx, gscale=1.0, lr_t_dev=None):
         """Fused Adam over the flat buffers + the step's loss scalars (device tensors)."""
-        self._optimizer.apply(self._stores, gscale=gscale, lr_t_dev=lr_t_dev)
+        with nvtx('adam'):
+            self._optimizer.apply(self._stores, gscale=gscale, lr_t_dev=lr_t_dev)
         comp = ctx['comp']
         loss_ce_v = ctx['loss_ce'] / float(ctx['M'])
         loss_nip_v = ctx['acc'] / float(ctx['Y_numel'])

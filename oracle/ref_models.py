@@ -138,7 +138,7 @@ def dcn_codebook(latent_bpf=5, dtype=torch.float32):
     return torch.arange(-2 ** (latent_bpf - 1) + 1, 2 ** (latent_bpf - 1) + 1, dtype=dtype)
 
 
-def twitter_dcn_encode(P, x, latent_bpf=5):
+def twitter_dcn_encode(P, x, latent_bpf=5, rounding='soft-codebook'):
     """models/compression.py:213-241. P uses the product's names (encoder/conv2d[_k], .../latent_scaling)."""
     act = R.ACT['leaky_relu']
     cv = lambda t, name, stride=1: R.conv2d(t, P[name + '/kernel'], P[name + '/bias'], stride=stride)
@@ -149,7 +149,7 @@ def twitter_dcn_encode(P, x, latent_bpf=5):
         inp = R.leaky_relu(net) if i == 0 else net
         net = net + cv(act(cv(inp, 'encoder/conv2d_%d' % (2 + 2 * i))), 'encoder/conv2d_%d' % (3 + 2 * i))
     z = cv(net, 'encoder/conv2d_8', 2)
-    return R.discrete_latent(z, P.get('encoder/discrete_latent/latent_scaling'), dcn_codebook(latent_bpf)) + (z,)
+    return R.discrete_latent(z, P.get('encoder/discrete_latent/latent_scaling'), dcn_codebook(latent_bpf), rounding=rounding) + (z,)
 
 
 def twitter_dcn_decode(P, q):
@@ -164,8 +164,8 @@ def twitter_dcn_decode(P, q):
     return R.ste_clip((inet + 1) / 2)
 
 
-def twitter_dcn_forward(P, x, latent_bpf=5):
-    q, ent, z = twitter_dcn_encode(P, x, latent_bpf)
+def twitter_dcn_forward(P, x, latent_bpf=5, rounding='soft-codebook'):
+    q, ent, z = twitter_dcn_encode(P, x, latent_bpf, rounding)
     return twitter_dcn_decode(P, q), ent, q, z
 
 
@@ -174,9 +174,9 @@ def dcn_loss(x, y, ent, entropy_weight=250.0):
     return R.l2_loss(x - y) + entropy_weight * ent.to(x.dtype)
 
 
-def dcn_training_step(P, opt_state, x, lr=1e-3, entropy_weight=250.0, latent_bpf=5):
+def dcn_training_step(P, opt_state, x, lr=1e-3, entropy_weight=250.0, latent_bpf=5, rounding='soft-codebook'):
     """DCN.training_step (models/compression.py:123-139) with Keras Adam; parameters updated in place."""
-    y, ent, q, z = twitter_dcn_forward(P, x, latent_bpf)
+    y, ent, q, z = twitter_dcn_forward(P, x, latent_bpf, rounding)
     loss = dcn_loss(x, y, ent, entropy_weight)
     names = list(P.keys())
     grads = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)

@@ -185,8 +185,10 @@ def djpeg(inputs, q_luma, q_chroma, rounding='soft'):
     X = dF.unsqueeze(0) @ r                                                                      # :118
     X = X @ dI.unsqueeze(0)                                                                      # :119
     nb = p.shape[-1]
-    Ql = torch.tensor(np.asarray(q_luma, np.float32), dtype=dt).unsqueeze(0).repeat(nb, 1, 1)    # :125
-    Qc = torch.tensor(np.asarray(q_chroma, np.float32), dtype=dt).unsqueeze(0).repeat(2 * nb, 1, 1)
+    # tables: numpy arrays (fixed codec) or tensors carrying gradient (trainable=True: the tables are weights, :58-62)
+    as_t = lambda q: q.to(dt) if isinstance(q, torch.Tensor) else torch.tensor(np.asarray(q, np.float32), dtype=dt)
+    Ql = as_t(q_luma).unsqueeze(0).repeat(nb, 1, 1)                                              # :125
+    Qc = as_t(q_chroma).unsqueeze(0).repeat(2 * nb, 1, 1)
     Q = torch.cat((Ql, Qc), dim=0).repeat(n, 1, 1)                                               # :127-128
     X = X / Q
     X = quantization(X, rounding)
@@ -393,9 +395,13 @@ def entropy(values, codebook, v=50, gamma=25):
     return (-(histogram * torch.log(histogram)).sum() / 0.6931).to(torch.float32), histogram
 
 
-def discrete_latent(z, scale, codebook, v=50, gamma=25):
-    """DiscreteLatent.call, models/layers.py:195-203: the entropy is estimated on the QUANTISED latent."""
+def discrete_latent(z, scale, codebook, v=50, gamma=25, rounding='soft-codebook'):
+    """DiscreteLatent.call, models/layers.py:195-203: the entropy is estimated on the QUANTISED latent. rounding: the Quantization
+    mode the codec was built with (models/compression.py:66: 'soft-codebook' | 'sin' | 'soft' | 'identity')."""
     latent = z * scale.to(z.dtype) if scale is not None else z
+    if rounding != 'soft-codebook':
+        q = quantization(latent, rounding)
+        return q, entropy(q, codebook, v, gamma)[0]
     if z.dtype == torch.float32:
         q = soft_codebook_quantization(latent, codebook, v, gamma)
     else:       # float64 truth run: keep the soft value in float64

@@ -172,6 +172,17 @@ def case_djpeg():
             assert np.array_equal(N(y2), N(y))
             return {'y': N(y), 'X': N(X), 'dx': dx}
         record('djpeg_q{}_{}'.format(q, mode), both(run))
+    # trainable quantisation tables (models/jpeg.py:58-62): gradients w.r.t. the two 8x8 weights
+    META['djpeg']['trainable_cases'] = [[50, 'sin'], [80, 'soft'], [30, 'harmonic']]
+    for q, mode in META['djpeg']['trainable_cases']:
+        def run_t(dt):
+            m = jpeg.DifferentiableJPEG(q, mode, trainable=True)
+            assert len(m.trainable_weights) == 2
+            xt = T(x, dt, True)
+            y, X = m(xt)
+            dx, dql, dqc = grad_of((y * T(w, dt)).sum(), [xt, m._q_mtx_luma, m._q_mtx_chroma])
+            return {'y': N(y), 'dx': dx, 'dq_luma': dql, 'dq_chroma': dqc}
+        record('djpeg_trainable_q{}_{}'.format(q, mode), both(run_t))
     # the lazily created module-level codec of the 'jpeg' manipulation is JPEG(None, 'soft') (models/jpeg.py:38-42)
 
     def run_common(dt):
@@ -363,7 +374,9 @@ def case_fan():
 
 
 def case_dcn():
-    for kw, seed, ps in (({}, 41, 32), (dict(n_features=8, latent_bpf=3, entropy_weight=100), 42, 16)):
+    for kw, seed, ps in (({}, 41, 32), (dict(n_features=8, latent_bpf=3, entropy_weight=100), 42, 16),
+                         (dict(n_features=8, rounding='sin'), 43, 16), (dict(n_features=8, rounding='soft', latent_bpf=4), 44, 16),
+                         (dict(n_features=4, rounding='identity', entropy_weight=50), 45, 16)):
         case = 'dcn_{}'.format(seed)
         pm = p_compression.TwitterDCN(patch_size=ps, seed=1, **kw)
         specs = C.specs_of(pm)

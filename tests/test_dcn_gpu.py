@@ -160,8 +160,9 @@ def test_dcn_loss_matches_reference_definition():
     got = float(model.loss(a, b, 0.75).numpy())
     want = 0.5 * float(((a.astype(np.float64) - b) ** 2).sum()) + 250 * 0.75
     assert abs(got - want) < 1e-5 * want
-    with pytest.raises(NotImplementedError):
-        compression.TwitterDCN(patch_size=32, rounding='soft')
+    assert compression.TwitterDCN(patch_size=32, rounding='soft')._rounding == 2          # scalar rounding modes: tests/test_tf_graph_golden_gpu.py
+    with pytest.raises(ValueError):
+        compression.TwitterDCN(patch_size=32, rounding='round')          # ParamSpec of the reference: {'identity', 'soft', 'soft-codebook', 'sin'}
     s = model.ssim(a, a)
     assert abs(float(s.numpy()) - 1.0) < 1e-5
 

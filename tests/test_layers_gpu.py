@@ -45,8 +45,15 @@ def test_quantization_soft_codebook_and_discrete_latent():
     assert abs(float(ent.numpy()) - float(rent)) < 1e-5 * max(1.0, abs(float(rent)))
     with pytest.raises(ValueError):
         Quantization('no-such-mode')
-    with pytest.raises(NotImplementedError):
-        DiscreteLatent('sin')
+    with pytest.raises(ValueError):
+        DiscreteLatent('no-such-mode')
+    # the scalar rounding modes of the latent quantiser (models/layers.py:118-136) with the same entropy estimate
+    for mode in ('sin', 'soft', 'identity'):
+        layer = DiscreteLatent(mode, latent_bpf=5)
+        lat, ent = layer(z)
+        rq, rent = R.discrete_latent(torch.tensor(z), torch.ones(()), M.dcn_codebook(5), rounding=mode)
+        assert np.mean(np.abs(lat.numpy() - rq.numpy()) > 1e-5) < 1e-3, mode          # 'soft': a value within float32 noise of k + 1/2 may round the other way
+        assert abs(float(ent.numpy()) - float(rent)) < 1e-4 * max(1.0, abs(float(rent))), mode
 
 
 @pytest.mark.gpu

@@ -341,3 +341,30 @@ def test_fused_pooled_stack_inside_the_training_step():
             ref = res[False][k][name]
             e = np.abs(g - ref) / max(float(np.abs(ref).max()), 1e-30)
             assert np.mean(e > 2e-5) <= 0.02, (name, float(e.max()))
+
+
+def test_fan_dropout_semantics():
+    """FAN(dropout > 0) (models/forensics.py:86-88): Dropout follows each hidden dense layer; it is the identity in process(), in
+    training_step (the reference calls the model without training=True there) and only acts in process(x, training=True)."""
+    from neural_imaging_b200.models import forensics
+    rs = np.random.RandomState(5)
+    x = rs.uniform(size=(64, 16, 16, 3)).astype(np.float32)
+    labels = rs.randint(0, 5, size=(64,))
+    kw = dict(n_classes=5, patch_size=16, n_filters=8, n_convolutions=2, n_dense=2, seed=3)
+    a, b = forensics.FAN(dropout=0.0, **kw), forensics.FAN(dropout=0.5, **kw)
+    assert np.array_equal(a.process(x).numpy(), b.process(x).numpy())
+    la, lb = a.training_step(x, labels, 1e-3), b.training_step(x, labels, 1e-3)
+    assert float(la.numpy()) == float(lb.numpy())
+    # (weight gradients are summed with atomics: run-to-run rounding differences, amplified to +-lr by Adam where a gradient is ~0)
+    assert np.mean(np.abs(a._store.flat.cpu().numpy() - b._store.flat.cpu().numpy()) > 1e-6) < 0.02
+    p0, p1, p2 = b.process(x).numpy(), b.process(x, training=True).numpy(), b.process(x, training=True).numpy()
+    assert not np.array_equal(p0, p1) and not np.array_equal(p1, p2)          # active, and a fresh mask per call
+    assert np.allclose(p1.sum(axis=1), 1.0, atol=1e-5)
+    # the kernel itself: keep rate and inverted scaling
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream
+    v = as_device(np.ones((1 << 16,), np.float32))
+    out = empty(v.shape)
+    _lib.lib().ni_dropout(ptr(v), ptr(out), v.numel(), 0.25, 1234, stream())
+    o = out.cpu().numpy()
+    assert set(np.unique(o)).issubset({0.0, np.float32(1.0 / 0.75)}) and abs(float((o > 0).mean()) - 0.75) < 0.01

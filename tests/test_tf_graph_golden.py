@@ -61,6 +61,12 @@ def test_oracle_djpeg_matches_executed_reference(G):
         dx, = torch.autograd.grad((y * t64(w)).sum(), xt)
         chk(G, case, 'y', y), chk(G, case, 'X', X), chk(G, case, 'dx', dx)
     chk(G, 'djpeg_common_q80', 'y', R.jpeg_manipulation(t64(x), 80))
+    for q, mode in m['trainable_cases']:          # DifferentiableJPEG(trainable=True): gradients w.r.t. the quantisation tables
+        case = 'djpeg_trainable_q{}_{}'.format(q, mode)
+        xt, ql, qc = t64(x, True), t64(R.jpeg_qtable(q, 0), True), t64(R.jpeg_qtable(q, 1), True)
+        y, _ = R.djpeg(xt, ql, qc, mode)
+        dx, dql, dqc = torch.autograd.grad((y * t64(w)).sum(), [xt, ql, qc])
+        chk(G, case, 'y', y), chk(G, case, 'dx', dx), chk(G, case, 'dq_luma', dql), chk(G, case, 'dq_chroma', dqc)
 
 
 # ------------------------------------------------------------------------------------------------------------------ manipulations
@@ -242,11 +248,11 @@ def test_oracle_twitter_dcn_matches_executed_reference(G, host_models):
         specs = C.specs_of(pm)
         state = C.golden_state(specs, meta['seed'])
         x = np.random.RandomState(meta['seed']).uniform(size=(2, ps, ps, 3)).astype(np.float32)
-        bpf, ew = kw.get('latent_bpf', 5), float(kw.get('entropy_weight', 250))
+        bpf, ew, rnd = kw.get('latent_bpf', 5), float(kw.get('entropy_weight', 250)), kw.get('rounding', 'soft-codebook')
         P = M.to_params(state, torch.float64)
         names = list(P.keys())
         xt = t64(x, True)
-        y, ent, q, z = M.twitter_dcn_forward(P, xt, bpf)
+        y, ent, q, z = M.twitter_dcn_forward(P, xt, bpf, rnd)
         loss = M.dcn_loss(xt, y, ent, ew)
         g = torch.autograd.grad(loss, [xt] + [P[n] for n in names])
         # the reference casts the soft latent and the entropy to float32 in the middle of the graph (models/layers.py:161, tf_helpers.py:331)
@@ -256,8 +262,8 @@ def test_oracle_twitter_dcn_matches_executed_reference(G, host_models):
         for n, e in zip(names, g[1:]):
             chk(G, case, 'grad/' + n, e, 2e-6)
         opt = {'t': 0, 'm': {}, 'v': {}}
-        s1 = M.dcn_training_step(P, opt, t64(x), 1e-3, ew, bpf)[0]
-        s2 = M.dcn_training_step(P, opt, t64(x), 5e-4, ew, bpf)[0]
+        s1 = M.dcn_training_step(P, opt, t64(x), 1e-3, ew, bpf, rnd)[0]
+        s2 = M.dcn_training_step(P, opt, t64(x), 5e-4, ew, bpf, rnd)[0]
         chk(G, case, 'step_loss', np.array([s1['loss'], s2['loss']]), 1e-6)
         chk(G, case, 'step_entropy', np.array([s1['entropy'], s2['entropy']]), 1e-6)
         for n in names:

@@ -60,6 +60,17 @@ def test_djpeg_against_executed_reference(G):
             G.check(case, 'X', _np(X), tol=1e-5)
             G.check(case, 'dx', _np(dx), tol=2e-5)
     G.check('djpeg_common_q80', 'y', jpeg.differentiable_jpeg(x, 80).numpy(), tol=1e-5, outliers=0.03, loose=0.2)
+    # trainable quantisation tables (models/jpeg.py:58-62): the table gradients sum over every block, so a flipped rounding decision
+    # ('soft') moves one entry by one block's worth
+    for q, mode in m['trainable_cases']:
+        case = 'djpeg_trainable_q{}_{}'.format(q, mode)
+        model = jpeg.DifferentiableJPEG(q, mode, trainable=True)
+        assert len(model.trainable_weights) == 2 and jpeg.JPEG(q, mode, trainable=True).count_parameters() == 128
+        dx = model.backward(as_device(x), as_device(w))
+        soft = mode == 'soft'
+        G.check(case, 'dx', _np(dx), tol=2e-5, outliers=0.03 if soft else 0.0, loose=2.0 if soft else None)
+        G.check(case, 'dq_luma', _np(model._pl.grad), tol=5e-5, outliers=0.05 if soft else 0.0, loose=0.5 if soft else None)
+        G.check(case, 'dq_chroma', _np(model._pc.grad), tol=5e-5, outliers=0.05 if soft else 0.0, loose=0.5 if soft else None)
 
 
 # ------------------------------------------------------------------------------------------------------------------ a5-a9 manipulations
