@@ -167,6 +167,25 @@ int pick_bnt(int n) {
     return n % 32 == 0 ? 32 : 0;
 }
 
+// N-tile width of the persistent gemm chosen against WAVE QUANTISATION: one CTA per SM walks mtiles * N / bnt tiles; with few pixel tiles
+// (deep U-Net layers, small per-GPU batches: 16 - 64 tiles of 128 pixels) a 128-wide tile leaves most SMs idle. Cost of a choice =
+// waves * cycles per 32-deep 3xTF32 k-iteration of that width (12 MMAs of 20.5 + 0.42 N cycles, measured: profiles/r1_hw_probes.txt).
+int pick_bnt_gemm(int n, int mtiles) {
+    const int widest = pick_bnt(n);
+    if (widest <= 32) return widest;
+    const int sms = ni_num_sms();
+    int best = widest;
+    double best_cost = 1e30;
+    for (int b = widest; b >= 32; b >>= 1) {
+        if (n % b) continue;
+        const long long tiles = (long long)mtiles * (n / b);
+        const long long waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (20.5 + 0.42 * b);
+        if (cost < best_cost * 0.97) { best_cost = cost; best = b; }      // prefer the wider tile on near ties (less weight traffic per MMA)
+    }
+    return best;
+}
+
 template <typename K>
 int set_dyn_smem(K kern, size_t bytes) {
     NI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -197,7 +216,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         return NI_ERR_UNSUPPORTED;
     }
     p.sa = tcv2::kMaxSA;           // two halo stages: the next chunk / the next tile's halo is in flight while this one is converted
-    const int bnt = pick_bnt(N);
+    const int bnt = pick_bnt_gemm(N, (tw / p.bw) * (th / p.bh) * ((d->n + p.bn - 1) / p.bn));
     float* scratch = nullptr;
     const size_t wbytes = (size_t)2 * taps * K * N * sizeof(float);
     int rc = get_scratch(wbytes, &scratch);
