@@ -133,6 +133,30 @@ class EventProfiler:
         if name == 'ni_djpeg_bwd':
             n, h, w = args[3], args[4], args[5]
             return ('byte', 36.0 * n * h * w)
+        # algorithmic bytes of the other HBM-bound entry points (float32 NHWC; DESIGN.md section 4 states each formula)
+        if name == 'ni_maxpool2_act_bwd_bias':          # read y (full), read d(pooled), write dy (full)
+            n, h, w, c = args[5], args[6], args[7], args[8]
+            return ('byte', 4.0 * n * h * w * c * (1 + 0.25 + 1))
+        if name == 'ni_maxpool2_fwd':                   # read x, write pooled
+            n, h, w, c = args[2], args[3], args[4], args[5]
+            return ('byte', 4.0 * n * h * w * c * 1.25)
+        if name == 'ni_act_bwd_bias':                   # read y (when the activation needs it), read + write dy
+            n, h, w, c = args[3], args[4], args[5], args[6]
+            return ('byte', 4.0 * n * h * w * c * (3 if args[0] else 2))
+        if name == 'ni_manip_stack_pool2_fwd':          # read Y (12 B/px), write 4 pooled slots (4 x 3 B/px) + 1 mask byte
+            b, h, w = args[3], args[4], args[5]
+            return ('byte', 25.0 * b * h * w)
+        if name == 'ni_manip_stack_pool2_bwd':          # read 3 pooled gradient slots (9 B/px) + mask, read + write dY (24 B/px)
+            b, h, w = args[3], args[4], args[5]
+            return ('byte', 34.0 * b * h * w)
+        if name in ('ni_cconv5_fwd', 'ni_cconv5_bwd_data', 'ni_cconv5_bwd_filter'):      # 225 MAC per pixel: FP32-FMA bound, not HBM (AI 18.8 flop/B)
+            n, h, w = args[3], args[4], args[5]
+            return ('flop', 2.0 * 225 * n * h * w)
+        if name in ('ni_avgpool_fwd', 'ni_avgpool_bwd'):
+            n, h, w = args[2], args[3], args[4]
+            return ('byte', 15.0 * n * h * w)
+        if name == 'ni_adam_keras' or name == 'ni_adam_keras_dev':
+            return ('byte', 28.0 * args[4])
         return ('none', 0.0)
 
     def summary(self):
@@ -292,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
             e['gbs'] = r['work'] / (r['ms'] * 1e-3) / 1e9
             e['frac_of_hbm_peak'] = e['gbs'] / pk['hbm_gbs']
         kernels.append(e)
-    conv = [k for k in kernels if k['entry'].startswith('ni_conv2d_')]
+    conv = [k for k in kernels if k['entry'].startswith(('ni_conv2d_', 'ni_cconv5_'))]       # every convolution launch, incl. the constrained 5x5 3->3 filter
     conv_ms = sum(k['ms_per_step'] for k in conv)
     conv_flop = sum(agg[k['entry']]['work'] for k in conv) / args.steps
     dj = next((k for k in kernels if k['entry'] == 'ni_djpeg_fwd'), None)
@@ -300,9 +324,12 @@ def run_ours(args, rank, world, local_rank):
     # DRAM traffic per launch comes from the committed `ncu --set full` captures (profiles/r1_ncu_traffic.json, written by
     # tools/ncu_traffic.py from the .ncu-rep files): it cannot be measured live without a profiler attached.
     traffic = {}
-    tpath = os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')
-    if os.path.isfile(tpath):
-        traffic = json.load(open(tpath))
+    for tname in ('r2_ncu_traffic.json', 'r1_ncu_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath))
+            traffic['source'] = 'profiles/' + tname
+            break
     n_conv_launches = sum(k['calls_per_step'] for k in conv)
     roofline = {'kernel': 'conv2d tcgen05 3xTF32 implicit GEMM + direct FP32 stencils (fprop+dgrad+wgrad, all %d conv launches of the step)' % int(n_conv_launches),
                 'bound': 'tensor', 'achieved': conv_tf, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': conv_tf / pk['bf16_tflops_sustained'],
@@ -344,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
                              'h2d_bytes_per_step': int(xi.numel() * 2 + yi.numel()) * world, 'd2h_bytes_per_step': 4 * world,
                              'api': 'as e2e, host batches as stored (uint16 RAW / uint8 RGB), converted on the device (ni_feed_convert)'},
         'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'cuda_graph': not args.no_graph,
-        'host_enqueue_ms_per_step': host_ms.get('step_resident'), 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:12],
+        'host_enqueue_ms_per_step': host_ms.get('step_resident'), 'clocks': clk, 'roofline': roofline, 'roofline_djpeg': roofline_djpeg, 'kernels': kernels[:16],
         'images_per_sec_codec_fan': 5 * gb / (ms * 1e-3), 'loss': float(loss.numpy()), 'param_checksum': checksum,
     }
     if lat is not None:
@@ -417,7 +444,7 @@ def _profiled(step, steps):
 
 
 def _conv_roofline(agg, steps, prof_ms, pk):
-    conv = {k: r for k, r in agg.items() if k.startswith('ni_conv2d_')}
+    conv = {k: r for k, r in agg.items() if k.startswith(('ni_conv2d_', 'ni_cconv5_'))}
     ms = sum(r['ms'] for r in conv.values()) / steps
     flop = sum(r['work'] for r in conv.values()) / steps
     n = sum(r['calls'] for r in conv.values()) / steps

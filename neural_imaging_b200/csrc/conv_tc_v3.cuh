@@ -337,6 +337,16 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
             const int ox = x0 + lw, oy = y0 + lh, on = n0 + ln;
             const bool valid = on < p.n && oy < p.oh && ox < p.ow;
             if (fuse_act && nt != bs_nt) { flush_bias(); bs_nt = nt; }
+            // fused activation backward: the forward output of the layer below is fetched BEFORE waiting for the accumulators (chunk 0)
+            // and one chunk ahead afterwards, so that its HBM latency hides behind the main loop / the previous chunk's work
+            const bool want_y = fuse_act && p.dact_y != nullptr && valid && p.dact != NI_ACT_NONE;
+            const float4* y4base = want_y ? reinterpret_cast<const float4*>(
+                p.dact_y + (((long long)on * p.oh + oy) * p.ow + ox) * p.dact_pitch + p.dact_coff + nt * BNT) : nullptr;
+            float4 ynext[8];
+            if (want_y) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ynext[j] = y4base[j];
+            }
             TCP_START();
             mbar_wait(&bar_accfull[aset], use & 1, 4);
             TCP_ADD(10);
@@ -360,12 +370,14 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 const int co0 = nt * BNT + c * 32;
                 if (fuse_act) {
                     // v <- v * act'(y) with y = the forward output of the layer whose output gradient this is (same pixel, same channels)
-                    if (p.dact_y != nullptr && valid && p.dact != NI_ACT_NONE) {
-                        const float4* y4 = reinterpret_cast<const float4*>(
-                            p.dact_y + (((long long)on * p.oh + oy) * p.ow + ox) * p.dact_pitch + p.dact_coff + co0);
+                    if (want_y) {
                         float4 yv[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) yv[j] = y4[j];
+                        for (int j = 0; j < 8; ++j) yv[j] = ynext[j];
+                        if (c + 1 < BNT / 32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) ynext[j] = y4base[(c + 1) * 8 + j];
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float ye[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 evidence for profiles/: full GPU test-suite (+ parity report), smoke, bench lines of every BASELINE configuration, the reference
+# arm, the ncu launch list of one step, `ncu --set full` captures of the dominant kernels and of the new HBM-side kernels.
+#   ./gpu.sh 2400 'bash tools/gpu_round2_evidence.sh'
+cd /root/repo
+O=gpurun_out/r2
+mkdir -p $O
+( timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4 ) > $O/tests_gpu.log; tail -2 $O/tests_gpu.log
+cp gpurun_out/parity_report.json $O/parity_report.json 2>/dev/null
+( timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ) > $O/smoke.log; cat $O/smoke.log
+( timeout 900 python bench.py --steps 20 --warmup 5 --layer-report $O/layers_b256.json 2>&1 | tail -1 ) > $O/bench_c4.json; head -c 300 $O/bench_c4.json; echo
+( timeout 300 python bench.py --batch 32 --steps 20 --warmup 5 --no-cpu-baseline --layer-report $O/layers_b32.json 2>&1 | tail -1 ) > $O/bench_c4_b32.json; head -c 260 $O/bench_c4_b32.json; echo
+for c in c1 c2 c3; do ( timeout 600 python bench.py --config $c --steps 20 --warmup 5 2>&1 | tail -1 ) > $O/bench_$c.json; echo "$c: $(head -c 260 $O/bench_$c.json)"; done
+( timeout 900 python bench.py --config c5 --steps 10 --warmup 3 --sweep 2>&1 | tail -1 ) > $O/bench_c5.json; echo "c5: $(head -c 260 $O/bench_c5.json)"
+( timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 ) > $O/bench_reference_arm.json; head -c 300 $O/bench_reference_arm.json; echo
+timeout 120 python tools/profile_djpeg.py 1280 20 > $O/djpeg_time.json 2>&1; cat $O/djpeg_time.json
+timeout 120 python tools/profile_manip.py 10 > $O/manip_time.json 2>&1; cat $O/manip_time.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file $O/launches_step.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_bench.log 2>&1; echo "ncu launches exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:djpeg -s 3 -c 2 -o $O/prof_djpeg -f python tools/profile_djpeg.py 1280 1 > $O/ncu_djpeg.log 2>&1; echo "ncu djpeg exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_gemm -s 2 -c 1 -o $O/prof_conv_fprop -f python tools/profile_conv.py 2 > $O/ncu_conv.log 2>&1; echo "ncu conv fprop exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_wgrad -s 2 -c 1 -o $O/prof_conv_wgrad -f python tools/profile_conv.py 2 >> $O/ncu_conv.log 2>&1; echo "ncu conv wgrad exit $?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"manip_stack|cconv5" -c 20 -o $O/prof_manip -f python tools/profile_manip.py 1 > $O/ncu_manip.log 2>&1; echo "ncu manip exit $?"
+ls -la $O | tail -30
