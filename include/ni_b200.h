@@ -230,6 +230,12 @@ int ni_softmax_ce(const float* logits, const int* labels, float* probs, float* l
 int ni_cconv5_fwd(const float* x, const float* nf, float* y, int n, int h, int w, ni_stream_t stream);
 int ni_cconv5_bwd_data(const float* dy, const float* nf, float* dx, int n, int h, int w, int accumulate, ni_stream_t stream);
 int ni_cconv5_bwd_filter(const float* x, const float* dy, float* dnf, int n, int h, int w, ni_stream_t stream);
+/* A SAME stride-2 5x5 convolution on an even-sized input (the DCN encoder's down-sampling layers, models/compression.py:221-222,237) =
+ * a SAME stride-1 3x3 convolution over space_to_depth(2) of the input with the taps scattered into a zero-padded 6x6 grid: that form runs
+ * on the tcgen05 path. ni_space_to_depth2 moves activations (inverse = 1: plain (+)= deep, the input-gradient way back), ni_s2conv_weights
+ * moves weights (inverse = 1: the 5x5 weight gradient gathered from the 3x3 x 4cin one). tf.nn.space_to_depth channel order. */
+int ni_space_to_depth2(float* plain, float* deep, int n, int h2, int w2, int c, int inverse, int accumulate, ni_stream_t stream);
+int ni_s2conv_weights(float* w5, float* w3, int cin, int cout, int inverse, ni_stream_t stream);
 /* tf.keras.layers.Dropout(rate) in training mode (models/forensics.py:88; FAN.process(x, training=True)): inverted dropout, own generator */
 int ni_dropout(const float* x, float* y, long long n, float rate, unsigned long long seed, ni_stream_t stream);
 /* validate_fan's decisions and confusion matrix (training/validation.py:163-203; workflows/manipulation_classification.py:178-180):

@@ -651,6 +651,79 @@ extern "C" int ni_softmax_ce(const float* logits, const int* labels, float* prob
     return NI_OK;
 }
 
+// ---------------------------------------------------------------- stride-2 5x5 convolution as a 3x3 convolution over space_to_depth(2)
+// A SAME, stride-2, 5x5 convolution on an even-sized input (models/compression.py:221-222,237: the DCN encoder's down-sampling layers)
+// reads input rows 2o + a - 1, a = 0..4, for output row o: in the space_to_depth(2) domain (block i = rows 2i, 2i + 1) these are
+// block o - 1 (second row), block o (both rows), block o + 1 (both rows) -- a SAME 3x3 stride-1 convolution over 4 x cin channels with
+// the 5x5 taps scattered into a zero-padded 6x6 grid. That form runs on the tcgen05 implicit-GEMM path (stride 1, cin' % 32 == 0);
+// the price is 36 / 25 of the MACs. These kernels move the activations and the weights between the two forms.
+//   xs[n, i, j, (di*2 + dj)*C + c] = x[n, 2i + di, 2j + dj, c]                       (tf.nn.space_to_depth order)
+//   w3[bi, bj, (di*2 + dj)*C + c, f] = w5[2bi + di - 1, 2bj + dj - 1, c, f] or 0
+__global__ void s2d2_kernel(const float* __restrict__ x, float* __restrict__ y, long long total4, int h2, int w2, int c4, int inverse,
+                            int accumulate) {
+    // one thread per 4 channels of one (n, i, j, block offset) cell; x is the plain (n, 2h2, 2w2, C) tensor, y the (n, h2, w2, 4C) one
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total4) return;
+    const int cq = (int)(t % c4);
+    long long r = t / c4;
+    const int blk = (int)(r % 4); r /= 4;
+    const int j = (int)(r % w2); r /= w2;
+    const int i = (int)(r % h2);
+    const long long n = r / h2;
+    const int C = c4 * 4;
+    const long long plain = (((n * 2 * h2 + 2 * i + (blk >> 1)) * (2LL * w2) + 2 * j + (blk & 1)) * C) + cq * 4;
+    const long long deep = (((n * h2 + i) * (long long)w2 + j) * 4 + blk) * C + cq * 4;
+    if (!inverse) {
+        *reinterpret_cast<float4*>(y + deep) = *reinterpret_cast<const float4*>(x + plain);
+    } else {        // y (deep) -> x (plain): here `x` is the destination
+        float4 v = *reinterpret_cast<const float4*>(y + deep);
+        float4* o = reinterpret_cast<float4*>(const_cast<float*>(x) + plain);
+        if (accumulate) { const float4 old = *o; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+        *o = v;
+    }
+}
+// plain (n, 2*h2, 2*w2, c) <-> deep (n, h2, w2, 4c); inverse = 0: deep <- plain, 1: plain (+)= deep. c % 4 == 0.
+extern "C" int ni_space_to_depth2(float* plain, float* deep, int n, int h2, int w2, int c, int inverse, int accumulate, cudaStream_t st) {
+    NI_REQUIRE(plain && deep && n >= 0 && h2 > 0 && w2 > 0 && c > 0 && (c % 4) == 0, "ni_space_to_depth2: invalid arguments");
+    const long long total4 = (long long)n * h2 * w2 * c;      // = n*h2*w2*4 blocks * c/4 quads
+    if (total4 == 0) return NI_OK;
+    s2d2_kernel<<<ni_cdiv(total4, kT), kT, 0, st>>>(plain, deep, total4, h2, w2, c / 4, inverse, accumulate);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+__global__ void s2conv_weights_kernel(const float* __restrict__ w5, float* __restrict__ w3, int cin, int cout, int inverse) {
+    if (!inverse) {        // w3 <- scatter(w5), one thread per w3 element
+        const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long total = 9LL * 4 * cin * cout;
+        if (t >= total) return;
+        const int f = (int)(t % cout);
+        long long r = t / cout;
+        const int c = (int)(r % cin); r /= cin;
+        const int blk = (int)(r % 4); r /= 4;
+        const int bj = (int)(r % 3), bi = (int)(r / 3);
+        const int a = 2 * bi + (blk >> 1) - 1, b = 2 * bj + (blk & 1) - 1;
+        w3[t] = (a >= 0 && a < 5 && b >= 0 && b < 5) ? w5[(((long long)a * 5 + b) * cin + c) * cout + f] : 0.f;
+    } else {               // dw5 <- gather(dw3), one thread per w5 element
+        const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long total = 25LL * cin * cout;
+        if (t >= total) return;
+        const int f = (int)(t % cout);
+        long long r = t / cout;
+        const int c = (int)(r % cin); r /= cin;
+        const int b = (int)(r % 5), a = (int)(r / 5);
+        const int bi = (a + 1) >> 1, di = (a + 1) & 1, bj = (b + 1) >> 1, dj = (b + 1) & 1;
+        const_cast<float*>(w5)[t] = w3[((((long long)bi * 3 + bj) * 4 + di * 2 + dj) * cin + c) * cout + f];
+    }
+}
+// inverse = 0: w3 (3, 3, 4*cin, cout) <- w5 (5, 5, cin, cout); inverse = 1: w5 <- the 5x5 taps of w3 (weight-gradient way back)
+extern "C" int ni_s2conv_weights(float* w5, float* w3, int cin, int cout, int inverse, cudaStream_t st) {
+    NI_REQUIRE(w5 && w3 && cin > 0 && cout > 0, "ni_s2conv_weights: invalid arguments");
+    const long long total = inverse ? 25LL * cin * cout : 36LL * cin * cout;
+    s2conv_weights_kernel<<<ni_cdiv(total, kT), kT, 0, st>>>(w5, w3, cin, cout, inverse);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
 // Keras Dropout(rate) in training mode (models/forensics.py:88: after each hidden dense layer when the model is CALLED with
 // training=True; the reference's training steps call it without, so the layer is inactive there): y = x * keep / (1 - rate), keep ~
 // Bernoulli(1 - rate) from a counter-based generator (splitmix64 of seed and element index; TensorFlow's stream cannot be reproduced).

@@ -239,10 +239,11 @@ class TwitterDCN(DCN):
         st, rng, act = self._store, self._rng, self._h.activation
         C = nn.Conv2D
         self._e1 = C(st, 'encoder/conv2d', 5, 3, 64, stride=2, activation=act, rng=rng)
-        self._e2 = C(st, 'encoder/conv2d_1', 5, 64, 128, stride=2, rng=rng)
+        # the two wide down-sampling layers run as 3x3 convolutions over space_to_depth(2) on the tcgen05 path (nn.StridedConv5)
+        self._e2 = nn.StridedConv5(st, 'encoder/conv2d_1', 64, 128, rng=rng)
         self._eres = [(C(st, 'encoder/conv2d_%d' % (2 + 2 * i), 3, 128, 128, activation=act, rng=rng),
                        C(st, 'encoder/conv2d_%d' % (3 + 2 * i), 3, 128, 128, rng=rng)) for i in range(3)]
-        self._eout = C(st, 'encoder/conv2d_8', 5, 128, nf, stride=2, rng=rng)
+        self._eout = nn.StridedConv5(st, 'encoder/conv2d_8', 128, nf, rng=rng) if nf % 32 == 0 else C(st, 'encoder/conv2d_8', 5, 128, nf, stride=2, rng=rng)
         self._scale = st.add('encoder/discrete_latent/latent_scaling', (), np.float32(1.0), True) if self._h.scale_latent else None
         self._d1 = C(st, 'decoder/conv2d_9', 3, nf, 512, rng=rng)
         self._dres = [(C(st, 'decoder/conv2d_%d' % (10 + 2 * i), 3, 128, 128, activation=act, rng=rng),

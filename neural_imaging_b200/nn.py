@@ -246,6 +246,72 @@ class Conv2D:
         return dx
 
 
+class StridedConv5(Conv2D):
+    """Conv2D(k = 5, stride 2, SAME) on even-sized inputs, evaluated as a 3x3 stride-1 convolution over space_to_depth(2) of the input
+    (see ni_space_to_depth2 / ni_s2conv_weights in csrc/nn_misc.cu): the parameters keep Keras' (5, 5, cin, cout) layout, the
+    computation runs on the tcgen05 implicit-GEMM path (cin % 8 == 0, cout % 32 == 0) instead of the FP32 SIMT fallback."""
+
+    def __init__(self, store, name, cin, cout, **kw):
+        super().__init__(store, name, 5, cin, cout, stride=2, **kw)
+        if cin % 8 or cout % 32:
+            raise ValueError('StridedConv5 needs cin % 8 == 0 and cout % 32 == 0')
+        self._inner = None           # geometry helper: a 3x3 stride-1 convolution over 4 * cin channels
+        self._bufs = {}
+
+    def _buf(self, tag, shape):
+        b = self._bufs.get((tag, tuple(shape)))
+        if b is None:
+            b = self._bufs[(tag, tuple(shape))] = empty(tuple(shape))
+        return b
+
+    def desc(self, n, h, w, **kw):
+        if h % 2 or w % 2:
+            raise ValueError('StridedConv5 needs even input sides, got {}x{}'.format(h, w))
+        d = ConvDesc()
+        d.n, d.h, d.w, d.cin, d.cout, d.kh, d.kw, d.stride = n, h // 2, w // 2, 4 * self.cin, self.cout, 3, 3, 1
+        d.pad_t, d.pad_l, d.oh, d.ow = 1, 1, h // 2, w // 2
+        d.in_pitch, d.in_coff, d.out_pitch, d.out_coff = 4 * self.cin, 0, self.cout, 0
+        d.in_mode, d.out_mode = MODE_PLAIN, MODE_PLAIN
+        d.act, d.act_alpha = (self.act if kw.get('act') is None else kw['act']), self.alpha
+        d.accumulate, d.pad_mode, d.bias_mod = int(kw.get('accumulate', False)), PAD_ZERO, 0
+        return d
+
+    def _w3(self):
+        L = _lib.lib()
+        w3 = self._buf('w3', (3, 3, 4 * self.cin, self.cout))
+        L.ni_s2conv_weights(ptr(self.w.value), ptr(w3), self.cin, self.cout, 0, stream())
+        return w3
+
+    def fprop(self, x, y, d, weight=None):
+        L = _lib.lib()
+        xs = self._buf('xs', (d.n, d.h, d.w, 4 * self.cin))
+        L.ni_space_to_depth2(ptr(x), ptr(xs), d.n, d.h, d.w, self.cin, 0, 0, stream())
+        L.ni_conv2d_fprop(ctypes.byref(d), ptr(xs), ptr(self._w3()), self._bias_ptr(), ptr(y), stream())
+        return y
+
+    def bprop(self, x, y, dy, dx, d, need_dx=True, need_dw=True, act_bias_done=False, dx_accumulate=False, **unused):
+        """x: the layer's plain input (its space_to_depth copy from the forward pass is still in the layer's buffer)."""
+        L, st = _lib.lib(), stream()
+        self.fused_prev = False
+        db = ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
+        if not act_bias_done and (db is not None or d.act not in (ACT_NONE, ACT_CLIP01)):
+            L.ni_act_bwd_bias(ptr(y), ptr(dy), db, d.n, d.oh, d.ow, d.cout, d.out_pitch, d.out_coff, d.out_mode,
+                              d.out_pitch, d.out_coff, d.out_mode, d.act, d.act_alpha, 0, st)
+        dd = ConvDesc()
+        ctypes.memmove(ctypes.byref(dd), ctypes.byref(d), ctypes.sizeof(ConvDesc))
+        dd.accumulate = 0
+        xs = self._buf('xs', (d.n, d.h, d.w, 4 * self.cin))
+        if need_dw and self.w.trainable:
+            dw3 = self._buf('dw3', (3, 3, 4 * self.cin, self.cout))
+            L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(xs), ptr(dy), ptr(dw3), st)
+            L.ni_s2conv_weights(ptr(self.w.grad), ptr(dw3), self.cin, self.cout, 1, st)
+        if need_dx:
+            dxs = self._buf('dxs', (d.n, d.h, d.w, 4 * self.cin))
+            L.ni_conv2d_dgrad(ctypes.byref(dd), ptr(dy), ptr(self._w3()), ptr(dxs), st)
+            L.ni_space_to_depth2(ptr(dx), ptr(dxs), d.n, d.h, d.w, self.cin, 1, int(dx_accumulate), st)
+        return dx
+
+
 def unify_gradients(stores):
     """Lay the flat gradient buffers of several stores out back to back in ONE arena, so that the data-parallel exchange is a single
     all-reduce over one bucket instead of one collective per model. Returns the arena. Call before the first step (nothing
