@@ -193,6 +193,14 @@ int ni_conv2d_direct_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_direct(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_direct(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);
 int ni_conv2d_wgrad_direct(const ni_conv_desc* d, const float* x, const float* dy, float* dw, ni_stream_t stream);
+/* Conv2D (3 / 4 input channels) + bias + activation + MaxPool2D(2x2) in one kernel (first block of the FAN, models/forensics.py:66-69):
+ * pooled (n, oh/2, ow/2, cout) + one code byte per pooled element (argmax position | (value > 0) << 2); the full-resolution activation
+ * is never written. ni_maxpool2_code_bwd_bias is the matching backward of (activation + pooling): dx (n, oh, ow, c) from dy, dbias overwritten. */
+int ni_conv2d_pool2_supported(const ni_conv_desc* d);
+int ni_conv2d_pool2_fwd(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* pooled, unsigned char* code,
+                        ni_stream_t stream);
+int ni_maxpool2_code_bwd_bias(const unsigned char* code, const float* dy, float* dx, float* dbias, int n, int oh, int ow, int c, int act,
+                              float alpha, ni_stream_t stream);
 int ni_conv2d_small_supported(const ni_conv_desc* d, int op);
 int ni_conv2d_fprop_small(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, ni_stream_t stream);
 int ni_conv2d_dgrad_small(const ni_conv_desc* d, const float* dy, const float* w, float* dx, ni_stream_t stream);

@@ -20,6 +20,10 @@ struct DirectParams {
     TensorView src, dst;
     int n, pad_t, pad_l, pad_mode;
     int act, bias_mod; float alpha; int accumulate;
+    // POOL variant of the few-input kernel (conv + bias + activation + 2x2 max-pool in one pass): pooled output (n, H/2, W/2, COUT) and one
+    // code byte per pooled element = argmax position (bits 0-1, scan order) | (value > 0) << 2 — what the backward needs instead of the
+    // full-resolution activation. dst is then only a shape.
+    float* pool; unsigned char* code;
 };
 
 __device__ __forceinline__ int mirror_idx(int u, int n, int mode) {
@@ -63,7 +67,7 @@ __device__ __forceinline__ bool view_vec4(const TensorView& v) { return v.mode =
 constexpr int FW = 64, FH = 8;     // output tile, 256 threads = 128 pixel groups x 2 channel halves
 constexpr int FXS = FW + 4;        // input tile row stride (floats): room for the 8-wide window of the last pixel group
 
-template <int CIN, int COUT, int K>
+template <int CIN, int COUT, int K, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y) {
     static_assert(K <= 5 && COUT % 8 == 0, "window of 4 + K - 1 <= 8 input columns; two channel halves of whole float4s");
@@ -118,6 +122,48 @@ conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __re
         }
     }
     const int oy = ty0 + gy;
+    if (POOL) {
+        // bias + activation, then the 2x2 max-pool: columns pair up inside the thread (pixels 0,1 | 2,3), rows across lanes l and l ^ 16
+        // (the lane holding the row below / above, same column group, same channel half). The even-row lane finishes the left pooled
+        // pixel of the group, the odd-row lane the right one; each sends the partner the row maximum it needs.
+        const bool top = (gy & 1) == 0;
+        const int py = (ty0 + gy) >> 1, px = ((tx0 + gx * 4) >> 1) + (top ? 0 : 1);
+        const bool live = (ty0 + (gy | 1)) < p.dst.H && (tx0 + gx * 4 + (top ? 1 : 3)) < p.dst.W;
+        float pv[COG];
+        unsigned int cd[COG / 4];
+#pragma unroll
+        for (int j4 = 0; j4 < COG / 4; ++j4) cd[j4] = 0u;
+#pragma unroll
+        for (int j = 0; j < COG; ++j) {
+            const int co = cog * COG + j;
+            const float b = bias ? __ldg(bias + co) : 0.f;
+            const float v0 = act_direct(acc[0][j] + b, p.act, p.alpha), v1 = act_direct(acc[1][j] + b, p.act, p.alpha);
+            const float v2 = act_direct(acc[2][j] + b, p.act, p.alpha), v3 = act_direct(acc[3][j] + b, p.act, p.alpha);
+            // row maxima of the two pooled pixels of this thread's row (first maximum wins: strict >)
+            const float mA = v1 > v0 ? v1 : v0, mB = v3 > v2 ? v3 : v2;
+            const int iA = v1 > v0 ? 1 : 0, iB = v3 > v2 ? 1 : 0;
+            const float send_m = top ? mB : mA;
+            const int send_i = top ? iB : iA;
+            const float om = __shfl_xor_sync(0xffffffffu, send_m, 16);
+            const int oi = __shfl_xor_sync(0xffffffffu, send_i, 16);
+            // scan order of the window: (row 0, col 0), (0, 1), (1, 0), (1, 1)
+            const float mt = top ? mA : om, mb = top ? om : mB;
+            const int it = top ? iA : oi, ib = top ? oi : iB;
+            const float m = mb > mt ? mb : mt;
+            const unsigned int arg = mb > mt ? (2u + (unsigned)ib) : (unsigned)it;
+            pv[j] = m;
+            cd[j >> 2] |= (arg | (m > 0.f ? 4u : 0u)) << (8 * (j & 3));
+        }
+        if (!live) return;
+        const long long o = (((long long)n * (p.dst.H >> 1) + py) * (p.dst.W >> 1) + px) * COUT + cog * COG;
+        float4* po = reinterpret_cast<float4*>(p.pool + o);
+#pragma unroll
+        for (int j4 = 0; j4 < COG / 4; ++j4) po[j4] = make_float4(pv[4 * j4], pv[4 * j4 + 1], pv[4 * j4 + 2], pv[4 * j4 + 3]);
+        unsigned int* co4 = reinterpret_cast<unsigned int*>(p.code + o);
+#pragma unroll
+        for (int j4 = 0; j4 < COG / 4; ++j4) co4[j4] = cd[j4];
+        return;
+    }
     if (oy >= p.dst.H) return;
     float bv[COG];
 #pragma unroll
@@ -367,12 +413,12 @@ conv_direct_wgrad_kernel(DirectWgradParams p, const float* __restrict__ x, const
         }
 }
 
-template <int CIN, int COUT, int K>
+template <int CIN, int COUT, int K, bool POOL = false>
 int launch_fewin(const DirectParams& p, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
     const size_t smem = sizeof(float) * (K * K * CIN * COUT + CIN * (FH + K - 1) * FXS);
-    NI_CUDA(cudaFuncSetAttribute(conv_fewin_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NI_CUDA(cudaFuncSetAttribute(conv_fewin_kernel<CIN, COUT, K, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ((p.dst.W + FW - 1) / FW) * ((p.dst.H + FH - 1) / FH) * p.n;
-    conv_fewin_kernel<CIN, COUT, K><<<tiles, 256, smem, st>>>(p, x, w, bias, y);
+    conv_fewin_kernel<CIN, COUT, K, POOL><<<tiles, 256, smem, st>>>(p, x, w, bias, y);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
@@ -443,6 +489,7 @@ extern "C" int ni_conv2d_fprop_direct(const ni_conv_desc* d, const float* x, con
     p.dst = TensorView{d->oh, d->ow, d->cout, d->out_pitch, d->out_coff, d->out_mode};
     p.n = d->n; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
     p.act = d->act; p.bias_mod = d->bias_mod; p.alpha = d->act_alpha; p.accumulate = d->accumulate;
+    p.pool = nullptr; p.code = nullptr;
 #define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return launch_fewin<a, b, c>(p, x, w, bias, y, st);
     NI_FEWIN_SHAPES(X)
 #undef X
@@ -451,6 +498,33 @@ extern "C" int ni_conv2d_fprop_direct(const ni_conv_desc* d, const float* x, con
     if (rc) return rc;
 #define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return launch_manyin<a, b, c>(p, x, wr, bias, y, st);
     NI_MANYIN_SHAPES(X)
+#undef X
+    return NI_ERR_UNSUPPORTED;
+}
+
+// Conv2D(few input channels) + bias + activation + MaxPool2D(2x2) in one kernel (models/forensics.py:66-69, first block of the FAN):
+// writes the pooled activation and one code byte per pooled element instead of the full-resolution activation (2.7 GB at 1280 images
+// of 128x128x32 that the stand-alone pooling kernel read back and the pooling backward read again).
+extern "C" int ni_conv2d_pool2_supported(const ni_conv_desc* d) {
+    if (!d || d->n <= 0 || d->stride != 1 || d->kh != d->kw || d->in_mode != NI_MODE_PLAIN || d->out_mode != NI_MODE_PLAIN) return 0;
+    if ((d->oh & 1) || (d->ow & 1) || d->accumulate || d->bias_mod || d->out_coff || d->out_pitch != d->cout) return 0;
+    if (d->act != NI_ACT_LEAKY_RELU && d->act != NI_ACT_RELU) return 0;           // the code byte stores the slope as "value > 0"
+#define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return 1;
+    NI_FEWIN_SHAPES(X)
+#undef X
+    return 0;
+}
+extern "C" int ni_conv2d_pool2_fwd(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* pooled,
+                                   unsigned char* code, cudaStream_t st) {
+    NI_REQUIRE(ni_conv2d_pool2_supported(d) && x && w && pooled && code, "ni_conv2d_pool2_fwd: unsupported problem or null pointer");
+    DirectParams p;
+    p.src = TensorView{d->h, d->w, d->cin, d->in_pitch, d->in_coff, d->in_mode};
+    p.dst = TensorView{d->oh, d->ow, d->cout, d->out_pitch, d->out_coff, d->out_mode};
+    p.n = d->n; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
+    p.act = d->act; p.bias_mod = 0; p.alpha = d->act_alpha; p.accumulate = 0;
+    p.pool = pooled; p.code = code;
+#define X(a, b, c) if (d->cin == a && d->cout == b && d->kh == c) return launch_fewin<a, b, c, true>(p, x, w, bias, nullptr, st);
+    NI_FEWIN_SHAPES(X)
 #undef X
     return NI_ERR_UNSUPPORTED;
 }
@@ -468,6 +542,7 @@ extern "C" int ni_conv2d_dgrad_direct(const ni_conv_desc* d, const float* dy, co
     p.dst = TensorView{d->h, d->w, d->cin, d->in_pitch, d->in_coff, d->in_mode};
     p.n = d->n; p.pad_t = k - 1 - d->pad_t; p.pad_l = k - 1 - d->pad_l; p.pad_mode = NI_PAD_ZERO;
     p.act = NI_ACT_NONE; p.bias_mod = 0; p.alpha = 0.f; p.accumulate = d->accumulate;
+    p.pool = nullptr; p.code = nullptr;
 #define X(a, b, c) if (d->cout == a && d->cin == b && d->kh == c) return launch_manyin<a, b, c>(p, dy, wr, nullptr, dx, st);
     NI_MANYIN_SHAPES(X)
 #undef X

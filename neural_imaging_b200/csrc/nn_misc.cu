@@ -291,6 +291,46 @@ maxpool_act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict
     }
 }
 
+// Backward of (activation + 2x2 max-pool) from the code bytes written by ni_conv2d_pool2_fwd: dx[window position == code & 3] =
+// dy * (code & 4 ? 1 : slope0), zero elsewhere; dbias[c] += sum. Reads 5 B and writes 16 B per pooled element (the float path reads 20).
+__global__ void __launch_bounds__(256)
+maxpool_code_bwd_bias_kernel(const unsigned char* __restrict__ code, const float* __restrict__ dy, float* __restrict__ dx,
+                             float* __restrict__ dbias, int n, int oh, int ow, int c4n, float slope0) {
+    __shared__ float4 red[256];
+    const long long npix = (long long)n * oh * ow;
+    const int c4 = threadIdx.x % c4n, C = c4n * 4;
+    const long long pstride = (long long)gridDim.x * (256 / c4n);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long pix = (long long)blockIdx.x * (256 / c4n) + threadIdx.x / c4n; pix < npix; pix += pstride) {
+        const int ox = (int)(pix % ow), oy = (int)((pix / ow) % oh);
+        const long long nn = pix / ((long long)ow * oh);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + pix * C + c4 * 4));
+        const unsigned int cd = __ldg(reinterpret_cast<const unsigned int*>(code + pix * C + c4 * 4));
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+        float o[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned int b = (cd >> (8 * e)) & 0xffu;
+            const float v = gv[e] * ((b & 4u) ? 1.f : slope0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k][e] = (b & 3u) == (unsigned)k ? v : 0.f;
+            if (e == 0) s.x += v; else if (e == 1) s.y += v; else if (e == 2) s.z += v; else s.w += v;
+        }
+        const long long r0 = ((nn * 2 * oh + 2 * oy) * (2LL * ow) + 2 * ox);
+        const long long r[4] = {r0, r0 + 1, r0 + 2 * ow, r0 + 2 * ow + 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(dx + r[k] * C + c4 * 4) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    }
+    if (!dbias) return;
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < c4n) {
+        float4 t = red[threadIdx.x];
+        for (int j = threadIdx.x + c4n; j < 256; j += c4n) { const float4 u = red[j]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        atomicAdd(dbias + c4 * 4, t.x); atomicAdd(dbias + c4 * 4 + 1, t.y); atomicAdd(dbias + c4 * 4 + 2, t.z); atomicAdd(dbias + c4 * 4 + 3, t.w);
+    }
+}
+
 // ------------------------------------------------------------------ global average pooling (n,h,w,c) <-> (n,c)
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int hw, int c) {
     const int n = blockIdx.x;
@@ -543,6 +583,24 @@ extern "C" int ni_act_bwd_bias(const float* y, float* dy, float* dbias, int n, i
 
 // ni_maxpool2_bwd followed by ni_act_bwd_bias on the pooled layer's own output x (conv -> activation -> pool chains of FAN and the
 // U-Net encoder), as ONE pass where the layout allows it; dbias (c floats, may be null) is overwritten.
+// code / dy: (n, oh, ow, c) pooled layout; dx: (n, 2 oh, 2 ow, c) plain; act: leaky-relu (slope alpha) or relu. dbias is overwritten.
+extern "C" int ni_maxpool2_code_bwd_bias(const unsigned char* code, const float* dy, float* dx, float* dbias, int n, int oh, int ow, int c,
+                                         int act, float alpha, cudaStream_t st) {
+    NI_REQUIRE(code && dy && dx && n >= 0 && oh > 0 && ow > 0 && c > 0 && (c % 4) == 0 && 256 % (c / 4) == 0,
+               "ni_maxpool2_code_bwd_bias: invalid arguments (c must be a multiple of 4 with 256 %% (c/4) == 0)");
+    NI_REQUIRE(act == NI_ACT_LEAKY_RELU || act == NI_ACT_RELU, "ni_maxpool2_code_bwd_bias: activation must be leaky-relu or relu");
+    if (dbias) NI_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * c, st));
+    const long long npix = (long long)n * oh * ow;
+    if (npix == 0) return NI_OK;
+    const int c4n = c / 4, ppb = 256 / c4n;
+    long long blocks = (npix + ppb - 1) / ppb;
+    const long long cap = 16LL * ni_num_sms();
+    if (blocks > cap) blocks = cap;
+    maxpool_code_bwd_bias_kernel<<<(unsigned)blocks, 256, 0, st>>>(code, dy, dx, dbias, n, oh, ow, c4n, act == NI_ACT_RELU ? 0.f : alpha);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    return NI_OK;
+}
+
 extern "C" int ni_maxpool2_act_bwd_bias(const float* x, const float* dy, const float* add, float* dx, float* dbias, int n, int h, int w, int c,
                                         int same, int x_pitch, int x_coff, int dy_pitch, int dy_coff, int add_pitch, int add_coff, int dx_pitch,
                                         int dx_coff, int act, float alpha, cudaStream_t st) {

@@ -45,6 +45,7 @@ class FAN(TFModel):
 
         rng = np.random.RandomState(seed)
         self._seed, self._dropout_calls = int(seed or 0), 0
+        self._fuse_pool = True          # tests switch it off to compare with the conv -> max-pool kernel pair
         st = self._store = nn.ParamStore()
         act = self._h.activation
         # constrained residual filter: trainable raw kernel (5,5,3,3), normalised on every call (models/layers.py:36-53)
@@ -93,9 +94,17 @@ class FAN(TFModel):
         cur, ch, cw = r, h, w
         for i, conv in enumerate(self._convs):
             d = conv.desc(m, ch, cw)
-            c = conv.fprop(cur, ws.get('c%d' % i, (m, ch, cw, conv.cout)), d)
             p = ws.get('p%d' % i, (m, ch // 2, cw // 2, conv.cout))
-            L.ni_maxpool2_fwd(ptr(c), ptr(p), m, ch, cw, conv.cout, 0, conv.cout, 0, conv.cout, 0, s)
+            if self._fuse_pool and L.ni_conv2d_pool2_supported(ctypes.byref(d)):
+                # conv + bias + activation + max-pool in one kernel: pooled output + one code byte per pooled element (arg-max position,
+                # activation slope) instead of the full-resolution activation (first block: 2.7 GB at 1280 images)
+                code = ws.get('code%d' % i, p.shape, torch.uint8)
+                L.ni_conv2d_pool2_fwd(ctypes.byref(d), ptr(cur), ptr(conv.w.value), conv._bias_ptr(), ptr(p), ptr(code), s)
+                c = None
+                acts['code%d' % i] = code
+            else:
+                c = conv.fprop(cur, ws.get('c%d' % i, (m, ch, cw, conv.cout)), d)
+                L.ni_maxpool2_fwd(ptr(c), ptr(p), m, ch, cw, conv.cout, 0, conv.cout, 0, conv.cout, 0, s)
             acts['c%d' % i], acts['p%d' % i], descs['c%d' % i] = c, p, d
             cur, ch, cw = p, ch // 2, cw // 2
         d = self._conv1x1.desc(m, ch, cw)
@@ -182,8 +191,12 @@ class FAN(TFModel):
             d = descs['c%d' % i]
             dc = ws.get('dc%d' % i, (m, d.oh, d.ow, conv.cout))
             # pool backward + activation backward + bias gradient of conv i in one pass
-            L.ni_maxpool2_act_bwd_bias(ptr(acts['c%d' % i]), ptr(dp), None, ptr(dc), conv.bias_grad_ptr(), m, d.oh, d.ow, conv.cout, 0,
-                                       conv.cout, 0, conv.cout, 0, 0, 0, conv.cout, 0, d.act, d.act_alpha, s)
+            if acts['c%d' % i] is None:
+                L.ni_maxpool2_code_bwd_bias(ptr(acts['code%d' % i]), ptr(dp), ptr(dc), conv.bias_grad_ptr(), m, d.oh // 2, d.ow // 2, conv.cout,
+                                            d.act, d.act_alpha, s)
+            else:
+                L.ni_maxpool2_act_bwd_bias(ptr(acts['c%d' % i]), ptr(dp), None, ptr(dc), conv.bias_grad_ptr(), m, d.oh, d.ow, conv.cout, 0,
+                                           conv.cout, 0, conv.cout, 0, 0, 0, conv.cout, 0, d.act, d.act_alpha, s)
             x_in = acts['p%d' % (i - 1)] if i > 0 else acts['r']
             dp = ws.get('dp%d' % (i - 1), (m, d.h, d.w, conv.cin)) if i > 0 else ws.get('dr', (m, h, w, 3))
             conv.bprop(x_in, acts['c%d' % i], dc, dp, d, act_bias_done=True)

@@ -91,6 +91,35 @@ def test_fan_forward_backward(kw):
         assert_parity(g[name], ref, out[torch.float32][3][name], tol=5e-5, slack=6.0, what='FAN grad ' + name)
 
 
+@pytest.mark.parametrize('ps', [32, 44])
+def test_fan_fused_first_block_equals_the_kernel_pair(ps):
+    """conv 5x5 3->32 + bias + LeakyReLU + MaxPool 2x2 in one kernel (ni_conv2d_pool2_fwd, code byte instead of the full-resolution
+    activation; backward ni_maxpool2_code_bwd_bias) against the conv -> ni_maxpool2_fwd / ni_maxpool2_act_bwd_bias pair: same
+    accumulation order, so the pooled activations and the routed gradients are bit-equal; the bias gradient is a different
+    reduction tree (tight tolerance)."""
+    from neural_imaging_b200.models import forensics
+    from neural_imaging_b200.tensor import as_device
+    rs = np.random.RandomState(5)
+    m = 5
+    x = as_device(rs.uniform(size=(m, ps, ps, 3)).astype(np.float32))
+    labels = as_device(rs.randint(0, 5, size=(m,)).astype(np.int32), torch.int32)
+    res = []
+    for fuse in (True, False):
+        fan = forensics.FAN(n_classes=5, patch_size=ps, seed=3)
+        fan._fuse_pool = fuse
+        probs, loss, dlogits = fan.forward_loss(x, labels)
+        acts = fan._saved[0]
+        assert (acts['c0'] is None) == fuse and ('code0' in acts) == fuse
+        dx = fan.backward(dlogits, need_dx=True)
+        res.append((probs.cpu().numpy().copy(), acts['p0'].cpu().numpy().copy(), dx.cpu().numpy().copy(), _grads(fan._store)))
+    (pa, p0a, dxa, ga), (pb, p0b, dxb, gb) = res
+    assert np.array_equal(p0a, p0b) and np.array_equal(pa, pb)
+    assert np.array_equal(dxa, dxb)
+    for k in ga:            # (filter gradients: split-K atomics, bias gradients: another reduction tree -> not bit-reproducible)
+        scale = float(np.abs(gb[k]).max()) + 1e-12
+        assert float(np.abs(ga[k] - gb[k]).max()) <= 2e-5 * scale, k
+
+
 @pytest.mark.parametrize('train_nip', [True, False])
 def test_joint_training_step(train_nip):
     """ManipulationClassification.training_step: losses, every gradient and the Adam update vs the oracle."""

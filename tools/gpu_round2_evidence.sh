@@ -19,5 +19,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:djpeg -s 3 -c 2 -o $O/prof_djpeg -f python tools/profile_djpeg.py 1280 1 > $O/ncu_djpeg.log 2>&1; echo "ncu djpeg exit $?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_gemm -s 2 -c 1 -o $O/prof_conv_fprop -f python tools/profile_conv.py 2 > $O/ncu_conv.log 2>&1; echo "ncu conv fprop exit $?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_wgrad -s 2 -c 1 -o $O/prof_conv_wgrad -f python tools/profile_conv.py 2 >> $O/ncu_conv.log 2>&1; echo "ncu conv wgrad exit $?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"manip_stack|cconv5" -c 20 -o $O/prof_manip -f python tools/profile_manip.py 1 > $O/ncu_manip.log 2>&1; echo "ncu manip exit $?"
+timeout 300 ncu --set full --clock-control none -k regex:"manip_stack|cconv5" -c 5 -o $O/prof_manip -f python tools/profile_manip.py 0 > $O/ncu_manip.log 2>&1; echo "ncu manip exit $?"
+# gpurun copies back at most 64 MiB: summarise the captures on the box and drop the raw reports that do not fit
+for f in prof_djpeg prof_conv_fprop prof_conv_wgrad prof_manip; do
+  ncu -i $O/$f.ncu-rep --page raw --csv > $O/$f.raw.csv 2>/dev/null
+done
+du -sm gpurun_out | tail -1
+while [ $(du -sm gpurun_out | cut -f1) -gt 58 ]; do big=$(ls -S $O/*.ncu-rep 2>/dev/null | head -1); [ -z "$big" ] && break; echo "dropping $big (raw CSV kept)"; rm -f $big; done
 ls -la $O | tail -30

@@ -33,8 +33,11 @@ cases = OrderedDict([
 ])
 res = {}
 for name, (fn, nbytes, flop) in cases.items():
-    for _ in range(3):
+    for _ in range(3 if iters > 0 else 0):
         fn()
+    if iters == 0:          # ncu capture mode: every kernel exactly once, no timing
+        fn()
+        continue
     ts = []
     for _ in range(iters):
         flush.zero_()
