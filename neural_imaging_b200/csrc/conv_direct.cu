@@ -64,107 +64,41 @@ __device__ __forceinline__ bool view_vec4(const TensorView& v) { return v.mode =
 // at full FMA rate) whether they are broadcasts or not; these kernels move 0.5 - 1.5 B per FMA and sit at 30 - 34 TFLOP/s.
 // Measured alternative: weights in __constant__ memory indexed by the (rolled) filter-row loop compile to per-thread LDC
 // loads, which were no faster (3.06 vs 2.99 ms for the FAN 3->32 fprop) and add a global staging buffer -- not kept.
-constexpr int FW = 64, FH = 8;     // output tile, 256 threads = 128 pixel groups x 2 channel halves
+constexpr int FW = 64, FH = 8;     // output tile, 256 threads = 64 pixel groups (2 rows x 4 columns) x 4 channel quarters
 constexpr int FXS = FW + 4;        // input tile row stride (floats): room for the 8-wide window of the last pixel group
 
+// Persistent: a CTA loads the filter once and walks over tiles with the NEXT tile's input in flight (cp.async into the other buffer)
+// while it computes the current one. The one-tile-per-CTA version spent ~1/3 of its life in the load phase (filter + tile through 4-byte
+// cp.async, then wait_all: issue slots 63 % busy, long-scoreboard the top stall, ncu r2_prof_fan_first). Thread = 2 x 4 pixels x COUT/4
+// channels: 14 LDS.128 per 320 FMAs (was 22 with 1 x 4 pixels x COUT/2), and a 2x2 pooling window lives inside one thread.
 template <int CIN, int COUT, int K, bool POOL>
 __global__ void __launch_bounds__(256, 2)
 conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y) {
-    static_assert(K <= 5 && COUT % 8 == 0, "window of 4 + K - 1 <= 8 input columns; two channel halves of whole float4s");
-    constexpr int COG = COUT / 2, IH = FH + K - 1;
+    static_assert(K <= 5 && COUT % 16 == 0, "window of 4 + K - 1 <= 8 input columns; four channel quarters of whole float4s");
+    constexpr int COG = COUT / 4, IH = FH + K - 1, XT = CIN * IH * FXS;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;                              // [K*K][CIN][COUT]
-    float* sx = smem + K * K * CIN * COUT;         // [CIN][IH][FXS]
+    float* sx0 = smem + K * K * CIN * COUT;        // 2 x [CIN][IH][FXS]
     const int tid = threadIdx.x;
     const int tiles_x = (p.dst.W + FW - 1) / FW, tiles_y = (p.dst.H + FH - 1) / FH;
-    const int tx0 = (blockIdx.x % tiles_x) * FW, ty0 = ((blockIdx.x / tiles_x) % tiles_y) * FH, n = blockIdx.x / (tiles_x * tiles_y);
+    const int tiles_total = tiles_x * tiles_y * p.n;
+
+    auto load_tile = [&](int tile, float* sx) {
+        const int tx0 = (tile % tiles_x) * FW, ty0 = ((tile / tiles_x) % tiles_y) * FH, n = tile / (tiles_x * tiles_y);
+        for (int i = tid; i < XT; i += 256) {
+            const int c = i % CIN, px = (i / CIN) % FXS, py = i / (CIN * FXS);
+            int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+            if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
+            const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
+            cp_async4_zfill(sx + (c * IH + py) * FXS + px, in ? x + view_addr(p.src, n, sy, sxx, c) : x, in);
+        }
+    };
 
     for (int i = tid; i < K * K * CIN * COUT; i += 256) cp_async4_zfill(sw + i, w + i, true);   // w: slice of the flat parameter buffer (4-byte aligned)
-    for (int i = tid; i < IH * FXS * CIN; i += 256) {
-        const int c = i % CIN, px = (i / CIN) % FXS, py = i / (CIN * FXS);
-        int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
-        if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
-        const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
-        cp_async4_zfill(sx + (c * IH + py) * FXS + px, in ? x + view_addr(p.src, n, sy, sxx, c) : x, in);
-    }
-    cp_async_wait();
-    __syncthreads();
+    if ((int)blockIdx.x < tiles_total) load_tile(blockIdx.x, sx0);
 
-    const int pg = tid & 127, cog = tid >> 7;      // warp-uniform channel half: weight loads are pure broadcasts
-    const int gx = pg & 15, gy = pg >> 4;
-    float acc[4][COG];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int j = 0; j < COG; ++j) acc[q][j] = 0.f;
-#pragma unroll 1
-    for (int a = 0; a < K; ++a) {
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float4* xp = reinterpret_cast<const float4*>(sx + (ci * IH + gy + a) * FXS + gx * 4);
-            const float4 x0 = xp[0], x1 = xp[1];
-            const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-            for (int b = 0; b < K; ++b) {
-                const float4* wp = reinterpret_cast<const float4*>(sw + ((a * K + b) * CIN + ci) * COUT + cog * COG);
-#pragma unroll
-                for (int j4 = 0; j4 < COG / 4; ++j4) {
-                    const float4 wv = wp[j4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        acc[q][4 * j4] = fmaf(xr[q + b], wv.x, acc[q][4 * j4]);
-                        acc[q][4 * j4 + 1] = fmaf(xr[q + b], wv.y, acc[q][4 * j4 + 1]);
-                        acc[q][4 * j4 + 2] = fmaf(xr[q + b], wv.z, acc[q][4 * j4 + 2]);
-                        acc[q][4 * j4 + 3] = fmaf(xr[q + b], wv.w, acc[q][4 * j4 + 3]);
-                    }
-                }
-            }
-        }
-    }
-    const int oy = ty0 + gy;
-    if (POOL) {
-        // bias + activation, then the 2x2 max-pool: columns pair up inside the thread (pixels 0,1 | 2,3), rows across lanes l and l ^ 16
-        // (the lane holding the row below / above, same column group, same channel half). The even-row lane finishes the left pooled
-        // pixel of the group, the odd-row lane the right one; each sends the partner the row maximum it needs.
-        const bool top = (gy & 1) == 0;
-        const int py = (ty0 + gy) >> 1, px = ((tx0 + gx * 4) >> 1) + (top ? 0 : 1);
-        const bool live = (ty0 + (gy | 1)) < p.dst.H && (tx0 + gx * 4 + (top ? 1 : 3)) < p.dst.W;
-        float pv[COG];
-        unsigned int cd[COG / 4];
-#pragma unroll
-        for (int j4 = 0; j4 < COG / 4; ++j4) cd[j4] = 0u;
-#pragma unroll
-        for (int j = 0; j < COG; ++j) {
-            const int co = cog * COG + j;
-            const float b = bias ? __ldg(bias + co) : 0.f;
-            const float v0 = act_direct(acc[0][j] + b, p.act, p.alpha), v1 = act_direct(acc[1][j] + b, p.act, p.alpha);
-            const float v2 = act_direct(acc[2][j] + b, p.act, p.alpha), v3 = act_direct(acc[3][j] + b, p.act, p.alpha);
-            // row maxima of the two pooled pixels of this thread's row (first maximum wins: strict >)
-            const float mA = v1 > v0 ? v1 : v0, mB = v3 > v2 ? v3 : v2;
-            const int iA = v1 > v0 ? 1 : 0, iB = v3 > v2 ? 1 : 0;
-            const float send_m = top ? mB : mA;
-            const int send_i = top ? iB : iA;
-            const float om = __shfl_xor_sync(0xffffffffu, send_m, 16);
-            const int oi = __shfl_xor_sync(0xffffffffu, send_i, 16);
-            // scan order of the window: (row 0, col 0), (0, 1), (1, 0), (1, 1)
-            const float mt = top ? mA : om, mb = top ? om : mB;
-            const int it = top ? iA : oi, ib = top ? oi : iB;
-            const float m = mb > mt ? mb : mt;
-            const unsigned int arg = mb > mt ? (2u + (unsigned)ib) : (unsigned)it;
-            pv[j] = m;
-            cd[j >> 2] |= (arg | (m > 0.f ? 4u : 0u)) << (8 * (j & 3));
-        }
-        if (!live) return;
-        const long long o = (((long long)n * (p.dst.H >> 1) + py) * (p.dst.W >> 1) + px) * COUT + cog * COG;
-        float4* po = reinterpret_cast<float4*>(p.pool + o);
-#pragma unroll
-        for (int j4 = 0; j4 < COG / 4; ++j4) po[j4] = make_float4(pv[4 * j4], pv[4 * j4 + 1], pv[4 * j4 + 2], pv[4 * j4 + 3]);
-        unsigned int* co4 = reinterpret_cast<unsigned int*>(p.code + o);
-#pragma unroll
-        for (int j4 = 0; j4 < COG / 4; ++j4) co4[j4] = cd[j4];
-        return;
-    }
-    if (oy >= p.dst.H) return;
+    const int pg = tid & 63, cog = tid >> 6;       // warp-uniform channel quarter: weight loads are pure broadcasts
+    const int gx = pg & 15, gy = (pg >> 4) * 2;    // first of the thread's two rows
     float bv[COG];
 #pragma unroll
     for (int j = 0; j < COG; ++j) {
@@ -172,26 +106,114 @@ conv_fewin_kernel(DirectParams p, const float* __restrict__ x, const float* __re
         bv[j] = bias ? __ldg(bias + (p.bias_mod > 0 ? co % p.bias_mod : co)) : 0.f;
     }
     const bool vec = view_vec4(p.dst);
+
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, buf ^= 1) {
+        cp_async_wait();
+        __syncthreads();        // this tile (and the filter) landed; every thread is done with the buffer the next copy overwrites
+        if (tile + (int)gridDim.x < tiles_total) load_tile(tile + gridDim.x, sx0 + (buf ^ 1) * XT);
+        const float* sx = sx0 + buf * XT;
+        const int tx0 = (tile % tiles_x) * FW, ty0 = ((tile / tiles_x) % tiles_y) * FH, n = tile / (tiles_x * tiles_y);
+
+        float acc[2][4][COG];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int ox = tx0 + gx * 4 + q;
-        if (ox >= p.dst.W) continue;
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int j = 0; j < COG; ++j) acc[q][j] = act_direct(acc[q][j] + bv[j], p.act, p.alpha);
-        if (vec) {
-            float4* o = reinterpret_cast<float4*>(y + view_addr(p.dst, n, oy, ox, cog * COG));
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j4 = 0; j4 < COG / 4; ++j4) {
-                float4 r = make_float4(acc[q][4 * j4], acc[q][4 * j4 + 1], acc[q][4 * j4 + 2], acc[q][4 * j4 + 3]);
-                if (p.accumulate) { const float4 old = o[j4]; r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
-                o[j4] = r;
+                for (int j = 0; j < COG; ++j) acc[r][q][j] = 0.f;
+#pragma unroll 1
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                float xr[2][8];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float4* xp = reinterpret_cast<const float4*>(sx + (ci * IH + gy + r + a) * FXS + gx * 4);
+                    const float4 x0 = xp[0], x1 = xp[1];
+                    xr[r][0] = x0.x; xr[r][1] = x0.y; xr[r][2] = x0.z; xr[r][3] = x0.w;
+                    xr[r][4] = x1.x; xr[r][5] = x1.y; xr[r][6] = x1.z; xr[r][7] = x1.w;
+                }
+#pragma unroll
+                for (int b = 0; b < K; ++b) {
+                    const float4* wp = reinterpret_cast<const float4*>(sw + ((a * K + b) * CIN + ci) * COUT + cog * COG);
+#pragma unroll
+                    for (int j4 = 0; j4 < COG / 4; ++j4) {
+                        const float4 wv = wp[j4];
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                acc[r][q][4 * j4] = fmaf(xr[r][q + b], wv.x, acc[r][q][4 * j4]);
+                                acc[r][q][4 * j4 + 1] = fmaf(xr[r][q + b], wv.y, acc[r][q][4 * j4 + 1]);
+                                acc[r][q][4 * j4 + 2] = fmaf(xr[r][q + b], wv.z, acc[r][q][4 * j4 + 2]);
+                                acc[r][q][4 * j4 + 3] = fmaf(xr[r][q + b], wv.w, acc[r][q][4 * j4 + 3]);
+                            }
+                    }
+                }
+            }
+        }
+        const int oy = ty0 + gy, ox0 = tx0 + gx * 4;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < COG; ++j) acc[r][q][j] = act_direct(acc[r][q][j] + bv[j], p.act, p.alpha);
+        if constexpr (POOL) {
+            // 2x2 max-pool inside the thread: pooled pixels (columns 0,1 | 2,3) of its row pair; first maximum in scan order
+            // (row 0 col 0, (0,1), (1,0), (1,1)) wins, as in ni_maxpool2_fwd / tf.nn.max_pool's gradient routing
+            if (oy + 1 >= p.dst.H) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (ox0 + 2 * h + 1 >= p.dst.W) continue;
+                float pv[COG];
+                unsigned int cd[COG / 4];
+#pragma unroll
+                for (int j4 = 0; j4 < COG / 4; ++j4) cd[j4] = 0u;
+#pragma unroll
+                for (int j = 0; j < COG; ++j) {
+                    float m = acc[0][2 * h][j];
+                    unsigned int arg = 0u;
+                    if (acc[0][2 * h + 1][j] > m) { m = acc[0][2 * h + 1][j]; arg = 1u; }
+                    if (acc[1][2 * h][j] > m) { m = acc[1][2 * h][j]; arg = 2u; }
+                    if (acc[1][2 * h + 1][j] > m) { m = acc[1][2 * h + 1][j]; arg = 3u; }
+                    pv[j] = m;
+                    cd[j >> 2] |= (arg | (m > 0.f ? 4u : 0u)) << (8 * (j & 3));
+                }
+                const long long o = (((long long)n * (p.dst.H >> 1) + (oy >> 1)) * (p.dst.W >> 1) + (ox0 >> 1) + h) * COUT + cog * COG;
+                float4* po = reinterpret_cast<float4*>(p.pool + o);
+#pragma unroll
+                for (int j4 = 0; j4 < COG / 4; ++j4) po[j4] = make_float4(pv[4 * j4], pv[4 * j4 + 1], pv[4 * j4 + 2], pv[4 * j4 + 3]);
+                unsigned int* co4 = reinterpret_cast<unsigned int*>(p.code + o);
+#pragma unroll
+                for (int j4 = 0; j4 < COG / 4; ++j4) co4[j4] = cd[j4];
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < COG; ++j) {
-                float* o = y + view_addr(p.dst, n, oy, ox, cog * COG + j);
-                *o = p.accumulate ? *o + acc[q][j] : acc[q][j];
+        for (int r = 0; r < 2; ++r) {
+            if (oy + r >= p.dst.H) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ox = ox0 + q;
+                if (ox >= p.dst.W) continue;
+                if (vec) {
+                    float4* o = reinterpret_cast<float4*>(y + view_addr(p.dst, n, oy + r, ox, cog * COG));
+#pragma unroll
+                    for (int j4 = 0; j4 < COG / 4; ++j4) {
+                        float4 v = make_float4(acc[r][q][4 * j4], acc[r][q][4 * j4 + 1], acc[r][q][4 * j4 + 2], acc[r][q][4 * j4 + 3]);
+                        if (p.accumulate) { const float4 old = o[j4]; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+                        o[j4] = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < COG; ++j) {
+                        float* o = y + view_addr(p.dst, n, oy + r, ox, cog * COG + j);
+                        *o = p.accumulate ? *o + acc[r][q][j] : acc[r][q][j];
+                    }
+                }
             }
+        }
         }
     }
 }
@@ -278,6 +300,111 @@ conv_manyin_kernel(DirectParams p, const float* __restrict__ x, const float* __r
             t = act_direct(t, p.act, p.alpha);
             float* o = y + view_addr(p.dst, n, oy, ox, j);
             *o = p.accumulate ? *o + t : t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ many input channels, <= 4 outputs
+// The input gradient of the FAN front end (5x5, 32 -> 3 at 1280 x 128 x 128: 100 GFLOP with three outputs per pixel). With so few
+// outputs per pixel a thread needs many pixels to amortise a weight operand: thread = 8 rows x 2 columns x COUT accumulators, the K x 4 x
+// COUT weights of a (filter column, channel quad) live in registers while the thread streams its (8 + K - 1)-row input column through
+// them: 39 LDS.128 per 960 FMAs (0.65 B per FMA; conv_manyin_kernel: 1.5). Persistent CTA per SM, 64 x 64-pixel tiles taken one channel
+// quad at a time (74 KB), the next quad / tile in flight (cp.async into the other buffer) while this one is computed.
+constexpr int M3W = 64, M3H = 64;
+
+template <int CIN, int COUT, int K>
+__global__ void __launch_bounds__(256, 1)
+conv_manyin3_kernel(DirectParams p, const float* __restrict__ x, const float* __restrict__ wr, const float* __restrict__ bias, float* __restrict__ y) {
+    static_assert(CIN % 4 == 0 && COUT <= 4 && (K * 4 * COUT) % 4 == 0, "channel quads; whole float4 weight runs");
+    constexpr int C4 = CIN / 4, IH = M3H + K - 1, IW = M3W + K - 1, R = 8 + K - 1, WN = K * 4 * COUT;
+    constexpr int PLANE = IH * IW * 4;
+    extern __shared__ __align__(16) float smem[];
+    float* sw = smem;                              // [K][C4][K][4][COUT]
+    float* sx0 = smem + K * K * CIN * COUT;        // 2 x [IH][IW][4]
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int tiles_x = (p.dst.W + M3W - 1) / M3W, tiles_y = (p.dst.H + M3H - 1) / M3H;
+    const int tiles_total = tiles_x * tiles_y * p.n;
+    const int my_tiles = (int)blockIdx.x < tiles_total ? (tiles_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int steps = my_tiles * C4;
+    const bool vec_in = view_vec4(p.src);
+
+    auto load_step = [&](int step, float* buf) {
+        const int tile = blockIdx.x + (step / C4) * gridDim.x, c4 = step % C4;
+        const int tx0 = (tile % tiles_x) * M3W, ty0 = ((tile / tiles_x) % tiles_y) * M3H, n = tile / (tiles_x * tiles_y);
+        for (int i = tid; i < IH * IW; i += 256) {
+            const int px = i % IW, py = i / IW;
+            int sy = ty0 + py - p.pad_t, sxx = tx0 + px - p.pad_l;
+            if (p.pad_mode != NI_PAD_ZERO) { sy = mirror_idx(sy, p.src.H, p.pad_mode); sxx = mirror_idx(sxx, p.src.W, p.pad_mode); }
+            const bool in = sy >= 0 && sy < p.src.H && sxx >= 0 && sxx < p.src.W;
+            float* dst = buf + i * 4;
+            if (vec_in) cp_async16_zfill(dst, in ? x + view_addr(p.src, n, sy, sxx, c4 * 4) : x, in);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cp_async4_zfill(dst + e, in ? x + view_addr(p.src, n, sy, sxx, c4 * 4 + e) : x, in);
+            }
+        }
+    };
+
+    for (int i = tid; i < K * K * CIN * COUT / 4; i += 256) cp_async16_zfill(sw + 4 * i, wr + 4 * i, true);
+    if (steps > 0) load_step(0, sx0);
+
+    float acc[8][2][COUT];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) acc[r][h][j] = 0.f;
+
+    for (int step = 0; step < steps; ++step) {
+        cp_async_wait();
+        __syncthreads();        // this quad (and the filter) landed; everybody is done with the buffer the next copy overwrites
+        if (step + 1 < steps) load_step(step + 1, sx0 + ((step + 1) & 1) * PLANE);
+        const float* sx = sx0 + (step & 1) * PLANE;
+        const int c4 = step % C4;
+#pragma unroll 1
+        for (int b = 0; b < K; ++b) {
+            float wv[WN];
+            const float4* wp = reinterpret_cast<const float4*>(sw + (b * C4 + c4) * WN);      // broadcast loads
+#pragma unroll
+            for (int i = 0; i < WN / 4; ++i) { const float4 t = wp[i]; wv[4 * i] = t.x; wv[4 * i + 1] = t.y; wv[4 * i + 2] = t.z; wv[4 * i + 3] = t.w; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 xv[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(sx + ((wrp * 8 + r) * IW + lane + 32 * h + b) * 4);
+#pragma unroll
+                for (int a = 0; a < K; ++a)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const float xe = e == 0 ? xv[r + a].x : (e == 1 ? xv[r + a].y : (e == 2 ? xv[r + a].z : xv[r + a].w));
+#pragma unroll
+                            for (int j = 0; j < COUT; ++j) acc[r][h][j] = fmaf(xe, wv[(a * 4 + e) * COUT + j], acc[r][h][j]);
+                        }
+            }
+        }
+        if (c4 != C4 - 1) continue;
+        const int tile = blockIdx.x + (step / C4) * gridDim.x;
+        const int tx0 = (tile % tiles_x) * M3W, ty0 = ((tile / tiles_x) % tiles_y) * M3H, n = tile / (tiles_x * tiles_y);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int oy = ty0 + wrp * 8 + r;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ox = tx0 + lane + 32 * h;
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) {
+                    float t = acc[r][h][j];
+                    acc[r][h][j] = 0.f;
+                    if (oy >= p.dst.H || ox >= p.dst.W) continue;
+                    if (bias) t += __ldg(bias + (p.bias_mod > 0 ? j % p.bias_mod : j));
+                    t = act_direct(t, p.act, p.alpha);
+                    float* o = y + view_addr(p.dst, n, oy, ox, j);
+                    *o = p.accumulate ? *o + t : t;
+                }
+            }
         }
     }
 }
@@ -415,16 +542,30 @@ conv_direct_wgrad_kernel(DirectWgradParams p, const float* __restrict__ x, const
 
 template <int CIN, int COUT, int K, bool POOL = false>
 int launch_fewin(const DirectParams& p, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (K * K * CIN * COUT + CIN * (FH + K - 1) * FXS);
+    const size_t smem = sizeof(float) * (K * K * CIN * COUT + 2 * CIN * (FH + K - 1) * FXS);
     NI_CUDA(cudaFuncSetAttribute(conv_fewin_kernel<CIN, COUT, K, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ((p.dst.W + FW - 1) / FW) * ((p.dst.H + FH - 1) / FH) * p.n;
-    conv_fewin_kernel<CIN, COUT, K, POOL><<<tiles, 256, smem, st>>>(p, x, w, bias, y);
+    const int grid = tiles < 2 * ni_num_sms() ? tiles : 2 * ni_num_sms();           // persistent: two CTAs per SM (<= 128 registers)
+    conv_fewin_kernel<CIN, COUT, K, POOL><<<grid, 256, smem, st>>>(p, x, w, bias, y);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
 
 template <int CIN, int COUT, int K>
 int launch_manyin(const DirectParams& p, const float* x, const float* wr, const float* bias, float* y, cudaStream_t st) {
+    if constexpr (COUT <= 4) {
+        // 64 x 64 tiles, persistent (conv_manyin3_kernel) when the tile grid is mostly real pixels
+        const long long covered = (long long)((p.dst.W + M3W - 1) / M3W) * M3W * ((p.dst.H + M3H - 1) / M3H) * M3H;
+        if (4 * (long long)p.dst.W * p.dst.H >= 3 * covered) {
+            const size_t smem3 = sizeof(float) * (K * K * CIN * COUT + 2 * (M3H + K - 1) * (M3W + K - 1) * 4);
+            NI_CUDA(cudaFuncSetAttribute(conv_manyin3_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            const int tiles3 = ((p.dst.W + M3W - 1) / M3W) * ((p.dst.H + M3H - 1) / M3H) * p.n;
+            const int grid = tiles3 < ni_num_sms() ? tiles3 : ni_num_sms();
+            conv_manyin3_kernel<CIN, COUT, K><<<grid, 256, smem3, st>>>(p, x, wr, bias, y);
+            NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+            return NI_OK;
+        }
+    }
     const size_t smem = sizeof(float) * (K * K * CIN * COUT + (CIN / 4) * ((MH + K - 1) * (MW + K - 1) * 4 + 4));
     NI_CUDA(cudaFuncSetAttribute(conv_manyin_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ((p.dst.W + MW - 1) / MW) * ((p.dst.H + MH - 1) / MH) * p.n;

@@ -1,4 +1,4 @@
-"""Write profiles/r1_ncu_traffic.json (DRAM bytes per launch, from `ncu --set full` captures) for bench.py's roofline.traffic.
+"""Write profiles/r<round>_ncu_traffic.json (DRAM bytes per launch, from `ncu --set full` captures) for bench.py's roofline.traffic.
 usage: python tools/ncu_traffic.py <djpeg.ncu-rep> <conv.ncu-rep> [out.json]"""
 import csv, io, json, subprocess, sys
 
