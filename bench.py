@@ -149,6 +149,9 @@ class EventProfiler:
         if name == 'ni_manip_stack_pool2_bwd':          # read 3 pooled gradient slots (9 B/px) + mask, read + write dY (24 B/px)
             b, h, w = args[3], args[4], args[5]
             return ('byte', 34.0 * b * h * w)
+        if name == 'ni_maxpool2_code_bwd_bias':         # read the code byte + d(pooled), write dy (full resolution)
+            n, oh, ow, c = args[4], args[5], args[6], args[7]
+            return ('byte', n * oh * ow * c * (1.0 + 4.0 + 16.0))
         if name in ('ni_cconv5_fwd', 'ni_cconv5_bwd_data', 'ni_cconv5_bwd_filter'):      # 225 MAC per pixel: FP32-FMA bound, not HBM (AI 18.8 flop/B)
             n, h, w = args[3], args[4], args[5]
             return ('flop', 2.0 * 225 * n * h * w)
@@ -315,6 +318,8 @@ def run_ours(args, rank, world, local_rank):
         if r['kind'] == 'byte' and r['ms'] > 0:
             e['gbs'] = r['work'] / (r['ms'] * 1e-3) / 1e9
             e['frac_of_hbm_peak'] = e['gbs'] / pk['hbm_gbs']
+        if _bound_of(name):
+            e['bound'] = _bound_of(name)
         kernels.append(e)
     conv = [k for k in kernels if k['entry'].startswith(('ni_conv2d_', 'ni_cconv5_'))]       # every convolution launch, incl. the constrained 5x5 3->3 filter
     conv_ms = sum(k['ms_per_step'] for k in conv)
@@ -352,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
                           'bytes_per_launch_basis': '24 B/pixel (read x + write y); the two launches of the step (256 x 256x256 at q=80, 1280 x 128x128 at q=50) averaged; '
                                                     'timed inside the step (inputs partly L2-resident); tools/profile_djpeg.py times it alone with L2 flushed',
                           'peak_source': pk['source']}
-    lat = next((k for k in kernels if k['entry'] == 'ni_latent_softcodebook_fwd'), None)
+    lat = next((k for k in kernels if k['entry'] in ('ni_latent_quantise_fwd', 'ni_latent_softcodebook_fwd')), None)
     metric = METRIC if not c5 else 'patches_per_sec_unet_twitterdcn_fan_train_step'
     workload = ('BASELINE config 4: UNet(128x128x4 raw) -> [native,sharpen,resample,gaussian,jpeg80] -> avgpool2 -> dJPEG(50,soft) -> FAN(5 classes); '
                 'fwd+bwd+Adam, trainable {fan,nip}, lambda_nip=0.1') if not c5 else \
@@ -455,6 +460,24 @@ def _conv_roofline(agg, steps, prof_ms, pk):
             'peak_source': pk['source'], 'note': 'FP32 results (1e-5 parity) => 3xTF32: 1/6 of the bf16 peak is the ceiling of an ideal kernel'}
 
 
+# What bounds each entry point (ncu evidence: profiles/r2_*_ncu.txt). The fused stencil kernels move so few bytes per pixel BY DESIGN
+# (fusion removed the intermediate tensors) that instruction issue, not HBM, is their limit: their gbs figure is informational.
+BOUND = {'ni_manip_stack_pool2_fwd': 'fp32-issue (four fused stencils + pool per pass; issue slots 81 % busy, DRAM = algorithmic)',
+         'ni_manip_stack_pool2_bwd': 'fp32-issue / latency (issue slots 57 % busy, 59 registers)',
+         'ni_djpeg_fwd': 'hbm', 'ni_djpeg_bwd': 'fp32-issue (recomputes the forward chain: ~190 thread-instructions per pixel)',
+         'ni_maxpool2_act_bwd_bias': 'hbm', 'ni_maxpool2_fwd': 'hbm', 'ni_act_bwd_bias': 'hbm', 'ni_maxpool2_code_bwd_bias': 'hbm',
+         'ni_avgpool_fwd': 'hbm', 'ni_avgpool_bwd': 'hbm', 'ni_adam_keras': 'hbm', 'ni_adam_keras_dev': 'hbm',
+         'ni_cconv5_fwd': 'fp32-fma', 'ni_cconv5_bwd_data': 'fp32-fma', 'ni_cconv5_bwd_filter': 'fp32-fma', 'ni_conv2d_pool2_fwd': 'fp32-fma'}
+
+
+def _bound_of(name):
+    if name in BOUND:
+        return BOUND[name]
+    if name.startswith('ni_conv2d_'):
+        return 'tensor (3xTF32) / fp32-fma for the 3-, 4- and 12-channel layers'
+    return None
+
+
 def _kernel_list(agg, steps, prof_ms, pk):
     out = []
     for name, r in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])[:10]:
@@ -464,6 +487,8 @@ def _kernel_list(agg, steps, prof_ms, pk):
         if r['kind'] == 'byte' and r['ms'] > 0:
             e['gbs'] = r['work'] / (r['ms'] * 1e-3) / 1e9
             e['frac_of_hbm_peak'] = e['gbs'] / pk['hbm_gbs']
+        if _bound_of(name):
+            e['bound'] = _bound_of(name)
         out.append(e)
     return out
 
@@ -642,13 +667,13 @@ def run_c3(args, rank, world, local_rank):
     lat = {k: agg[k] for k in agg if k.startswith('ni_latent_') or k == 'ni_entropy_from_hist'}
     nz = bl * (RAW // 8) * (RAW // 8) * 32
     lat_ms = {k: r['ms'] / max(r['calls'], 1) for k, r in lat.items()}
-    fwd_ms = lat_ms.get('ni_latent_softcodebook_fwd')
+    fwd_ms = lat_ms.get('ni_latent_quantise_fwd', lat_ms.get('ni_latent_softcodebook_fwd'))
     extra = {'config': {'workload': 'BASELINE config 3: TwitterDCN-32C (2.53 M parameters) training step: l2_loss (sum) + 250 x entropy of the batch-global soft '
                                     'histogram (float64 latent path), Keras Adam, 128x128x3 images', 'name': 'c3', 'global_batch': args.batch, 'per_gpu_batch': bl,
                         'parallelism': 'dp%d (32-double histogram all-reduce before the entropy + gradient all-reduce)' % world,
                         'l2': 'activations of a step (GBs) >> 126 MB L2'},
              'roofline': _conv_roofline(agg, args.steps, prof_ms, pk),
-             'roofline_latent': {'kernel': 'latent_softcodebook_fwd_kernel', 'bound': 'hbm', 'unit': 'GB/s', 'ms_per_launch': fwd_ms,
+             'roofline_latent': {'kernel': 'latent quantisation forward (ni_latent_quantise_fwd: scale, soft code book in float64, hard value, soft histogram)', 'bound': 'hbm', 'unit': 'GB/s', 'ms_per_launch': fwd_ms,
                                  'algorithmic_bytes_per_launch': 8.0 * nz, 'achieved': (8.0 * nz / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
                                  'peak': pk['hbm_gbs'], 'frac': (8.0 * nz / (fwd_ms * 1e-3) / 1e9 / pk['hbm_gbs']) if fwd_ms else None,
                                  'note': '4 B read + 4 B written per latent value; {} values per launch: a few MB, i.e. latency- not bandwidth-sized at this batch '

@@ -740,11 +740,31 @@ __global__ void s2d2_kernel(const float* __restrict__ x, float* __restrict__ y, 
         *o = v;
     }
 }
-// plain (n, 2*h2, 2*w2, c) <-> deep (n, h2, w2, 4c); inverse = 0: deep <- plain, 1: plain (+)= deep. c % 4 == 0.
+// channel counts that are not multiples of 4 (the 3-channel image end of the DCN encoder): one element per thread, indexed by the
+// PLAIN position so that both sides are read / written in runs of c (plain) and c (deep) floats
+__global__ void s2d2_scalar_kernel(float* __restrict__ x, float* __restrict__ y, long long total, int h2, int w2, int c, int inverse, int accumulate) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cc = (int)(t % c);
+    long long r = t / c;
+    const int X = (int)(r % (2 * w2)); r /= 2 * w2;
+    const int Y = (int)(r % (2 * h2));
+    const long long n = r / (2 * h2);
+    const int blk = (Y & 1) * 2 + (X & 1);
+    const long long deep = (((n * h2 + (Y >> 1)) * (long long)w2 + (X >> 1)) * 4 + blk) * c + cc;
+    if (!inverse) y[deep] = x[t];
+    else x[t] = accumulate ? x[t] + y[deep] : y[deep];
+}
+// plain (n, 2*h2, 2*w2, c) <-> deep (n, h2, w2, 4c); inverse = 0: deep <- plain, 1: plain (+)= deep.
 extern "C" int ni_space_to_depth2(float* plain, float* deep, int n, int h2, int w2, int c, int inverse, int accumulate, cudaStream_t st) {
-    NI_REQUIRE(plain && deep && n >= 0 && h2 > 0 && w2 > 0 && c > 0 && (c % 4) == 0, "ni_space_to_depth2: invalid arguments");
+    NI_REQUIRE(plain && deep && n >= 0 && h2 > 0 && w2 > 0 && c > 0, "ni_space_to_depth2: invalid arguments");
     const long long total4 = (long long)n * h2 * w2 * c;      // = n*h2*w2*4 blocks * c/4 quads
     if (total4 == 0) return NI_OK;
+    if (c % 4) {
+        s2d2_scalar_kernel<<<ni_cdiv(total4 * 4, kT), kT, 0, st>>>(plain, deep, total4 * 4, h2, w2, c, inverse, accumulate);
+        NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
     s2d2_kernel<<<ni_cdiv(total4, kT), kT, 0, st>>>(plain, deep, total4, h2, w2, c / 4, inverse, accumulate);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;

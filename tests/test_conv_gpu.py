@@ -137,6 +137,59 @@ def test_pitch_offset_and_block2_addressing():
         assert_parity(p.grad.cpu().numpy(), gref[p.name], tol=2e-5, what='parity')
 
 
+@pytest.mark.parametrize('act', ['leaky_relu', None])
+def test_subpixel_conv3_with_depth_to_space_backward(act):
+    """3x3 convolution + depth_to_space(2) epilogue (the DCN decoder's up-sampling layers, models/compression.py:250-262): the backward
+    converts the depth_to_space-addressed gradient to the logical layout once and runs wgrad / dgrad on the dense tcgen05 path."""
+    from neural_imaging_b200 import nn
+    from neural_imaging_b200._lib import MODE_BLOCK2
+    from neural_imaging_b200.tensor import as_device, empty
+    n, h, w, cin, f = 3, 16, 16, 32, 32
+    rs = np.random.RandomState(11)
+    x = rs.normal(size=(n, h, w, cin)).astype(np.float32)
+    st = nn.ParamStore()
+    conv = nn.Conv2D(st, 'up', 3, cin, 4 * f, activation=act, rng=rs, bias_init=rs.normal(size=(4 * f,)).astype(np.float32))
+    st.finalize()
+    d = conv.desc(n, h, w, out_mode=MODE_BLOCK2)
+    xd = as_device(x)
+    y = conv.fprop(xd, empty((n, 2 * h, 2 * w, f)), d)
+    dy = rs.normal(size=(n, 2 * h, 2 * w, f)).astype(np.float32)
+
+    def d2s(t):          # TensorFlow block-major depth_to_space(2) on NHWC
+        return t.reshape(n, h, w, 2, 2, f).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, f)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        P = {k_: torch.tensor(v, dtype=dt, requires_grad=True) for k_, v in st.state_dict().items()}
+        xt = torch.tensor(x, dtype=dt, requires_grad=True)
+        yt = d2s(R.ACT[act](R.conv2d(xt, P['up/kernel'], P['up/bias'])))
+        g = torch.autograd.grad(yt, [xt, P['up/kernel'], P['up/bias']], torch.tensor(dy, dtype=dt))
+        res[dt] = [yt.detach().numpy()] + [t.numpy() for t in g]
+    r64, r32 = res[torch.float64], res[torch.float32]
+    assert_parity(y.cpu().numpy(), r64[0], r32[0], tol=1e-5, what='y')
+    dx = empty(x.shape)
+    conv.bprop(xd, y, as_device(dy), dx, d)
+    assert_parity(dx.cpu().numpy(), r64[1], r32[1], tol=1e-5, slack=6.0, what='dx')
+    assert_parity(conv.w.grad.cpu().numpy(), r64[2], r32[2], tol=2e-5, slack=6.0, what='dw')
+    assert_parity(conv.b.grad.cpu().numpy(), r64[3], r32[3], tol=2e-5, slack=6.0, what='db')
+
+
+def test_space_to_depth2_round_trip_any_channel_count():
+    from neural_imaging_b200 import _lib
+    from neural_imaging_b200.tensor import as_device, empty, ptr, stream
+    L = _lib.lib()
+    rs = np.random.RandomState(3)
+    for c in (3, 8):
+        n, h2, w2 = 2, 5, 7
+        x = rs.normal(size=(n, 2 * h2, 2 * w2, c)).astype(np.float32)
+        ref = x.reshape(n, h2, 2, w2, 2, c).transpose(0, 1, 3, 2, 4, 5).reshape(n, h2, w2, 4 * c)      # tf.nn.space_to_depth(x, 2)
+        xd, deep = as_device(x), empty((n, h2, w2, 4 * c))
+        L.ni_space_to_depth2(ptr(xd), ptr(deep), n, h2, w2, c, 0, 0, stream())
+        assert np.array_equal(deep.cpu().numpy(), ref)
+        back = as_device(np.ones_like(x))
+        L.ni_space_to_depth2(ptr(back), ptr(deep), n, h2, w2, c, 1, 1, stream())
+        assert np.array_equal(back.cpu().numpy(), x + 1.0)
+
+
 def test_mirrored_pad_conv_and_fold():
     """ConstrainedConv2D-style conv: SYMMETRIC pad folded into the addressing; dgrad via padded-domain + ni_pad_fold."""
     from neural_imaging_b200 import _lib, nn
