@@ -21,7 +21,15 @@ struct LatentParams {
     int ncodes;
     double nu, gamma;
     int rounding;      // 0 'soft-codebook', 1 'sin', 2 'soft' (round forward, sine gradient), 3 'identity' (models/layers.py:118-170)
+    int e2;            // nu + 1 when that is a small integer (toolbox default nu = 50 -> 51), else 0: see kernel_weight
+    double c_dlog;     // -(nu + 1) * gamma / nu
 };
+
+LatentParams make_params(long long n, int ncodes, double nu, double gamma, int rounding) {
+    const double e = nu + 1.0;
+    const int e2 = (nu > 0 && e == (double)(int)e && e >= 2.0 && e <= 128.0) ? (int)e : 0;
+    return LatentParams{n, ncodes, nu, gamma, rounding, e2, nu > 0 ? -(nu + 1.0) * gamma / nu : 0.0};
+}
 
 // scalar rounding modes of the Quantization layer on the (float32) scaled latent; period-1 reduction keeps the SFU argument small
 __device__ __forceinline__ float scalar_round(float v, int mode) {
@@ -36,16 +44,25 @@ __device__ __forceinline__ double scalar_round_grad(float v, int mode) {
     return 1.0 - (double)cosf(6.2831855f * f);         // d/dv [v - sin(2 pi v) / 2 pi], also the straight-through gradient of 'soft'
 }
 
-__device__ __forceinline__ double kernel_weight(double diff, double nu, double gamma, double& dlog) {
-    // returns w and d(ln w)/dv (diff = v - c)
-    if (nu > 0) {
-        const double g = gamma * diff;
-        const double base = 1.0 + g * g / nu;
-        dlog = -(nu + 1.0) / 2.0 * (2.0 * gamma * g / nu) / base;
-        return pow(base, -(nu + 1.0) / 2.0);
+// The weight of one (value, code) pair. float64 pow() is ~250 instructions and float64 divisions ~35 each; the kernels used to evaluate
+// 96 (forward) / 128 (backward) weights per latent value with pow + 3 - 5 divisions each (27 ms per step of config 5). With nu + 1 an
+// integer, base^(-(nu+1)/2) = rsqrt(base^(nu+1)): repeated squaring (~9 multiplications for 51) + one rsqrt, <= ~10 ulp from pow's
+// result -- far inside the float64 path's 1e-9 tolerance. WANT_DLOG also returns d(ln w)/dv (one division).
+template <bool WANT_DLOG>
+__device__ __forceinline__ double kernel_weight(double diff, const LatentParams& p, double& dlog) {
+    if (p.nu > 0) {
+        const double g = p.gamma * diff;
+        const double base = 1.0 + g * g / p.nu;
+        if (WANT_DLOG) dlog = p.c_dlog * g / base;               // -(nu+1)/2 * (2 gamma g / nu) / base
+        if (p.e2 > 0) {
+            double r = 1.0, b = base;
+            for (int e = p.e2; e; e >>= 1) { if (e & 1) r *= b; b *= b; }
+            return rsqrt(r);          // base >= 1; r overflows to inf only where the true weight is < 1e-300: rsqrt(inf) = 0
+        }
+        return pow(base, -(p.nu + 1.0) / 2.0);
     }
-    dlog = -2.0 * gamma * diff;
-    return exp(-gamma * diff * diff);
+    if (WANT_DLOG) dlog = -2.0 * p.gamma * diff;
+    return exp(-p.gamma * diff * diff);
 }
 
 // hist_acc[k] += sum_i wn_ik (double atomics, one per block and bin)
@@ -57,8 +74,12 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
     for (int k = threadIdx.x; k < p.ncodes; k += kT) { sh[k] = 0.0; cb[k] = codebook[k]; }
     __syncthreads();
     const float sc = scale ? *scale : 1.f;
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < p.n; i += (long long)gridDim.x * kT) {
-        const float vf = x[i] * sc;                  // float32 multiply, as the reference (latent * scaling_factor)
+    // every lane of a warp runs the same number of iterations (the histogram step below is a warp-wide reduction): the tail is masked
+    const long long stride = (long long)gridDim.x * kT;
+    for (long long i0 = (long long)blockIdx.x * kT; i0 < p.n; i0 += stride) {
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < p.n;
+        const float vf = (live ? x[i] : 0.f) * sc;   // float32 multiply, as the reference (latent * scaling_factor)
         const double v = (double)vf;
         float q;
         if (p.rounding == 0) {
@@ -66,7 +87,7 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
             int arg = 0;
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
+                const double w = kernel_weight<false>(v - (double)cb[k], p, dl) + 1e-72;
                 S += w;
                 soft += w * (double)cb[k];
                 if (w > best) { best = w; arg = k; }
@@ -77,19 +98,23 @@ latent_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
         } else {
             q = scalar_round(vf, p.rounding);
         }
-        out[i] = q;
+        if (live) out[i] = q;
         if (hist_acc) {
             // the reference estimates the entropy of the QUANTISED latent (models/layers.py:200-201): weights at q
             const double vq = (double)q;
             double Sq = 0.0;
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                Sq += kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl) + 1e-72;
+                Sq += kernel_weight<false>(vq - (double)cb[k], p, dl) + 1e-72;
             }
+            const double inv_sq = 1.0 / Sq;
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                const double w = (kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl) + 1e-72) / Sq;
-                if (w > 1e-30) atomicAdd(&sh[k], w);          // contributions below 1e-30 cannot change a float64 sum >= 1e-9 * n
+                double w = live ? (kernel_weight<false>(vq - (double)cb[k], p, dl) + 1e-72) * inv_sq : 0.0;
+                // one shared-memory atomic per warp and bin instead of one per lane (32 lanes on the same address serialise)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&sh[k], w);
             }
         }
     }
@@ -117,35 +142,36 @@ latent_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, 
         const double v = (double)(xf * sc);
         double dsoft = 0.0, dent = 0.0;
         if (p.rounding == 0) {
-            double S = 0.0, A = 0.0;            // S = sum (w+eps), A = sum w a   (a = dlnw/dv)
+            // d soft / dv = sum_k c_k d(wn_k)/dv, wn_k = (w_k + eps) / S: with A = sum w a (a = dlnw/dv), B = sum c w a, C = sum c (w + eps)
+            // this is B / S - C A / S^2 -- one pass over the code book
+            double S = 0.0, A = 0.0, B = 0.0, C = 0.0;
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
+                const double c = (double)cb[k];
+                const double w = kernel_weight<true>(v - c, p, dl);
                 S += w + 1e-72;
                 A += w * dl;
+                B += c * (w * dl);
+                C += c * (w + 1e-72);
             }
-            for (int k = 0; k < p.ncodes; ++k) {
-                double dl;
-                const double w = kernel_weight(v - (double)cb[k], p.nu, p.gamma, dl);
-                dsoft += (double)cb[k] * ((w * dl) / S - (w + 1e-72) * A / (S * S));
-            }
+            const double inv_s = 1.0 / S;
+            dsoft = (B - C * A * inv_s) * inv_s;
         } else {
             dsoft = scalar_round_grad(xf * sc, p.rounding);      // dq/dv of the scalar rounding modes
         }
         if (gh) {
             const double vq = (double)q[i];
-            double Sq = 0.0, Aq = 0.0;
+            double Sq = 0.0, Aq = 0.0, Bq = 0.0, Cq = 0.0;      // same identity with the histogram gradients gh_k in place of c_k
             for (int k = 0; k < p.ncodes; ++k) {
                 double dl;
-                const double w = kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl);
+                const double w = kernel_weight<true>(vq - (double)cb[k], p, dl);
                 Sq += w + 1e-72;
                 Aq += w * dl;
+                Bq += sgh[k] * (w * dl);
+                Cq += sgh[k] * (w + 1e-72);
             }
-            for (int k = 0; k < p.ncodes; ++k) {
-                double dl;
-                const double w = kernel_weight(vq - (double)cb[k], p.nu, p.gamma, dl);
-                dent += sgh[k] * ((w * dl) / Sq - (w + 1e-72) * Aq / (Sq * Sq));
-            }
+            const double inv_sq = 1.0 / Sq;
+            dent = (Bq - Cq * Aq * inv_sq) * inv_sq;
         }
         const double dv = ((g_out ? (double)g_out[i] : 0.0) + dent) * dsoft;
         dx[i] = (float)(dv * (double)sc);
@@ -186,7 +212,7 @@ extern "C" int ni_latent_quantise_fwd(const float* x, const float* scale, const 
     NI_REQUIRE(x && codebook && out && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes && rounding >= 0 && rounding <= 3,
                "ni_latent_quantise_fwd: invalid arguments");
     if (n == 0) return NI_OK;
-    LatentParams p{n, ncodes, nu, gamma, rounding};
+    const LatentParams p = make_params(n, ncodes, nu, gamma, rounding);
     int grid = ni_cdiv(n, kT * 4);
     if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
     latent_fwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, out, hist_acc, p);
@@ -206,7 +232,7 @@ extern "C" int ni_latent_quantise_bwd(const float* x, const float* scale, const 
     NI_REQUIRE(x && codebook && dx && (q || !gh) && n >= 0 && ncodes > 1 && ncodes <= kMaxCodes && rounding >= 0 && rounding <= 3,
                "ni_latent_quantise_bwd: invalid arguments");
     if (n == 0) return NI_OK;
-    LatentParams p{n, ncodes, nu, gamma, rounding};
+    const LatentParams p = make_params(n, ncodes, nu, gamma, rounding);
     int grid = ni_cdiv(n, kT * 4);
     if (grid > 16 * ni_num_sms()) grid = 16 * ni_num_sms();
     latent_bwd_kernel<<<grid, kT, 0, st>>>(x, scale, codebook, q, g_out, gh, dx, dscale_acc, p);

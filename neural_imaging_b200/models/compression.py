@@ -316,13 +316,15 @@ class TwitterDCN(DCN):
         L, ws, s = _lib.lib(), self._ws, stream()
         inp, r1, da, db = saved[tag]
         dr1 = ws.get('dres_r1', r1.shape)
-        cb.bprop(r1, None, g, dr1, db, need_dw=need_dw)
+        # conv_a's activation backward + bias gradient ride in the epilogue of conv_b's input-gradient kernel when the tcgen05 path takes it
+        cb.bprop(r1, None, g, dr1, db, need_dw=need_dw, fuse_prev=ca.fuse_info(r1, need_dw=need_dw))
+        done = cb.fused_prev
         if first_encoder_block:
             dinp = ws.get('dres_in', inp.shape)
-            ca.bprop(inp, r1, dr1, dinp, da, need_dw=need_dw)
+            ca.bprop(inp, r1, dr1, dinp, da, need_dw=need_dw, act_bias_done=done)
             L.ni_leaky_relu_bwd(ptr(saved['net0']), ptr(dinp), ptr(g), g.numel(), 0.2, 1, s)
         else:
-            ca.bprop(inp, r1, dr1, g, da, dx_accumulate=True, need_dw=need_dw)
+            ca.bprop(inp, r1, dr1, g, da, dx_accumulate=True, need_dw=need_dw, act_bias_done=done)
         return g
 
     def _backward(self, dy, entropy_upstream, need_dx, need_dw):

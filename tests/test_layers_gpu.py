@@ -74,6 +74,7 @@ def test_constrained_conv2d():
         layer(np.zeros((1, 8, 8, 4), np.float32))
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize('n,h,w', [(2, 32, 32), (1, 128, 128), (3, 40, 72), (2, 12, 20)])
 def test_constrained_conv_kernels_forward_data_and_filter_gradient(n, h, w):
     """ni_cconv5_fwd / _bwd_data / _bwd_filter (SYMMETRIC pad 2 + VALID 5x5 conv 3 -> 3 with the pad's transpose folded into the input
