@@ -43,6 +43,7 @@ def parse_header(path=HEADER):
     """Return {name: (restype, [argtypes], [argnames])} for every prototype in the header."""
     src = open(path).read()
     src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
+    src = re.sub(r'^[ \t]*#.*$', ' ', src, flags=re.M)            # preprocessor lines
     src = re.sub(r'typedef struct ni_conv_desc \{.*?\} ni_conv_desc;', ' ', src, flags=re.S)
     src = re.sub(r'enum \{.*?\};', ' ', src, flags=re.S)
     protos = {}

@@ -266,6 +266,7 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
         else { q.sb = room >= 1 ? 1 : 0; q.log_sb = 0; }
         static const int defer_env = dev_env("NI_TC_DEFER") ? atoi(dev_env("NI_TC_DEFER")) : -1;
         q.defer_st = defer_env >= 0 ? (defer_env >> (bnt == 128 ? 2 : (bnt == 64 ? 1 : 0))) & 1 : 1;      // bit 0: N = 32, bit 1: N = 64, bit 2: N = 128
+        q.experiment = dev_env("NI_TC_EXP") ? atoi(dev_env("NI_TC_EXP")) : 0;
         const int bstage = tcv3::kGroupBytes;
         // TMEM budget (tcv3::Cfg): N = 128 -> one set of (nacc + 1) accumulators + 2 A slots; N <= 64 -> fixed 4 accumulators per set
         int nacc = want_nacc;

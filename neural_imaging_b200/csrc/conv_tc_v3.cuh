@@ -62,6 +62,7 @@ struct PersistParams {
     int sb, log_sb;                // weight ring: stages (1, 2 or 4 groups) and log2; resident: groups per tile (ring unused)
     int b_resident;                // 1: the CTA's whole weight slice is loaded ONCE and stays in shared memory (single n tile)
     int defer_st;                  // 1: converters complete their tcgen05.st one iteration later (behind the next loads + split)
+    int experiment;                // development builds (-DNI_DEV): bit 0 converters skip LDS + split, bit 1 skip tcgen05.st, bit 2 issuers skip the MMAs, bit 3 skip the LDS only, bit 4 skip the split only, bit 5 epilogue skips its global stores
 };
 
 template <int BNT, int SL = (BNT == 128 ? 2 : 4)>
@@ -87,10 +88,10 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
     const int nsum = ISSUERS == 2 ? 2 * n_iss : p.nacc + 1;         // accumulators the epilogue adds up
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxSA; ++s) { mbar_init(&bar_afull[s], 1); mbar_init(&bar_afree[s], kNCW * 32); }
+        for (int s = 0; s < kMaxSA; ++s) { mbar_init(&bar_afull[s], 1); mbar_init(&bar_afree[s], kNCW); }
         for (int s = 0; s < kMaxGroups; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bfree[s], n_iss); }
-        for (int t = 0; t < SLOTS; ++t) { mbar_init(&bar_tready[t], kNCW * 32); mbar_init(&bar_tfree[t], 1); }
-        for (int a = 0; a < NSETS; ++a) { mbar_init(&bar_accfull[a], n_iss); mbar_init(&bar_accfree[a], 128); }
+        for (int t = 0; t < SLOTS; ++t) { mbar_init(&bar_tready[t], kNCW); mbar_init(&bar_tfree[t], 1); }
+        for (int a = 0; a < NSETS; ++a) { mbar_init(&bar_accfull[a], n_iss); mbar_init(&bar_accfree[a], 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
@@ -207,6 +208,9 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     // last k-iteration of THIS issuer inside the weight group: its commit hands the stage back (bfree counts n_iss arrivals)
                     const bool group_done = !q.b_resident && (it + n_iss >= min((g + 1) << LOG_G, iters));
                     if (elect_one()) {
+#ifdef NI_DEV
+                        if (!(q.experiment & 4))
+#endif
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint64_t dbh = dbh0 + (uint64_t)(ks * 2), dbl = dbl0 + (uint64_t)(ks * 2);   // +32 bytes
@@ -244,12 +248,12 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         for (int tile = blockIdx.x; tile < q.total_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 TCP_START();
-                if (!mbar_try_wait(&bar_afull[s], ph)) {
+                if (!__all_sync(0xffffffffu, mbar_try_wait(&bar_afull[s], ph))) {      // warp-uniform: the arrivals below are one per WARP
                     // the halo has not landed yet: do not keep the MMA warp waiting for the previous iteration's operand meanwhile
                     if (pending >= 0) {
                         tmem_st_wait();
                         tcgen05_fence_before();
-                        mbar_arrive(&bar_tready[pending]);
+                        warp_arrive(&bar_tready[pending], lane);
                         pending = -1;
                     }
                     mbar_wait(&bar_afull[s], ph, 3);
@@ -263,12 +267,26 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     if (++tb == p.kw) { tb = 0; ++ta; }
                     float hi[16], lo[16];
                     const uint32_t rp = stage + (uint32_t)prow * 128u;
+#ifdef NI_DEV
+                    if (q.experiment & 1) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { hi[e] = 1.f; lo[e] = 0.f; }
+                    } else
+#endif
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
+#ifdef NI_DEV
+                        const float4 v = (q.experiment & 8) ? make_float4((float)prow, (float)c, (float)tap, 1.f)
+                                                            : lds128(rp + (uint32_t)(((4 * half + c) ^ (prow & 7)) << 4));
+#else
                         const float4 v = lds128(rp + (uint32_t)(((4 * half + c) ^ (prow & 7)) << 4));
+#endif
                         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
+#ifdef NI_DEV
+                            if (q.experiment & 16) { hi[4 * c + e] = vv[e]; lo[4 * c + e] = vv[e]; continue; }
+#endif
                             const float h = __uint_as_float(__float_as_uint(vv[e]) & 0xFFFFE000u);
                             hi[4 * c + e] = h;
                             lo[4 * c + e] = vv[e] - h;
@@ -278,26 +296,31 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     if (pending >= 0) {
                         tmem_st_wait();
                         tcgen05_fence_before();
-                        mbar_arrive(&bar_tready[pending]);
+                        warp_arrive(&bar_tready[pending], lane);
                     }
                     TCP_ADD(9);
                     mbar_wait(&bar_tfree[t], pt ^ 1, 5);
                     TCP_ADD(8);
                     tcgen05_fence_after();
                     const uint32_t dst = a_base + ((uint32_t)(qd * 32) << 16) + t * 64 + 16 * half;
-                    tmem_st_32x16(dst, hi);
-                    tmem_st_32x16(dst + 32, lo);
+#ifdef NI_DEV
+                    if (!(q.experiment & 2))
+#endif
+                    {
+                        tmem_st_32x16(dst, hi);
+                        tmem_st_32x16(dst + 32, lo);
+                    }
                     pending = t;
                     if (!q.defer_st) {
                         tmem_st_wait();
                         tcgen05_fence_before();
-                        mbar_arrive(&bar_tready[pending]);
+                        warp_arrive(&bar_tready[pending], lane);
                         pending = -1;
                     }
                     // Stage back to the TMA producer only now: the tcgen05.st above consumed the registers of the last tap, so every
                     // shared-memory load of this thread from the stage has completed (an arrive right behind the LDS *issue* is not
                     // ordered after the loads' data phase)
-                    if (tap == taps - 1) mbar_arrive(&bar_afree[s]);
+                    if (tap == taps - 1) warp_arrive(&bar_afree[s], lane);
                 }
                 if (++s == p.sa) { s = 0; ph ^= 1; }
             }
@@ -305,7 +328,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
         if (pending >= 0) {
             tmem_st_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bar_tready[pending]);
+            warp_arrive(&bar_tready[pending], lane);
         }
     } else if (warp >= 12) {
         // ---- epilogue: accumulator set -> (+ bias, activation) -> global, while the MMA warp works on the other set
@@ -364,7 +387,7 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 TCP_ADD(14);
                 if (c == BNT / 32 - 1) {          // every TMEM read of this tile has completed: release the accumulator set
                     tcgen05_fence_before();
-                    mbar_arrive(&bar_accfree[aset]);
+                    warp_arrive(&bar_accfree[aset], lane);
                 }
                 if (!valid && !fuse_act) continue;
                 const int co0 = nt * BNT + c * 32;
@@ -449,6 +472,9 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                 }
                 TCP_ADD(15);
                 float4* o4 = reinterpret_cast<float4*>(o);
+#ifdef NI_DEV
+                if (q.experiment & 32) continue;
+#endif
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 w4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);

@@ -56,7 +56,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], NP); mbar_init(&bar_aready[s], 256); mbar_init(&bar_bready[s], NT * 32); mbar_init(&bar_free[s], 1);
+            mbar_init(&bar_full[s], NP); mbar_init(&bar_aready[s], 8); mbar_init(&bar_bready[s], NT); mbar_init(&bar_free[s], 1);      // "ready" arrivals are one per WARP (warp_arrive)
         }
         mbar_init(&bar_accum, 1);
         fence_barrier_init();
@@ -173,11 +173,11 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         int pending = -1;       // stage whose tcgen05.st is in flight: completion wait + "ready" arrive deferred behind the next step's loads
         for (int it = 0; it < iters; ++it) {
             TCP_START();
-            if (!mbar_try_wait(&bar_full[s], ph)) {
+            if (!__all_sync(0xffffffffu, mbar_try_wait(&bar_full[s], ph))) {       // warp-uniform (one arrival per warp below)
                 if (pending >= 0) {           // nothing to overlap with: do not keep the MMA warp waiting
                     tmem_st_wait();
                     tcgen05_fence_before();
-                    mbar_arrive(&bar_aready[pending]);
+                    warp_arrive(&bar_aready[pending], lane);
                     pending = -1;
                 }
                 mbar_wait(&bar_full[s], ph, 3);
@@ -202,7 +202,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             if (pending >= 0) {
                 tmem_st_wait();
                 tcgen05_fence_before();
-                mbar_arrive(&bar_aready[pending]);
+                warp_arrive(&bar_aready[pending], lane);
             }
             // slot s was last read by the MMAs of iteration it - STAGES, whose completion released bar_free[s] to the producers before
             // this stage was refilled, so the slot is free once bar_full[s] has fired
@@ -214,7 +214,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             if (!p.defer_st) {
                 tmem_st_wait();
                 tcgen05_fence_before();
-                mbar_arrive(&bar_aready[pending]);
+                warp_arrive(&bar_aready[pending], lane);
                 pending = -1;
             }
             TCP_ADD(39);
@@ -223,7 +223,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         if (pending >= 0) {
             tmem_st_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bar_aready[pending]);
+            warp_arrive(&bar_aready[pending], lane);
         }
         mbar_wait(&bar_accum, 0, 4);
         tcgen05_fence_after();
@@ -257,7 +257,7 @@ conv_tc3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int qq = tid; qq < NB * 256; qq += NT * 32)
                 transpose_split_chunk(smem_u32(raw_b(s)) + (uint32_t)((qq >> 8) * 4096), smem_u32(b_hi(s)), smem_u32(b_lo(s)), (qq >> 8) * 32, qq & 255);
             fence_proxy_async_smem();
-            mbar_arrive(&bar_bready[s]);
+            warp_arrive(&bar_bready[s], lane);
             TCP_ADD(41);
             if (++s == STAGES) { s = 0; ph ^= 1; }
         }

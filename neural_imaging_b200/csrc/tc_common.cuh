@@ -74,6 +74,15 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
     __syncwarp();
 }
 
+// One mbarrier arrival per WARP (barrier counts are in warps) instead of one per thread: 256 arrivals on one barrier word per k-iteration
+// are 256 serialised shared-memory operations. The warp has converged on a .sync.aligned tcgen05 wait or on __syncwarp here; every lane's
+// prior shared-memory reads / tensor-memory accesses are ordered before lane 0's release-arrive.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+    __syncwarp();
+}
+
 // Explicit shared-space accesses by 32-bit address. The dynamic shared-memory base is re-aligned through uintptr_t arithmetic, after
 // which the compiler no longer knows the address space and emits GENERIC LD.E / ST.E with 64-bit address arithmetic for tile accesses.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
