@@ -40,6 +40,8 @@ CASES = [
     (2, 20, 36, 32, 12, 3, 1, 'SAME', None),
     (2, 40, 40, 3, 3, 5, 1, 'SAME', None),
     (1, 128, 128, 3, 32, 5, 1, 'SAME', 'leaky_relu'),
+    (1, 64, 128, 32, 12, 3, 1, 'SAME', None),          # 12 outputs as three groups of 4 through the persistent column-blocked kernel
+    (2, 64, 64, 32, 3, 5, 1, 'SAME', None),
 ]
 
 
