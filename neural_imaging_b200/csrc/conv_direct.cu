@@ -24,8 +24,6 @@ struct DirectParams {
     // code byte per pooled element = argmax position (bits 0-1, scan order) | (value > 0) << 2 — what the backward needs instead of the
     // full-resolution activation. dst is then only a shape.
     float* pool; unsigned char* code;
-    // conv_manyin3_kernel on a GROUP of output channels [co_base, co_base + COUT) of a layer with co_total of them (0: the layer has COUT)
-    int co_base = 0, co_total = 0;
 };
 
 __device__ __forceinline__ int mirror_idx(int u, int n, int mode) {
@@ -379,11 +377,7 @@ conv_manyin3_kernel(DirectParams p, const float* __restrict__ x, const float* __
         }
     };
 
-    if (p.co_total == 0 || p.co_total == COUT) {
-        for (int i = tid; i < K * K * CIN * COUT / 4; i += 256) cp_async16_zfill(sw + 4 * i, wr + 4 * i, true);
-    } else {          // this launch's channel group out of the layer's [b][c4][a][ci % 4][co_total] filter
-        for (int i = tid; i < K * K * CIN * COUT; i += 256) cp_async4_zfill(sw + i, wr + (i / COUT) * p.co_total + p.co_base + i % COUT, true);
-    }
+    for (int i = tid; i < K * K * CIN * COUT / 4; i += 256) cp_async16_zfill(sw + 4 * i, wr + 4 * i, true);
     if (steps > 0) load_step(0, sx0);
 
     float acc[8][2][COUT];
@@ -437,10 +431,9 @@ conv_manyin3_kernel(DirectParams p, const float* __restrict__ x, const float* __
                     float t = acc[r][h][j];
                     acc[r][h][j] = 0.f;
                     if (oy >= p.dst.H || ox >= p.dst.W) continue;
-                    const int jc = p.co_base + j;
-                    if (bias) t += __ldg(bias + (p.bias_mod > 0 ? jc % p.bias_mod : jc));
+                    if (bias) t += __ldg(bias + (p.bias_mod > 0 ? j % p.bias_mod : j));
                     t = act_direct(t, p.act, p.alpha);
-                    float* o = y + view_addr(p.dst, n, oy, ox, jc);
+                    float* o = y + view_addr(p.dst, n, oy, ox, j);
                     *o = p.accumulate ? *o + t : t;
                 }
             }
@@ -594,22 +587,17 @@ template <int CIN, int COUT, int K>
 int launch_manyin(const DirectParams& p, const float* x, const float* wr, const float* bias, float* y, cudaStream_t st) {
     if constexpr (COUT <= 4) {
         // 64 x 64 tiles, persistent (conv_manyin3_kernel) when the tile grid is mostly real pixels. Measured and NOT used: layers with 12
-        // outputs as three groups of 4 (co_base / co_total below): 3 x 0.92 ms against 1.53 ms of conv_manyin_kernel for the U-Net output
-        // layer -- with K = 3 a channel quad is consumed so fast that the 128-byte pixel rows it was cut from leave L2 before the next
-        // quad needs them (each line fetched up to 8 times).
-        constexpr int G = COUT <= 4 ? COUT : 4;
+        // outputs as three groups of 4 output channels: 3 x 0.92 ms against 1.53 ms of conv_manyin_kernel for the U-Net output layer --
+        // with K = 3 a channel quad is consumed so fast that the 128-byte pixel rows it was cut from leave L2 before the next quad needs
+        // them (each line fetched up to 8 times).
         const long long covered = (long long)((p.dst.W + M3W - 1) / M3W) * M3W * ((p.dst.H + M3H - 1) / M3H) * M3H;
         if (4 * (long long)p.dst.W * p.dst.H >= 3 * covered) {
-            const size_t smem3 = sizeof(float) * (K * K * CIN * G + 2 * (M3H + K - 1) * (M3W + K - 1) * 4);
-            NI_CUDA(cudaFuncSetAttribute(conv_manyin3_kernel<CIN, G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            const size_t smem3 = sizeof(float) * (K * K * CIN * COUT + 2 * (M3H + K - 1) * (M3W + K - 1) * 4);
+            NI_CUDA(cudaFuncSetAttribute(conv_manyin3_kernel<CIN, COUT, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             const int tiles3 = ((p.dst.W + M3W - 1) / M3W) * ((p.dst.H + M3H - 1) / M3H) * p.n;
             const int grid = tiles3 < ni_num_sms() ? tiles3 : ni_num_sms();
-            for (int g = 0; g < COUT / G; ++g) {
-                DirectParams pg = p;
-                pg.co_base = g * G; pg.co_total = COUT;
-                conv_manyin3_kernel<CIN, G, K><<<grid, 256, smem3, st>>>(pg, x, wr, bias, y);
-                NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
-            }
+            conv_manyin3_kernel<CIN, COUT, K><<<grid, 256, smem3, st>>>(p, x, wr, bias, y);
+            NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
             return NI_OK;
         }
     }

@@ -20,8 +20,11 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:djpe
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_gemm -s 2 -c 1 -o $O/prof_conv_fprop -f python tools/profile_conv.py 2 > $O/ncu_conv.log 2>&1; echo "ncu conv fprop exit $?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc3_wgrad -s 2 -c 1 -o $O/prof_conv_wgrad -f python tools/profile_conv.py 2 >> $O/ncu_conv.log 2>&1; echo "ncu conv wgrad exit $?"
 timeout 300 ncu --set full --clock-control none -k regex:"manip_stack|cconv5" -c 5 -o $O/prof_manip -f python tools/profile_manip.py 0 > $O/ncu_manip.log 2>&1; echo "ncu manip exit $?"
+timeout 300 ncu --set full --clock-control none -k regex:"fewin|manyin3|direct_wgrad" -s 6 -c 3 -o $O/prof_direct -f python tools/profile_conv.py 4 > $O/ncu_direct.log 2>&1; echo "ncu direct exit $?"
+timeout 300 ncu --set full --clock-control none -k regex:"latent_" -s 4 -c 2 -o $O/prof_latent -f python bench.py --config c3 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_latent.log 2>&1; echo "ncu latent exit $?"
+timeout 120 python tools/profile_conv.py 4 5 > $O/direct_time.json 2>&1
 # gpurun copies back at most 64 MiB: summarise the captures on the box and drop the raw reports that do not fit
-for f in prof_djpeg prof_conv_fprop prof_conv_wgrad prof_manip; do
+for f in prof_djpeg prof_conv_fprop prof_conv_wgrad prof_manip prof_direct prof_latent; do
   ncu -i $O/$f.ncu-rep --page raw --csv > $O/$f.raw.csv 2>/dev/null
 done
 du -sm gpurun_out | tail -1
