@@ -44,7 +44,14 @@ static int g_force_simt_override = -1;   // -1: follow the environment, 0 / 1: e
 extern "C" void ni_conv2d_set_force_simt(int on) { g_force_simt_override = on; }
 static bool use_simt() { return g_force_simt_override >= 0 ? g_force_simt_override == 1 : force_simt(); }
 
+// Layers with 8 .. 28 channels on one side of a 32-multiple layer (U-Net 32 -> 12, DCN 64 -> 12): zero-padded tensor-core tiles beat the
+// register-blocked FP32 kernels (fprop 1.54 -> 0.7 ms, dgrad 1.17 -> 0.7 ms for the U-Net output layer at 256 x 128 x 128)
+static bool narrow_tc(const ni_conv_desc* d, int op) {
+    return d && d->cout >= 8 && d->cout < 32 && d->cin % 32 == 0 && ni_conv2d_tc_supported(d, op);
+}
+
 extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    if (!use_simt() && narrow_tc(d, 0) && aligned16(x) && aligned16(y)) return ni_conv2d_fprop_tc(d, x, w, bias, y, st);
     if (!use_simt() && ni_conv2d_direct_supported(d, 0)) return ni_conv2d_fprop_direct(d, x, w, bias, y, st);
     if (!use_simt() && ni_conv2d_small_supported(d, 0)) return ni_conv2d_fprop_small(d, x, w, bias, y, st);
     if (!use_simt() && ni_conv2d_tc_supported(d, 0) && aligned16(x) && aligned16(y)) return ni_conv2d_fprop_tc(d, x, w, bias, y, st);
@@ -54,6 +61,7 @@ extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const floa
 // w: the layer's HWIO weights (kh, kw, cin, cout).
 extern "C" int ni_conv2d_dgrad(const ni_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st) {
     NI_REQUIRE(d && w, "ni_conv2d_dgrad: null pointer");
+    if (!use_simt() && narrow_tc(d, 1) && aligned16(dy) && aligned16(dx)) return ni_conv2d_dgrad_tc(d, dy, w, dx, st);
     if (!use_simt() && ni_conv2d_direct_supported(d, 1)) return ni_conv2d_dgrad_direct(d, dy, w, dx, st);
     if (!use_simt() && ni_conv2d_small_supported(d, 1)) return ni_conv2d_dgrad_small(d, dy, w, dx, st);
     if (!use_simt() && ni_conv2d_tc_supported(d, 1) && aligned16(dy) && aligned16(dx)) return ni_conv2d_dgrad_tc(d, dy, w, dx, st);

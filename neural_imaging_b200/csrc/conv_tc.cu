@@ -42,7 +42,9 @@ namespace {
 
 // w (taps, cin, cout) HWIO -> tiles for the gemm kernel: block ((nt * K/32 + kc) * taps + tap) = [hi | lo], each a
 // (bnt rows x 32 k) K-major SWIZZLE_128B tile exactly as the MMA reads it. transpose: N = cout, K = cin (fprop); else N = cin, K = cout.
-__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int transpose, int bnt) {
+// kp = K rounded up to 32: layers with fewer than 32 channels on the contraction or the output side (U-Net 32 -> 12) run on padded tiles
+// whose padding the launcher zero-fills; the activation side is padded by the tensor map's out-of-bounds fill.
+__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cin, int cout, int transpose, int bnt, int kp) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)taps * cin * cout;
     if (i >= total) return;
@@ -52,7 +54,7 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
     const int n = (int)(t % N), tap = (int)(t / N);
     const float v = transpose ? w[((long long)tap * cin + k) * cout + n] : w[((long long)tap * cin + n) * cout + k];
     const int kc = k >> 5, kl = k & 31, nt = n / bnt, nl = n - nt * bnt;
-    const long long block = ((long long)nt * (K >> 5) + kc) * taps + tap;     // [n tile][k-iteration = kc * taps + tap]: a tile's stream is contiguous
+    const long long block = ((long long)nt * (kp >> 5) + kc) * taps + tap;    // [n tile][k-iteration = kc * taps + tap]: a tile's stream is contiguous
     const int off = (nl >> 3) * 256 + (nl & 7) * 32 + ((((kl >> 2) ^ (nl & 7)) << 2) + (kl & 3));
     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     float* o = out + block * (2 * bnt * 32);
@@ -202,7 +204,8 @@ struct FusedAct {
 // Shared launcher for fprop (dgrad = false) and dgrad (dgrad = true).
 int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float* w, const float* bias, float* dst, cudaStream_t st,
                 const FusedAct& fa = FusedAct()) {
-    const int K = dgrad ? d->cout : d->cin, N = dgrad ? d->cin : d->cout;
+    const int Kr = dgrad ? d->cout : d->cin, Nr = dgrad ? d->cin : d->cout;            // real channel counts
+    const int K = (Kr + 31) & ~31, N = (Nr + 31) & ~31;                                // what the tiles are padded to (see tc_prep_weights_kernel)
     const int sh = dgrad ? d->oh : d->h, sw = dgrad ? d->ow : d->w;           // source dims
     const int th = dgrad ? d->h : d->oh, tw = dgrad ? d->w : d->ow;           // target dims
     const int spitch = dgrad ? d->out_pitch : d->in_pitch, scoff = dgrad ? d->out_coff : d->in_coff;
@@ -221,20 +224,21 @@ int launch_gemm(const ni_conv_desc* d, bool dgrad, const float* src, const float
     const size_t wbytes = (size_t)2 * taps * K * N * sizeof(float);
     int rc = get_scratch(wbytes, &scratch);
     if (rc) return rc;
-    const long long total = (long long)taps * K * N;
-    tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1, bnt);
+    if (K != Kr || N != Nr) NI_CUDA(cudaMemsetAsync(scratch, 0, wbytes, st));          // padded rows / columns of the [hi | lo] tiles
+    const long long total = (long long)taps * Kr * Nr;
+    tc_prep_weights_kernel<<<ni_cdiv(total, 256), 256, 0, st>>>(w, scratch, taps, d->cin, d->cout, dgrad ? 0 : 1, bnt, K);
     NI_LAUNCH_CHECK();
     CUtensorMap tmA;
     p.src_block2_f = smode == NI_MODE_BLOCK2 ? K / 4 : 0;
     if (p.src_block2_f > 0) rc = encode_block2_map(&tmA, src + scoff, d->n, sh, sw, K / 4, spitch, p.hw, p.hh, p.bn);
-    else rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, K, spitch, p.hw, p.hh, p.bn);
+    else rc = encode_act_map(&tmA, src + scoff, d->n, sh, sw, Kr, spitch, p.hw, p.hh, p.bn);     // channels >= Kr: out-of-bounds zero fill
     if (rc) return rc;
     p.n = d->n; p.oh = th; p.ow = tw;
     p.tiles_w = tw / p.bw; p.tiles_h = th / p.bh;
     const int tiles_n = (d->n + p.bn - 1) / p.bn;
     p.kh = d->kh; p.kw = d->kw;
     p.off_y0 = dgrad ? d->pad_t : -d->pad_t; p.off_x0 = dgrad ? d->pad_l : -d->pad_l; p.off_sign = dgrad ? -1 : 1;
-    p.kchunks = K / 32; p.ntot = N;
+    p.kchunks = K / 32; p.ntot = N; p.n_valid = Nr;
     p.out_pitch = dpitch; p.out_coff = dcoff; p.out_mode = dmode;
     p.bias_mod = dgrad ? 0 : d->bias_mod; p.act = dgrad ? NI_ACT_NONE : d->act; p.accumulate = d->accumulate; p.alpha = d->act_alpha;
     p.bias = dgrad ? nullptr : bias; p.out = dst;
@@ -360,13 +364,17 @@ int ni_get_scratch2(size_t bytes, float** out) {
 extern "C" int ni_conv2d_tc_supported(const ni_conv_desc* d, int op) {
     if (!d || d->n <= 0) return 0;
     if (d->stride != 1 || d->pad_mode != NI_PAD_ZERO) return 0;
-    if (d->cin % 32 || d->cout % 32) return 0;
+    // fewer than 32 channels on ONE side of a 32-multiple layer (fprop: outputs, dgrad: contraction) run on zero-padded tiles
+    const bool narrow_out = op != 2 && d->cin % 32 == 0 && d->cout < 32 && d->cout % 4 == 0 && d->cout >= 8;
+    if (!narrow_out && (d->cin % 32 || d->cout % 32)) return 0;
+    if (narrow_out && (d->in_mode != NI_MODE_PLAIN || (op == 1 && d->out_mode != NI_MODE_PLAIN) || d->bias_mod != 0)) return 0;
     if (d->kh * d->kw > 64) return 0;
-    if ((d->in_pitch % 4) || (d->in_coff % 4) || (d->out_pitch % 4) || (d->out_coff % 4)) return 0;
+    if ((d->in_pitch % 4) || (d->in_coff % 4)) return 0;
+    if (((d->out_pitch % 4) || (d->out_coff % 4)) && !(narrow_out && op == 0)) return 0;      // the narrow epilogue stores scalars / float2
     int bw, bh, bn, hw, hh, ast;
     if (op == 0) {
         if (d->in_mode != NI_MODE_PLAIN) return 0;
-        if (d->out_mode == NI_MODE_BLOCK2 && ((d->cout / 4) % 32)) return 0;
+        if (d->out_mode == NI_MODE_BLOCK2 && ((d->cout / 4) % 32) && !narrow_out) return 0;
         return gemm_geometry(d->oh, d->ow, d->kh, d->kw, bw, bh, bn, hw, hh, ast) ? 1 : 0;
     }
     if (op == 1) {

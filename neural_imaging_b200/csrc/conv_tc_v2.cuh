@@ -32,6 +32,7 @@ struct GemmParams {
     int kh, kw, off_y0, off_x0, off_sign;
     int hw, hh, sa, a_stage;       // halo box (bw + kw - 1) x (bh + kh - 1) pixels, A stages and their byte size (1024-aligned)
     int kchunks, ntot;
+    int n_valid;                   // real output channels (< ntot when the n tile is zero-padded: scalar masked stores in the epilogue)
     int out_pitch, out_coff, out_mode;
     int bias_mod, act, accumulate, nacc;
     float alpha;

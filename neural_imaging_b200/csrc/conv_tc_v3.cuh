@@ -438,6 +438,43 @@ conv_tc3_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const float* __res
                     }
                     if (!valid) continue;
                 }
+                if (p.n_valid < p.ntot) {
+                    // zero-padded n tile (U-Net output layer, 12 of 32 columns): bias + activation on the real channels only
+                    const int F = p.n_valid >> 2;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < p.n_valid) v[j] = act_apply(v[j] + (p.bias ? __ldg(p.bias + j) : 0.f), p.act, p.alpha);
+                    if (p.out_mode != NI_MODE_PLAIN && F == 3 && p.out_pitch == 3 && p.out_coff == 0 && !p.accumulate) {
+                        // depth_to_space(2) of 12 channels into an RGB image: the two sub-pixels of a row are 6 contiguous floats (8-byte aligned)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            float2* o2 = reinterpret_cast<float2*>(p.out + (((long long)on * 2 * p.oh + 2 * oy + r) * (2 * p.ow) + 2 * ox) * 3);
+                            o2[0] = make_float2(v[6 * r], v[6 * r + 1]);
+                            o2[1] = make_float2(v[6 * r + 2], v[6 * r + 3]);
+                            o2[2] = make_float2(v[6 * r + 4], v[6 * r + 5]);
+                        }
+                        continue;
+                    }
+                    if (p.out_mode == NI_MODE_PLAIN && !(p.out_pitch & 3) && !(p.out_coff & 3) && !p.accumulate) {
+                        float4* o4n = reinterpret_cast<float4*>(p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            if (4 * j4 < p.n_valid) o4n[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        continue;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j >= p.n_valid) continue;
+                        float* oj;
+                        if (p.out_mode == NI_MODE_PLAIN) oj = p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff + j;
+                        else {
+                            const int blk = j / F, f = j - blk * F;
+                            oj = p.out + (((long long)on * 2 * p.oh + 2 * oy + (blk >> 1)) * (2 * p.ow) + 2 * ox + (blk & 1)) * p.out_pitch + p.out_coff + f;
+                        }
+                        *oj = p.accumulate ? *oj + v[j] : v[j];
+                    }
+                    continue;
+                }
                 float* o;
                 if (p.out_mode == NI_MODE_PLAIN) {
                     o = p.out + (((long long)on * p.oh + oy) * p.ow + ox) * p.out_pitch + p.out_coff + co0;

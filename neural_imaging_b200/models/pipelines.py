@@ -227,9 +227,9 @@ class UNet(NIPModel):
         # final conv (input dc{S-1}2)
         last = acts['dc%d2' % (S - 1)]
         dcur = ws.get('d_dc%d2' % (S - 1), last.shape)
-        self._final.bprop(last, None, dy, dcur, descs['final'])
+        self._final.bprop(last, None, dy, dcur, descs['final'], fuse_prev=self._dec[S - 2][2].fuse_info(last) if S > 1 else None)
         dcats = {}
-        done = False           # the gradient in `dcur` already carries act'(y) and the bias gradient of its layer has been accumulated
+        done = self._final.fused_prev      # the gradient in `dcur` already carries act'(y) and the bias gradient of its layer has been accumulated
         for n in reversed(range(1, S)):
             up, c1, c2 = self._dec[n - 1]
             c = c1.cout

@@ -218,9 +218,11 @@ class Conv2D:
         dyp, dyo, dym = dy_addr if dy_addr is not None else (d.out_pitch, d.out_coff, d.out_mode)
         db = ptr(self.b.grad) if (self.b is not None and self.b.trainable and need_dw) else None
         f4 = d.cout // 4
-        if (dym == MODE_BLOCK2 and d.kh * d.kw > 1 and d.stride == 1 and d.cin % 32 == 0 and d.cout % 32 == 0 and f4 % 4 == 0 and dyp == f4
+        if (dym == MODE_BLOCK2 and d.kh * d.kw > 1 and d.stride == 1 and d.cin % 32 == 0 and d.cout % 4 == 0 and dyp == f4
+                and (d.cout % 32 == 0 or 8 <= d.cout < 32) and (f4 % 4 == 0 or d.act in (ACT_NONE, ACT_CLIP01))
                 and dyo == 0 and d.out_mode == MODE_BLOCK2 and d.out_pitch == f4 and d.out_coff == 0 and self.bias_mod == 0):
-            # k x k convolution with a depth_to_space(2) epilogue (the sub-pixel up-sampling layers of the DCN decoder): the tensor-map
+            # k x k convolution with a depth_to_space(2) epilogue (the sub-pixel up-sampling layers of the DCN decoder, the U-Net output
+            # layer 32 -> 12 whose input gradient runs on zero-padded tensor-core tiles): the tensor-map
             # path reads depth_to_space-addressed gradients for 1x1 filters only, and the scalar fallback ran these layers at 14 - 30 TFLOP/s.
             # Activation backward on the physical (n, 2h, 2w, F) layout (elementwise, y and dy share it), then ONE space_to_depth copy of dy
             # into the logical (n, h, w, 4F) layout -- block-major, the order depth_to_space wrote -- and everything else on the dense path.

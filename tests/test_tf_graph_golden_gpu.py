@@ -240,7 +240,7 @@ def _check_all(G, case, items, **kw):
                 flipped += 1
             except AssertionError:
                 bad.append(str(e).splitlines()[0])
-    C.REPORT[case + '/tensors_at_flip_tier(count)'] = float(flipped)
+    C.REPORT[case + '/tensors_at_flip_tier(count)'] = C.REPORT.get(case + '/tensors_at_flip_tier(count)', 0.0) + float(flipped)     # (summed over the stores of a flow)
     assert not bad, '{} of {} tensors out of tolerance:\n  '.format(len(bad), len(items)) + '\n  '.join(bad)
     # the layers DOWNSTREAM of the flipped unit (last convolution, 1x1 convolution, dense) must still pass at the tight bound
     assert flipped <= len(items) - 4, '{} of {} tensors only pass at the flip tier'.format(flipped, len(items))
@@ -329,9 +329,12 @@ def test_joint_step_with_learned_codec_against_executed_reference(G):
     G.check(case, 'C', Cc.numpy(), tol=1e-4, outliers=0.02, loose=1.0)
     stores = {'fan': flow.fan._store, 'nip': flow.nip._store, 'dcn': flow.codec._store}
     loss1, parts1 = flow.training_step(x, t, lambda_nip=0.1, lambda_dcn=0.1, learning_rate=meta['lr'][0])
+    # two tiers like the other flows (_check_all): the codec's hard code-book decisions and the FAN's LeakyReLU / max-pool decisions flip on
+    # float32 noise (e.g. when the 64 -> 12 decoder layer moved from the FP32 kernel to 3xTF32 tensor-core tiles, 1e-6 apart), and one flip
+    # moves every upstream gradient by ~1e-4 .. 1e-2; tensors that only pass at the flip tier are counted in the parity report
     for tag, store in stores.items():
-        for n, g in _grads(store).items():
-            G.check(case, 'grad/{}/{}'.format(tag, n), g, tol=5e-4 if tag == 'dcn' else 2e-4, outliers=0.03, loose=1.0)
+        _check_all(G, case, [('grad/{}/{}'.format(tag, n), g) for n, g in _grads(store).items()],
+                   tol=5e-4 if tag == 'dcn' else 2e-4, outliers=0.03, loose=1.0)
     loss2, parts2 = flow.training_step(x, t, lambda_nip=0.1, lambda_dcn=0.1, learning_rate=meta['lr'][1])
     G.check(case, 'loss', np.array([float(loss1.numpy()), float(loss2.numpy())]), tol=2e-3)
     G.check(case, 'dcn', np.array([float(_np(parts1['dcn'])), float(_np(parts2['dcn']))]), tol=2e-3)
