@@ -628,7 +628,7 @@ int launch_wgrad(DirectWgradParams p, const float* x, const float* dy, float* dw
 // (cin, cout, k) of the logical FORWARD convolution each kernel family is instantiated for
 #define NI_FEWIN_SHAPES(X) X(3, 32, 5) X(4, 32, 3)
 #define NI_MANYIN_SHAPES(X) X(32, 3, 5) X(32, 12, 3) X(32, 4, 3) X(64, 12, 3)
-#define NI_DWGRAD_SHAPES(X) X(3, 32, 5, 8) X(4, 32, 3, 8) X(32, 12, 3, 12) X(3, 3, 5, 3)
+#define NI_DWGRAD_SHAPES(X) X(3, 32, 5, 8) X(4, 32, 3, 8) X(32, 12, 3, 12) X(3, 3, 5, 3) X(64, 12, 3, 12)
 
 }  // namespace
 

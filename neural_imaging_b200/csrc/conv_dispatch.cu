@@ -47,7 +47,9 @@ static bool use_simt() { return g_force_simt_override >= 0 ? g_force_simt_overri
 // Layers with 8 .. 28 channels on one side of a 32-multiple layer (U-Net 32 -> 12, DCN 64 -> 12): zero-padded tensor-core tiles beat the
 // register-blocked FP32 kernels (fprop 1.54 -> 0.7 ms, dgrad 1.17 -> 0.7 ms for the U-Net output layer at 256 x 128 x 128)
 static bool narrow_tc(const ni_conv_desc* d, int op) {
-    return d && d->cout >= 8 && d->cout < 32 && d->cin % 32 == 0 && ni_conv2d_tc_supported(d, op);
+    if (!d) return false;
+    const bool out_side = d->cout >= 8 && d->cout < 32 && d->cin % 32 == 0, in_side = d->cin >= 8 && d->cin < 32 && d->cout % 32 == 0;
+    return (out_side || in_side) && ni_conv2d_tc_supported(d, op);
 }
 
 extern "C" int ni_conv2d_fprop(const ni_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {

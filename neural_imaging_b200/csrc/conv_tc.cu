@@ -366,8 +366,10 @@ extern "C" int ni_conv2d_tc_supported(const ni_conv_desc* d, int op) {
     if (d->stride != 1 || d->pad_mode != NI_PAD_ZERO) return 0;
     // fewer than 32 channels on ONE side of a 32-multiple layer (fprop: outputs, dgrad: contraction) run on zero-padded tiles
     const bool narrow_out = op != 2 && d->cin % 32 == 0 && d->cout < 32 && d->cout % 4 == 0 && d->cout >= 8;
-    if (!narrow_out && (d->cin % 32 || d->cout % 32)) return 0;
+    const bool narrow_in = op != 2 && d->cout % 32 == 0 && d->cin < 32 && d->cin % 4 == 0 && d->cin >= 8;      // e.g. 12 -> 64: the image-end DCN layer in space_to_depth form
+    if (!narrow_out && !narrow_in && (d->cin % 32 || d->cout % 32)) return 0;
     if (narrow_out && (d->in_mode != NI_MODE_PLAIN || (op == 1 && d->out_mode != NI_MODE_PLAIN) || d->bias_mod != 0)) return 0;
+    if (narrow_in && (d->in_mode != NI_MODE_PLAIN || d->out_mode != NI_MODE_PLAIN)) return 0;
     if (d->kh * d->kw > 64) return 0;
     if ((d->in_pitch % 4) || (d->in_coff % 4)) return 0;
     if (((d->out_pitch % 4) || (d->out_coff % 4)) && !(narrow_out && op == 0)) return 0;      // the narrow epilogue stores scalars / float2

@@ -186,8 +186,33 @@ class Conv2D:
         return bufs[key]
 
     # ---- compute
+    def _s2d_desc(self, d):
+        """The 3x3 stride-1 convolution over space_to_depth(2) of the input that equals this 5x5 stride-2 SAME convolution (see StridedConv5)."""
+        d3 = ConvDesc()
+        d3.n, d3.h, d3.w, d3.cin, d3.cout, d3.kh, d3.kw, d3.stride = d.n, d.h // 2, d.w // 2, 4 * self.cin, self.cout, 3, 3, 1
+        d3.pad_t, d3.pad_l, d3.oh, d3.ow = 1, 1, d.h // 2, d.w // 2
+        d3.in_pitch, d3.in_coff, d3.in_mode = 4 * self.cin, 0, MODE_PLAIN
+        d3.out_pitch, d3.out_coff, d3.out_mode = d.out_pitch, d.out_coff, d.out_mode
+        d3.act, d3.act_alpha, d3.accumulate, d3.pad_mode, d3.bias_mod = d.act, d.act_alpha, d.accumulate, PAD_ZERO, d.bias_mod
+        return d3
+
+    def _image_end_s2(self, d):
+        """5x5 stride-2 SAME convolution on a 3 / 4-channel image with >= 32-multiple outputs (DCN encoder input layer)."""
+        return (d.stride == 2 and d.kh == 5 and d.kw == 5 and self.padding == 'SAME' and d.h % 2 == 0 and d.w % 2 == 0 and 2 <= self.cin <= 4
+                and self.cout % 32 == 0 and d.in_mode == MODE_PLAIN and d.in_pitch == self.cin and d.in_coff == 0 and d.out_mode == MODE_PLAIN)
+
     def fprop(self, x, y, d, weight=None):
         L = _lib.lib()
+        if weight is None and self._image_end_s2(d):
+            # as a 3x3 convolution over space_to_depth(2): 4 * cin = 12 / 16 contraction channels on zero-padded tensor-core tiles instead of
+            # the FP32 strided fallback (3.7 -> 1.1 ms for 1280 x 128 x 128 x 3 -> 64)
+            st = stream()
+            xs = self._scratch('xs', (d.n, d.h // 2, d.w // 2, 4 * self.cin))
+            w3 = self._scratch('w3', (3, 3, 4 * self.cin, self.cout))
+            L.ni_space_to_depth2(ptr(x), ptr(xs), d.n, d.h // 2, d.w // 2, self.cin, 0, 0, st)
+            L.ni_s2conv_weights(ptr(self.w.value), ptr(w3), self.cin, self.cout, 0, st)
+            L.ni_conv2d_fprop(ctypes.byref(self._s2d_desc(d)), ptr(xs), ptr(w3), self._bias_ptr(), ptr(y), st)
+            return y
         L.ni_conv2d_fprop(ctypes.byref(d), ptr(x), ptr(self.w.value if weight is None else weight), self._bias_ptr(), ptr(y), stream())
         return y
 
