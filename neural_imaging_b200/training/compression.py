@@ -67,6 +67,9 @@ def train_dcn(dcn, training, data, directory='./data/models/dcn/playground/', ov
     'gamma'}}. Returns the output directory (None when it exists and overwrite is off, like the reference)."""
     if tensorboard:
         raise NotImplementedError('TensorBoard summaries are not part of the B200 path')
+    if training['augmentation_probs'].get('resize', 0) > 0:         # fail before the first epoch, not part-way through training
+        raise NotImplementedError("the 'resize' augmentation (skimage.transform.resize, anti-aliased) is not available on this stack: set "
+                                  "augmentation_probs['resize'] = 0")
     n_batches = _count(data, 'training', 'count_training') // training['batch_size']
     v_batches = _count(data, 'validation', 'count_validation') // training['batch_size']
     perf = dcn.performance
@@ -84,8 +87,7 @@ def train_dcn(dcn, training, data, directory='./data/models/dcn/playground/', ov
         if epoch > 0 and epoch % training['learning_rate_reduction_schedule'] == 0:
             learning_rate *= training['learning_rate_reduction_factor']
         for batch_id in range(n_batches):
-            if np.random.uniform() < probs['resize']:
-                raise NotImplementedError("the 'resize' augmentation (skimage.transform.resize, anti-aliased) is not available on this stack")
+            np.random.uniform()           # the reference's draw for the 'resize' augmentation (probability 0 here): keeps the np.random sequence aligned
             batch_x = data.next_training_batch(batch_id, training['batch_size'], training['patch_size'])
             if isinstance(batch_x, tuple):
                 batch_x = batch_x[-1]
