@@ -61,19 +61,39 @@ def validate_fan(flow, data, get_labels=False):
     return accuracy, conf
 
 
+NIP_GROUP = 16      # validation images developed per device pass (the reference develops them one by one and renders a figure)
+
+
 def validate_nip(model, data, save_dir=None, epoch=0, show_ref=False, loss_type='L2'):
-    """Per-image (ssim, psnr, loss) lists of a NIP on the validation set (no figures)."""
+    """Per-image (ssim, psnr, loss) lists of a NIP on the validation set (reference training/validation.py:96-160 without the figure).
+    The images go through the ISP in groups; squared / absolute error and SSIM are reduced per image on the device, one host read per group."""
     if loss_type not in ('L1', 'L2'):
         raise ValueError('Invalid loss! Use either L1 or L2.')
+    import torch
+    from ..tensor import as_device
+    n = int(data.count_validation)
     ssims, psnrs, losss = [], [], []
-    for b in range(data.count_validation):
-        example_x, example_y = data.next_validation_batch(b, 1)
-        developed = model.process(example_x).numpy().clip(0, 1).squeeze()
-        reference = np.asarray(example_y).squeeze()
-        mse = float(np.mean(np.power(reference - developed, 2.0)))
-        psnrs.append(float(10.0 * np.log10(1.0 / mse)) if mse > 0 else float('inf'))
-        ssims.append(metrics.ssim(reference, developed))
-        losss.append(mse if loss_type == 'L2' else float(np.mean(np.abs(reference - developed))))
+
+    def run(batch_id, size):
+        example_x, example_y = data.next_validation_batch(batch_id, size)
+        developed = as_device(model.process(example_x)).clamp(0.0, 1.0)
+        reference = as_device(np.asarray(example_y, dtype=np.float32))
+        if reference.dim() == 3:
+            reference = reference.unsqueeze(0)
+        diff = (reference - developed).double()
+        stats = torch.stack((diff.pow(2).mean(dim=(1, 2, 3)), diff.abs().mean(dim=(1, 2, 3))), dim=1).cpu().numpy()
+        ss = np.atleast_1d(metrics.ssim(reference, developed) if size > 1 else metrics.ssim(reference[0], developed[0]))
+        for i in range(size):
+            mse = float(stats[i, 0])
+            psnrs.append(float(10.0 * np.log10(1.0 / mse)) if mse > 0 else float('inf'))
+            ssims.append(float(ss[i]))
+            losss.append(mse if loss_type == 'L2' else float(stats[i, 1]))
+
+    full = n // NIP_GROUP
+    for g in range(full):
+        run(g, NIP_GROUP)
+    for b in range(full * NIP_GROUP, n):
+        run(b, 1)
     return ssims, psnrs, losss
 
 

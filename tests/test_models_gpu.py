@@ -284,6 +284,28 @@ class _ToyData:
         return self._x[i:i + batch_size], self._y[i:i + batch_size]
 
 
+def test_validate_nip_grouped_equals_per_image():
+    """validate_nip develops the validation set in groups of NIP_GROUP with device-side reductions: same per-image ssim / psnr / loss as
+    developing the images one by one on the host (reference training/validation.py:112-131)."""
+    from neural_imaging_b200.helpers import metrics
+    from neural_imaging_b200.models import pipelines
+    from neural_imaging_b200.training import validation
+    data = _ToyData(n_train=4, n_valid=validation.NIP_GROUP + 3, raw=16)
+    model = pipelines.UNet(patch_size=16, seed=5)
+    for loss_type in ('L2', 'L1'):
+        ssims, psnrs, losss = validation.validate_nip(model, data, loss_type=loss_type)
+        assert len(ssims) == len(psnrs) == len(losss) == data.count_validation
+        for b in range(data.count_validation):
+            x, y = data.next_validation_batch(b, 1)
+            dev = model.process(x).numpy().clip(0, 1).squeeze()
+            ref = np.asarray(y).squeeze()
+            mse = float(np.mean(np.power(ref.astype(np.float64) - dev, 2.0)))
+            assert abs(psnrs[b] - 10.0 * np.log10(1.0 / mse)) < 1e-4
+            assert abs(ssims[b] - metrics.ssim(ref, dev)) < 1e-5
+            want = mse if loss_type == 'L2' else float(np.mean(np.abs(ref.astype(np.float64) - dev)))
+            assert abs(losss[b] - want) < 1e-6 * max(1.0, want)
+
+
 def test_training_loop_api(tmp_path):
     """training.manipulation.train_manipulation_nip (reference training/manipulation.py:36): runs epochs through
     flow.training_step, validates with validate_fan (confusion matrix rows sum to 1), snapshots the models."""

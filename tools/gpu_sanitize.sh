@@ -15,4 +15,5 @@ run djpeg memcheck 300 tests/test_djpeg_gpu.py
 run djpeg racecheck 300 tests/test_djpeg_gpu.py
 run manip memcheck 300 tests/test_manip_gpu.py
 run conv memcheck 420 tests/test_conv_gpu.py -k "not many_tiles"
-run conv racecheck 420 tests/test_conv_gpu.py -k "tc and not many_tiles"
+run conv racecheck 420 tests/test_conv_gpu.py -k "(tc or subpixel) and not many_tiles"
+run dcn memcheck 420 tests/test_dcn_gpu.py tests/test_layers_gpu.py
