@@ -676,8 +676,9 @@ def run_c3(args, rank, world, local_rank):
              'roofline_latent': {'kernel': 'latent quantisation forward (ni_latent_quantise_fwd: scale, soft code book in float64, hard value, soft histogram)', 'bound': 'hbm', 'unit': 'GB/s', 'ms_per_launch': fwd_ms,
                                  'algorithmic_bytes_per_launch': 8.0 * nz, 'achieved': (8.0 * nz / (fwd_ms * 1e-3) / 1e9) if fwd_ms else None,
                                  'peak': pk['hbm_gbs'], 'frac': (8.0 * nz / (fwd_ms * 1e-3) / 1e9 / pk['hbm_gbs']) if fwd_ms else None,
-                                 'note': '4 B read + 4 B written per latent value; {} values per launch: a few MB, i.e. latency- not bandwidth-sized at this batch '
-                                         '(32 float64 kernel evaluations per value are the work)'.format(nz), 'all_latent_entries_ms': lat_ms},
+                                 'limited_by': 'fp64 issue (ncu profiles/r2_latent_ncu.txt: issue slots 72-75 % busy, DRAM = the latents once)',
+                                 'note': '4 B read + 4 B written per latent value; {} values per launch: a few MB, i.e. not bandwidth-sized at this batch '
+                                         '(64 float64 code-book weights per value are the work); the HBM figure is reported for reference'.format(nz), 'all_latent_entries_ms': lat_ms},
              'kernels': _kernel_list(agg, args.steps, prof_ms, pk), 'param_checksum': param_checksum([model._store])}
     _emit(args, world, rank, ms, ms_e2e, args.batch, xp.numel() * 4, 4, launches, clk, extra)
 
