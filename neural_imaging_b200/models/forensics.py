@@ -67,9 +67,9 @@ class FAN(TFModel):
         self._dense = []
         for i in range(self._h.n_dense):
             nf = nf // n_fscale
-            self._dense.append(nn.Conv2D(st, 'dense_{}'.format(i), 1, feat, int(nf), padding='VALID', activation=act, rng=rng))
+            self._dense.append(nn.Conv2D(st, 'dense_{}'.format(i), 1, feat, int(nf), padding='VALID', activation=act, rng=rng, keras='dense'))
             feat = int(nf)
-        self._out = nn.Conv2D(st, 'dense_out', 1, feat, self.n_classes, padding='VALID', rng=rng)
+        self._out = nn.Conv2D(st, 'dense_out', 1, feat, self.n_classes, padding='VALID', rng=rng, keras='dense')
         st.finalize()
         self._ws = Workspace()
         self._nf = None if nn.HOST_ONLY else empty((5, 5, 3, 3))        # normalised constrained filter

@@ -377,7 +377,7 @@ class DNet(NIPModel):
             self._deep.append(nn.Conv2D(st, 'conv2d_%d' % r, k, cin, cout, activation='relu', kernel_init=vs(cin, cout), **kw))
             cin = cout
         self._padid = nn.Conv2D(st, 'reflect_pad_d2s', 1, 12, 12, padding='VALID', use_bias=False, trainable=False, pad_mode=PAD_REFLECT,
-                                explicit_pad=pad, kernel_init=np.eye(12, dtype=np.float32).reshape(1, 1, 12, 12))
+                                explicit_pad=pad, kernel_init=np.eye(12, dtype=np.float32).reshape(1, 1, 12, 12), keras='internal')
         upk = kernels.upsampling_kernel()
         self._up = nn.Conv2D(st, 'upsampling', 1, 4, 12, use_bias=False, trainable=False,
                              kernel_init=np.asarray(upk, np.float32).reshape(1, 1, 4, 12))

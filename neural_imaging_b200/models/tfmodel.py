@@ -1,8 +1,9 @@
 """Base class of all toolbox models: performance-metric bookkeeping, parameter access / counting, save / load.
 
 API mirror of reference models/tfmodel.py:86-294 (TFModel) without TensorFlow: weights live in a flat device
-buffer (neural_imaging_b200.nn.ParamStore); snapshots are ``<dir>/<scoped_name>/<class>.npz`` (+ ``.json`` with the
-hyper-parameters) because h5py / Keras are not part of this stack (h5 interchange is a "next" row).
+buffer (neural_imaging_b200.nn.ParamStore); snapshots are Keras-layout HDF5 weight files ``<dir>/<scoped_name>/<class>.h5``
+(+ ``.json`` with the hyper-parameters) written and read by the dependency-free ``helpers/h5lite.py``; the ``.npz``
+snapshots of earlier versions of this stack are still read.
 """
 import json
 import os
@@ -10,12 +11,97 @@ from pathlib import Path
 
 import numpy as np
 
-from ..helpers import utils
+from ..helpers import h5lite, utils
+
+
+# ---------------------------------------------------------------------------------------------------- Keras .h5 weight files
+def _to_keras(p, a):
+    """Product storage -> the Keras variable's shape (neural_imaging_b200/nn.py docstring)."""
+    if p.keras == 'dense':                                   # (1, 1, in, out) -> (in, out)
+        return a.reshape(a.shape[2], a.shape[3])
+    if p.keras == 'conv2d_transpose':                        # 1x1 conv (1, 1, ci, (a*2+b)*F + f) -> (2, 2, F, ci)
+        ci, f = a.shape[2], a.shape[3] // 4
+        return np.ascontiguousarray(a.reshape(ci, 2, 2, f).transpose(1, 2, 3, 0))
+    return a
+
+
+def _from_keras(p, a):
+    if p.keras == 'dense' and a.ndim == 2 and (1, 1) + a.shape == p.shape:
+        return a.reshape(p.shape)
+    if p.keras == 'conv2d_transpose' and a.ndim == 4 and a.shape[:2] == (2, 2) and p.shape == (1, 1, a.shape[3], 4 * a.shape[2]):
+        return np.ascontiguousarray(a.transpose(3, 0, 1, 2)).reshape(p.shape)
+    if tuple(a.shape) != p.shape:
+        raise ValueError('shape mismatch for {}: weight file {} vs model {}'.format(p.name, tuple(a.shape), p.shape))
+    return a
+
+
+def save_weights_h5(store, filename):
+    """``tf.keras.Model.save_weights(filename, save_format='h5')`` (reference models/tfmodel.py:159) for a ParamStore: the layout of
+    Keras' ``save_weights_to_hdf5_group`` — root attributes ``layer_names`` / ``backend`` / ``keras_version``, one group per layer with
+    a ``weight_names`` attribute and one dataset per variable at ``<layer>/<variable name>`` in the Keras storage shapes."""
+    layers, order = {}, []
+    for p in store.params:
+        if p.keras == 'internal':
+            continue
+        layer = p.name.rsplit('/', 1)[0] if '/' in p.name else p.name
+        if layer not in layers:
+            layers[layer] = []
+            order.append(layer)
+        a = p.value.detach().cpu().numpy() if p.value is not None else p.init
+        layers[layer].append((p.name + ':0', _to_keras(p, np.asarray(a, np.float32).reshape(p.shape))))
+    tree, attrs = {}, {'': {'layer_names': np.array([n.encode('utf8') for n in order] or [b''], dtype='S'),
+                            'backend': np.bytes_(b'tensorflow'), 'keras_version': np.bytes_(b'2.2.4-tf')}}
+
+    def put(path, value):
+        node = tree
+        parts = path.split('/')
+        for part in parts[:-1]:
+            node = node.setdefault(part, {})
+        if value is None:
+            node.setdefault(parts[-1], {})
+        else:
+            node[parts[-1]] = value
+    for layer in order:
+        put(layer, None)
+        attrs[layer] = {'weight_names': np.array([n.encode('utf8') for n, _ in layers[layer]], dtype='S')}
+        for n, a in layers[layer]:
+            put(layer + '/' + n, np.asarray(a, np.float32))
+    h5lite.write(filename, tree, attrs)
+
+
+def load_weights_h5(store, filename):
+    """``tf.keras.Model.load_weights`` on an h5 weight file (reference models/tfmodel.py:181): like Keras'
+    ``load_weights_from_hdf5_group`` the variables are matched BY ORDER (layers in ``layer_names`` order, variables in
+    ``weight_names`` order), not by name — Keras' automatic layer names depend on what else was built in the session. Chunked
+    attributes (``layer_names0``, ``layer_names1`` ... for attributes above 64 KB) are joined as Keras does."""
+    def attr_list(node, name):
+        if name in node.attrs:
+            vals = np.atleast_1d(node.attrs[name])
+        else:
+            vals, k = [], 0
+            while '{}{}'.format(name, k) in node.attrs:
+                vals.extend(np.atleast_1d(node.attrs['{}{}'.format(name, k)]))
+                k += 1
+        return [v.decode('utf8') if isinstance(v, bytes) else str(v) for v in vals]
+    with h5lite.File(filename) as f:
+        root = f['model_weights'] if 'layer_names' not in f.attrs and 'model_weights' in f else f   # model.save() files nest the weights
+        values = []
+        for layer in attr_list(root, 'layer_names'):
+            if not layer:
+                continue
+            g = root[layer]
+            for wn in attr_list(g, 'weight_names'):
+                values.append((layer + '/' + wn, g[wn].read()))
+    params = [p for p in store.params if p.keras != 'internal']
+    if len(values) != len(params):
+        raise ValueError('{} holds {} variables, the model has {}'.format(filename, len(values), len(params)))
+    state = {p.name: _from_keras(p, np.asarray(a, dtype=np.float32)) for p, (_, a) in zip(params, values)}
+    store.load_state_dict(state, strict=False)
 
 
 def restore(dir_name, module, key=None, patch_size=None, restore_perf=False, fetch_stats=False):
     """Restore a trained model from a training directory (*.json training log + weights) — reference models/tfmodel.py:16-83, same
-    arguments, errors and return value; the weights are this stack's .npz snapshots (Keras .h5 interchange: SURVEY 8f N4)."""
+    arguments, errors and return value; the weights are Keras-layout .h5 files (load_model)."""
     training_log_path = None
     if dir_name is None:
         raise ValueError('dcn directory cannot be None')
@@ -107,22 +193,30 @@ class TFModel(object):
     def _weights_path(self, dirname):
         if not dirname.endswith(self.scoped_name):
             dirname = os.path.join(dirname, self.scoped_name)
-        return dirname, os.path.join(dirname, '{}.npz'.format(self.class_name.lower()))
+        return dirname, os.path.join(dirname, '{}.h5'.format(self.class_name.lower()))
 
     def save_model(self, dirname, epoch=0, save_args=False, quiet=False):
+        """reference models/tfmodel.py:150-166: ``<dirname>/<scoped_name>/<class>.h5`` in the Keras weight-file layout (+ .json)."""
         dirname, filename = self._weights_path(dirname)
         os.makedirs(dirname, exist_ok=True)
-        np.savez(filename, **(self._store.state_dict() if self._store is not None else {}))
+        if self._store is not None:
+            save_weights_h5(self._store, filename)
         if save_args:
             with open(os.path.join(dirname, '{}.json'.format(self.class_name.lower())), 'w') as f:
                 json.dump({'model': self.class_name, 'args': self.get_hyperparameters()}, f, indent=4)
 
     def load_model(self, dirname, quiet=False):
+        """reference models/tfmodel.py:168-182: the Keras h5 weight file; falls back to this stack's earlier .npz snapshots (the
+        reference falls back to a TF checkpoint, which has no counterpart here)."""
         dirname, filename = self._weights_path(dirname)
-        if not os.path.isfile(filename):
-            raise FileNotFoundError('No weights found at {} (Keras .h5 snapshots are not readable here)'.format(filename))
-        with np.load(filename) as data:
-            self._store.load_state_dict({k: data[k] for k in data.files})
+        legacy = filename[:-3] + '.npz'
+        if os.path.isfile(filename):
+            load_weights_h5(self._store, filename)
+        elif os.path.isfile(legacy):
+            with np.load(legacy) as data:
+                self._store.load_state_dict({k: data[k] for k in data.files})
+        else:
+            raise FileNotFoundError('No weights found at {} (or {})'.format(filename, legacy))
         self.reset_performance_stats()
 
     @classmethod

@@ -53,10 +53,13 @@ HOST_ONLY = False
 
 
 class Param:
-    __slots__ = ('name', 'shape', 'init', 'trainable', 'offset', 'size', 'value', 'grad')
+    __slots__ = ('name', 'shape', 'init', 'trainable', 'offset', 'size', 'value', 'grad', 'keras')
 
     def __init__(self, name, shape, init, trainable):
         self.name, self.shape, self.trainable = name, tuple(int(s) for s in shape), trainable
+        # storage rule of the Keras variable this parameter stands for (Keras .h5 interchange, models/tfmodel.py): None = same shape,
+        # 'dense' = (in, out), 'conv2d_transpose' = (2, 2, cout, cin), 'internal' = no Keras counterpart (not part of a weight file)
+        self.keras = None
         self.init = np.ascontiguousarray(np.broadcast_to(np.asarray(init, dtype=np.float32), self.shape))
         self.size = int(np.prod(self.shape)) if self.shape else 1
         self.offset, self.value, self.grad = None, None, None
@@ -123,6 +126,9 @@ class ParamStore:
             a = np.asarray(state[p.name], dtype=np.float32)
             if tuple(a.shape) != p.shape:
                 raise ValueError('shape mismatch for {}: {} vs {}'.format(p.name, a.shape, p.shape))
+            if p.value is None:                        # HOST_ONLY stores (no device buffers): the host copy is the state
+                p.init = np.ascontiguousarray(a).copy()
+                continue
             p.value.copy_(torch.from_numpy(np.ascontiguousarray(a)).reshape(p.shape))
 
 
@@ -130,7 +136,8 @@ class Conv2D:
     """Keras Conv2D / Dense / Conv2DTranspose(2,2) with explicit fprop / bprop through libni_b200.so."""
 
     def __init__(self, store, name, k, cin, cout, stride=1, padding='SAME', activation=None, use_bias=True, rng=None,
-                 kernel_init=None, bias_init=None, trainable=True, pad_mode=PAD_ZERO, alpha=0.2, bias_mod=0, explicit_pad=None):
+                 kernel_init=None, bias_init=None, trainable=True, pad_mode=PAD_ZERO, alpha=0.2, bias_mod=0, explicit_pad=None,
+                 keras=None):
         self.name, self.k, self.cin, self.cout, self.stride = name, int(k), int(cin), int(cout), int(stride)
         self.padding, self.act, self.alpha = padding, ACTIVATIONS[activation], float(alpha)
         self.pad_mode, self.bias_mod, self.explicit_pad = pad_mode, int(bias_mod), explicit_pad
@@ -138,9 +145,12 @@ class Conv2D:
         if kernel_init is None:
             kernel_init = glorot_uniform(rng, shape)
         self.w = store.add(name + '/kernel', shape, kernel_init, trainable)
+        self.w.keras = keras if keras is not None else ('conv2d_transpose' if self.bias_mod else None)
         nb = self.bias_mod if self.bias_mod else self.cout
         self.b = store.add(name + '/bias', (nb,), np.zeros((nb,), np.float32) if bias_init is None else bias_init,
                            trainable) if use_bias else None
+        if self.b is not None and keras == 'internal':
+            self.b.keras = 'internal'
         self._wt = None          # (kh,kw,cout,cin) copy for dgrad
         self._bexp = None        # bias tiled to cout when bias_mod (transposed conv)
 
