@@ -350,7 +350,7 @@ def run_ours(args, rank, world, local_rank):
     roofline_djpeg = None
     if dj is not None:
         dj_bytes = agg['ni_djpeg_fwd']['work'] / max(agg['ni_djpeg_fwd']['calls'], 1)
-        roofline_djpeg = {'kernel': 'djpeg_fwd3_kernel (fused colour+DCT+quant+IDCT+colour)', 'bound': 'hbm', 'achieved': dj['gbs'],
+        roofline_djpeg = {'kernel': 'djpeg_fwd4_kernel (persistent CTAs, TMA-fed stage; fused colour+DCT+quant+IDCT+colour)', 'bound': 'hbm', 'achieved': dj['gbs'],
                           'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': dj['gbs'] / pk['hbm_gbs'],
                           'traffic': traffic.get('djpeg_fwd', {}).get('dram_bytes'), 'traffic_launch': traffic.get('djpeg_fwd'),
                           'algorithmic_bytes_per_launch_avg': dj_bytes,

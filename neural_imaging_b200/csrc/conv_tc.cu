@@ -85,7 +85,9 @@ int get_scratch(size_t bytes, float** out) {
 
 // cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so that the library has no link-time
 // dependency on libcuda.so.1: it must still load (and export its symbols) on a build box without a GPU driver.
-int ni_encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+// swizzle: 0 = CU_TENSOR_MAP_SWIZZLE_NONE (dense rows: the dJPEG pixel tiles), 1 = 128-byte swizzle (the convolution operands)
+int ni_encode_tiled_sw(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                       int swizzle) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn fn = nullptr;
@@ -98,12 +100,16 @@ int ni_encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         ni_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return NI_ERR_CUDA;
     }
     return NI_OK;
+}
+int ni_encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    return ni_encode_tiled_sw(tm, base, rank, dims, strides_bytes, box, 1);
 }
 
 namespace {

@@ -6,13 +6,20 @@
 // >= 25 full-size temporaries). HBM traffic = read x + write y (24 B/pixel) forward; read x, dy + write dx backward
 // (36 B/pixel, X/Q is recomputed instead of saved).
 //
-// Work decomposition: a CTA owns a tile of 32 8x8 pixel blocks (24.5 KB of interleaved RGB staged in shared
-// memory); one thread owns one (block, Y/Cb/Cr channel) pair (warp = channel, lane = block) and keeps the whole 8x8
-// coefficient block in registers, so the 2-D DCT / quantisation / IDCT need no inter-thread exchange. The 1-D transforms use the
-// even/odd symmetry that the literal rows preserve (36 instead of 64 FMA-class ops per 8-point transform) with
-// the literal coefficients as FFMA immediates. The colour transforms (which mix channels) run in cooperative
-// per-pixel passes over the shared-memory tile.
+// Work decomposition: a tile = 32 8x8 pixel blocks (24.5 KB of interleaved RGB staged in shared memory); one thread owns one
+// (block, Y/Cb/Cr channel) pair (warp = channel, lane = block) and keeps the whole 8x8 coefficient block in registers, so the 2-D DCT /
+// quantisation / IDCT need no inter-thread exchange. The 1-D transforms use the even/odd symmetry that the literal rows preserve (36
+// instead of 64 FMA-class ops per 8-point transform) with the literal coefficients as FFMA immediates. The colour transforms (which mix
+// channels) run in cooperative per-pixel passes over the shared-memory tile.
+// Forward: generation 4 (djpeg_fwd4_kernel) — PERSISTENT CTAs (4 per SM) whose tiles arrive as one TMA box each (cp.async.bulk.tensor
+// into a dense stage, mbarrier completion), issued by a producer warp while the other warps transform the previous tile; generation 3
+// (djpeg_fwd3_kernel: one tile per CTA, 16-byte cp.async staging) remains for widths whose block grid does not tile into rectangular
+// 32-block boxes (W / 8 not a multiple of 4). Backward / table gradient: generation 3 structure.
 #include "ni_common.cuh"
+#include "tc_common.cuh"
+
+int ni_encode_tiled_sw(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                       int swizzle);   // conv_tc.cu
 
 namespace {
 
@@ -248,6 +255,187 @@ djpeg_fwd3_kernel(const float* __restrict__ x, float* __restrict__ y, float* __r
     }
 }
 
+__device__ __forceinline__ void store_plane(float* plane, const float (&v)[8][8]) {
+    float4* pp = reinterpret_cast<float4*>(plane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pp[2 * i] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        pp[2 * i + 1] = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+    }
+}
+__device__ __forceinline__ void load_plane(const float* plane, float (&v)[8][8]) {
+    const float4* pp = reinterpret_cast<const float4*>(plane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 a = pp[2 * i], b = pp[2 * i + 1];
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- forward, generation 4
+// Persistent CTAs with a TMA ring (BASELINE north_star: "TMA staging into shared memory"). The image tensor is described to the copy
+// engine as a 3-D tensor (24 floats = one 8-pixel block row | blocks per image row | N*H pixel rows); a tile of TBX x TBY = 32 blocks is
+// ONE cp.async.bulk.tensor box (24 x TBX x 8*TBY) that lands densely ([row][block][24]) in a stage and completes on an mbarrier. One
+// elected thread issues the box of the CTA's NEXT tile as soon as the current stage has been consumed, so the load runs under the
+// DCT / quantisation / IDCT / colour work of the current tile (generation 3 relies on 8 co-resident single-tile CTAs for that overlap
+// and spends ~3 of its 93 thread-instructions per pixel on issuing 16-byte cp.async copies).
+// The dense stage cannot be read block-per-lane without bank conflicts (block pitch 96 B: only even 16-byte slots), so a colour
+// pre-pass converts it to the planar level-shifted Y | Cb | Cr layout of generation 3 (block pitch 196 words): a quarter-warp takes
+// 4 blocks x 2 half-rows with the row staggered per lane (i0 below) so that BOTH its 48-byte dense reads (slots 3u mod 8) and its planar
+// stores (slots block + 2*row + half mod 8) are conflict-free. Arithmetic and its order are those of generation 3: bit-identical output.
+constexpr int kDenseFloats = kTileBlocks * 192;
+constexpr uint32_t kDenseBytes = kDenseFloats * sizeof(float);
+struct Fwd4Geom {
+    int tbx, log_tbx, tby;      // blocks per tile along x (power of two, 4..32) and y (32 / tbx)
+    int tiles_x, ntiles;        // tiles per image row of blocks, total
+    int nbr, nbh, nbw, rowf;    // block rows of the whole tensor (N * H / 8), per image, blocks per row, floats per pixel row
+    int cx_mul;                 // tensor-map coordinate of a tile along x = tile_x * cx_mul (K neighbouring blocks are one tensor-map element row, see ni_djpeg_fwd)
+};
+
+// CTA = four warps: warps 0-2 own the Y | Cb | Cr channels of the tile's 32 blocks in the DCT phase (warp = channel, lane = block);
+// warp 3 is the producer (its lane 0 issues the next tile's box as soon as the stage has been consumed: an issue costs the issuing
+// thread several hundred cycles, tools/hw_probes.py, and now falls into the DCT phase in which warp 3 has nothing else to do). All FOUR
+// warps share the two latency-bound passes — colour pre-pass (16 steps = 4 per warp) and colour output (512 four-pixel units = 4 per
+// thread) — which shortens them by a quarter to a third compared with three warps doing 6/5/5 steps.
+// Measured and dropped (profiles/r2_djpeg4_variants.json): 2 stages (3 CTAs per SM fit: slower), two or three compute groups sharing one
+// stage and one producer (18 compute warps per SM, but a stage's load + pre-pass serialise: 0.16 - 0.21 ms against 0.12).
+constexpr int kThreads4 = 128;
+
+template <int MODE, bool WRITE_X>
+__global__ void __launch_bounds__(kThreads4, 4)
+djpeg_fwd4_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ y, float* __restrict__ Xd, const Fwd4Geom g,
+                  const __grid_constant__ DjpegTables tab) {
+    extern __shared__ __align__(16) float smem[];
+    // 128-byte aligned stage base by OFFSET arithmetic (a uintptr_t round trip loses the shared address space: generic LD.E / ST.E)
+    float* stage = smem + (((128u - (tc::smem_u32(smem) & 127u)) & 127u) >> 2);
+    float* planar = stage + kDenseFloats;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(planar + kTileFloats);
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    auto issue = [&](int tx_, int ty_) {
+        tc::mbar_expect_tx(bar_full, kDenseBytes);
+        tc::tma_load_3d(stage, &tmX, bar_full, 0, tx_ * g.cx_mul, ty_ * g.tby * 8);
+    };
+    int tile = blockIdx.x;
+    int tx = tile % g.tiles_x, ty = tile / g.tiles_x;
+    const int step_x = gridDim.x % g.tiles_x, step_y = gridDim.x / g.tiles_x;
+    if (threadIdx.x == 96) {
+        tc::mbar_init(bar_full, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmX);
+        if (tile < g.ntiles) issue(tx, ty);
+    }
+    __syncthreads();
+
+    // this thread's block in the DCT phase
+    const int bxl = lane & (g.tbx - 1), byl = lane >> g.log_tbx;
+    float* bp = planar + lane * kBlockFloats + c * 64;
+    // Index arithmetic is tile-invariant: computed once per thread, in 32 bits.
+    // pre-pass role: lane = (block p_bl of a 16-block half tile, half row); step t = c + 4 tt covers half tile tt >> 1 at row
+    // (i0 + t) & 7 with the start row i0 staggered per lane (conflict-free dense reads AND planar stores, see above)
+    const int p_half = lane & 1, p_bl = lane >> 1;
+    const int p_i0 = (p_half ? ((p_bl & 1) ? 1 : 2) : 0) + c;
+    const int row_f = 24 << g.log_tbx;                                   // floats per dense pixel row
+    int p_src[2], p_dst[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const int b = h2 * 16 + p_bl;
+        p_src[h2] = (((b >> g.log_tbx) * 8) << g.log_tbx) * 24 + (b & (g.tbx - 1)) * 24 + p_half * 12;
+        p_dst[h2] = b * kBlockFloats + p_half * 4;
+    }
+    // colour-pass role: unit u = tid + 128 it -> block (tid >> 4) + 8 it, row / half (tid & 15) fixed per thread
+    const int o_r = threadIdx.x & 15, o_b0 = threadIdx.x >> 4;
+    const float* o_pl = planar + o_b0 * kBlockFloats + o_r * 4;
+    const int o_thr = (o_r >> 1) * g.rowf + (o_r & 1) * 12;              // float offset of the thread's 4 pixels inside its block
+    const int brow_f = 8 * g.rowf;                                       // floats per block row of the image tensor
+
+    for (int k = 0; tile < g.ntiles; tile += gridDim.x, ++k) {
+        const uint32_t ph = (uint32_t)(k & 1);
+        if (lane == 0) tc::mbar_wait(bar_full, ph, 20);
+        __syncwarp();
+        tc::mbar_wait(bar_full, ph, 21);              // every lane observes the completed phase itself (acquire), first try succeeds
+
+        // ---- colour pre-pass: dense interleaved RGB -> planar level-shifted Y | Cb | Cr
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+            const int i = (p_i0 + 4 * tt) & 7;
+            const float4* src = reinterpret_cast<const float4*>(stage + p_src[tt >> 1] + i * row_f);
+            const float4 q0 = src[0], q1 = src[1], q2 = src[2];
+            const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            float4* dst = reinterpret_cast<float4*>(planar + p_dst[tt >> 1] + i * 8);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                float k0, kr, kg, kb;
+                color_fwd_coeffs(cc, k0, kr, kg, kb);
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = fmaf(kb, f[3 * j + 2], fmaf(kg, f[3 * j + 1], fmaf(kr, f[3 * j], k0)));
+                dst[cc * 16] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();   // planar tile complete; every register loaded from the stage has been consumed by the stores above
+
+        const int rows_valid = g.nbr - ty * g.tby;      // block rows of this tile inside the tensor (>= tby except in the last tile row)
+        int ntx = tx + step_x, nty = ty + step_y;       // the CTA's next tile
+        if (ntx >= g.tiles_x) { ntx -= g.tiles_x; ++nty; }
+        if (c == 3) {
+            // ---- producer: the next tile's box goes into the stage while the other three warps transform this tile
+            if (lane == 0 && tile + (int)gridDim.x < g.ntiles) {
+                tc::fence_proxy_async_smem();
+                issue(ntx, nty);
+            }
+        } else {
+            // ---- per (block, channel): DCT -> quantisation -> IDCT in registers
+            float v[8][8];
+            load_plane(bp, v);
+            dct2d_fwd(v);
+            if (c == 0) quantise_block<MODE, 0>(v, tab); else quantise_block<MODE, 1>(v, tab);
+            if (WRITE_X) {
+                if (byl < rows_valid) {
+                    const int gbr = ty * g.tby + byl;   // block row of this thread's block in the (N * H / 8) x nbw block grid
+                    const long long n = gbr / g.nbh, by = gbr % g.nbh, nb = (long long)g.nbw * g.nbh;
+                    float4* o = reinterpret_cast<float4*>(Xd + ((n * 3 + c) * nb + by * g.nbw + (tx << g.log_tbx) + bxl) * 64);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        o[kk * 2 + 0] = make_float4(v[kk][0], v[kk][1], v[kk][2], v[kk][3]);
+                        o[kk * 2 + 1] = make_float4(v[kk][4], v[kk][5], v[kk][6], v[kk][7]);
+                    }
+                }
+            }
+            dct2d_inv(v);
+            store_plane(bp, v);
+        }
+        __syncthreads();
+
+        // ---- colour pass: unit u = (block u/16, row (u%16)/2, half u%2) = 4 pixels = 48 contiguous output bytes; all planar loads of a
+        // thread's four units first, each into registers of its own (a load into a register that an earlier global store still has to read
+        // waits on that store)
+        float* const y_tile = y + ((long long)ty * g.tby * brow_f + (long long)(tx << g.log_tbx) * 24 + o_thr);
+        float4 pl[4][3];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const float4* pp = reinterpret_cast<const float4*>(o_pl + it * 8 * kBlockFloats);
+            pl[it][0] = pp[0]; pl[it][1] = pp[16]; pl[it][2] = pp[32];
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int bb = o_b0 + it * 8;
+            const int brl = bb >> g.log_tbx;
+            if (brl < rows_valid) {
+                float f[12];
+                color_inv_clip4(pl[it][0], pl[it][1], pl[it][2], f);
+                float4* o = reinterpret_cast<float4*>(y_tile + (brl * brow_f + (bb & (g.tbx - 1)) * 24));
+                __stcs(o, make_float4(f[0], f[1], f[2], f[3]));
+                __stcs(o + 1, make_float4(f[4], f[5], f[6], f[7]));
+                __stcs(o + 2, make_float4(f[8], f[9], f[10], f[11]));
+            }
+        }
+        __syncthreads();   // the planar tile is rewritten by the next pre-pass
+        tx = ntx; ty = nty;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- backward, generation 3
 // dx = J^T dy with everything recomputed from x. Chain (per block-channel):
 //   r = C_F[1,255x]-127 ; Z = (F r F^T)/Q ; Zq = q(Z) ; xi = F^T (Zq*Q) F ; ypre = (C_I[1,xi+127])/255 ; y = clip(ypre)
@@ -273,24 +461,6 @@ __device__ __forceinline__ void quantise_block_grad(float (&v)[8][8], float (&qg
             v[k][l] = quant_fwd<MODE>(z) * tab.q[CC][k * 8 + l];
         }
 }
-__device__ __forceinline__ void store_plane(float* plane, const float (&v)[8][8]) {
-    float4* pp = reinterpret_cast<float4*>(plane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        pp[2 * i] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-        pp[2 * i + 1] = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
-    }
-}
-__device__ __forceinline__ void load_plane(const float* plane, float (&v)[8][8]) {
-    const float4* pp = reinterpret_cast<const float4*>(plane);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 a = pp[2 * i], b = pp[2 * i + 1];
-        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
-        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
-    }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 4)
 djpeg_bwd3_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int nblk,
@@ -518,6 +688,53 @@ extern "C" int ni_djpeg_fwd(const float* x, float* y, float* x_deq, int n, int h
     NI_REQUIRE(fill_tables(tab, q_luma, q_chroma) == 0, "ni_djpeg_fwd: quantisation tables must be positive");
     const long long nblk = (long long)n * (h / 8) * (w / 8);
     NI_REQUIRE(nblk < (1ll << 31) - 64 * kTileBlocks, "ni_djpeg_fwd: tensor too large (%lld blocks)", nblk);
+    // generation 4 (persistent CTAs, TMA ring) where the block grid tiles into rectangular 32-block boxes; generation 3 otherwise
+    const int nbw = w / 8;
+    int variant = 4, ctas = 4;
+#ifdef NI_DEV
+    if (const char* e = getenv("NI_DJPEG_FWD")) variant = e[0] - '0';       // 3 | 4
+    if (const char* e = getenv("NI_DJPEG_CTAS")) ctas = atoi(e) > 0 ? atoi(e) : 4;
+#endif
+    if (variant == 4 && nbw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (long long)n * h < (1ll << 31)) {
+        Fwd4Geom g;
+        g.tbx = 4; g.log_tbx = 2;
+        while (g.tbx < 32 && nbw % (g.tbx * 2) == 0) { g.tbx *= 2; ++g.log_tbx; }
+        g.tby = kTileBlocks / g.tbx;
+        g.nbw = nbw; g.nbh = h / 8; g.nbr = n * g.nbh; g.rowf = w * 3;
+        g.tiles_x = nbw / g.tbx;
+        const long long nt = (long long)g.tiles_x * ((g.nbr + g.tby - 1) / g.tby);
+        NI_REQUIRE(nt < (1ll << 31), "ni_djpeg_fwd: tensor too large (%lld tiles)", nt);
+        g.ntiles = (int)nt;
+        // The copy engine works row by row (a few cycles per box row whatever its length, tools/hw_probes.py), and the 24 floats of one
+        // block row are only 96 bytes: K = 8 (or 4) neighbouring blocks of an image row are contiguous in memory, so the innermost
+        // tensor dimension is 24 K floats (768 bytes) and a tile is 8 * tby * tbx / K box rows instead of 256. Same bytes, same dense
+        // shared-memory image ([pixel row][block][24]).
+        const int kmerge = g.tbx % 8 == 0 ? 8 : 4;
+        g.cx_mul = g.tbx / kmerge;
+        CUtensorMap tm;
+        const cuuint64_t dims[3] = {(cuuint64_t)24 * kmerge, (cuuint64_t)(nbw / kmerge), (cuuint64_t)n * h};
+        const cuuint64_t strides[2] = {(cuuint64_t)96 * kmerge, (cuuint64_t)w * 12};
+        const cuuint32_t box[3] = {(cuuint32_t)24 * kmerge, (cuuint32_t)(g.tbx / kmerge), (cuuint32_t)g.tby * 8};
+        int rc = ni_encode_tiled_sw(&tm, x, 3, dims, strides, box, 0);
+        if (rc) return rc;
+        const size_t smem_bytes = 128 + kDenseBytes + kTileFloats * sizeof(float) + 2 * sizeof(uint64_t);
+        const int grid4 = (int)(nt < (long long)ctas * ni_num_sms() ? nt : (long long)ctas * ni_num_sms());
+#define NI_FWD4(MODE, WX)                                                                                        \
+    {                                                                                                             \
+        rc = set_smem(djpeg_fwd4_kernel<MODE, WX>, smem_bytes);                                                   \
+        if (rc) return rc;                                                                                        \
+        djpeg_fwd4_kernel<MODE, WX><<<grid4, kThreads4, smem_bytes, stream>>>(tm, y, x_deq, g, tab);              \
+    }
+        if (x_deq) {
+            if (mode == 0) NI_FWD4(0, true) else if (mode == 1) NI_FWD4(1, true) else NI_FWD4(2, true)
+        } else {
+            if (mode == 0) NI_FWD4(0, false) else if (mode == 1) NI_FWD4(1, false) else NI_FWD4(2, false)
+        }
+#undef NI_FWD4
+        NI_LAUNCH_CHECK();
+        NI_COUNT_LAUNCH(1);
+        return NI_OK;
+    }
     const int grid = ni_cdiv(nblk, kTileBlocks);
 #define NI_FWD(MODE, WX)                                                                                      \
     {                                                                                                          \

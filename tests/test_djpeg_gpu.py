@@ -21,7 +21,11 @@ def _oracle(x, q, mode, dtype):
 
 @pytest.mark.parametrize('mode', ['sin', 'harmonic'])
 @pytest.mark.parametrize('shape,q', [((1, 8, 8, 3), 50), ((3, 16, 24, 3), 80), ((2, 128, 128, 3), 50), ((1, 256, 256, 3), 90),
-                                     ((5, 40, 8, 3), 10), ((2, 8, 72, 3), 100)])
+                                     ((5, 40, 8, 3), 10), ((2, 8, 72, 3), 100),
+                                     # rectangular 32-block tiles of the TMA path: 8 x 4 blocks with a partial last tile across images,
+                                     # 4 x 8 blocks with three tiles per block row and a single valid block row, 16 x 2, 32 x 1
+                                     ((3, 24, 64, 3), 60), ((1, 8, 96, 3), 40), ((7, 16, 128, 3), 70), ((3, 8, 256, 3), 35),
+                                     ((2, 64, 32, 3), 25)])
 def test_forward_continuous_modes(mode, shape, q):
     """Continuous quantisers: strict 1e-5 (scale-relative) against the float64 oracle, y and coefficients."""
     from neural_imaging_b200 import ops
