@@ -7,6 +7,7 @@ Layout conventions (TensorFlow's): activations NHWC, Conv2D kernels HWIO (kh, kw
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -50,6 +51,24 @@ def variance_scaling(rng, shape, scale=1.0):
 
 # bench.py's CPU-baseline leg sets this to build the models' initial weights without a GPU (specs only, no device buffers)
 HOST_ONLY = False
+
+# The filter gradient of a layer runs on a SIDE stream next to the same layer's input gradient (both only read dy; they write disjoint
+# buffers) and is joined before bprop returns, so nothing outside the pair can observe the concurrency. The two persistent kernels cannot
+# share an SM (shared memory), so the later one takes the SMs the earlier one leaves: the tail of one fills with the head of the other and
+# grids smaller than the machine (deep layers, small per-GPU batches) run side by side. Off while bench.py's per-entry event profiler is
+# installed (events on the main stream would mis-attribute the time). The fork / join are stream waits, so they capture into CUDA graphs.
+WGRAD_OVERLAP = os.environ.get('NI_WGRAD_OVERLAP', '1') != '0'
+_SIDE_STREAMS = {}
+
+
+def _side_stream():
+    if not WGRAD_OVERLAP or _lib.PROFILER is not None:
+        return None
+    dev = torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class Param:
@@ -234,8 +253,30 @@ class Conv2D:
         (`bprop(fuse_prev=...)`): forward output y (plain NHWC, channel pitch / offset), activation, bias-gradient pointer."""
         return (y, self.cout if pitch is None else int(pitch), int(coff), self.act, self.alpha, self.bias_grad_ptr(need_dw), self.bias_mod)
 
-    def bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
-              dx_accumulate=False, need_dw=True, dpad=None, act_bias_done=False, fuse_prev=None):
+    def bprop(self, x, y, dy, dx, d, **kw):
+        """Backward of fprop(x -> y): see _bprop. The filter gradient is forked onto the side stream (when an input gradient follows it)
+        and joined here, before the caller can touch any of the buffers."""
+        self._forked = None
+        try:
+            return self._bprop(x, y, dy, dx, d, **kw)
+        finally:
+            if self._forked is not None:
+                torch.cuda.current_stream().wait_stream(self._forked)
+                self._forked = None
+
+    def _wgrad(self, dd, x, dy, dw, overlap):
+        """ni_conv2d_wgrad on the side stream (behind everything queued on the main stream so far) when `overlap`, else in order."""
+        L = _lib.lib()
+        side = _side_stream() if overlap else None
+        if side is None:
+            L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(dw), stream())
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(dw), side.cuda_stream)
+        self._forked = side
+
+    def _bprop(self, x, y, dy, dx, d, weight=None, dweight=None, need_dx=True, dy_addr=None, dx_addr=None,
+               dx_accumulate=False, need_dw=True, dpad=None, act_bias_done=False, fuse_prev=None):
         """Backward of fprop(x -> y) described by the forward descriptor `d`.
 
         For mirrored padding (REFLECT / SYMMETRIC + VALID conv) the input gradient is computed on the padded domain into
@@ -276,7 +317,7 @@ class Conv2D:
         dd.out_pitch, dd.out_coff, dd.out_mode = dyp, dyo, dym
         dd.accumulate = 0
         if need_dw and (self.w.trainable or dweight is not None):
-            L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(self.w.grad if dweight is None else dweight), st)
+            self._wgrad(dd, x, dy, self.w.grad if dweight is None else dweight, overlap=need_dx)
         if need_dx:
             wv = self.w.value if weight is None else weight
             if d.pad_mode != PAD_ZERO:
