@@ -622,6 +622,7 @@ def run_c2(args, rank, world, local_rank):
     L.ni_reset_launch_count()
     ms = timed(step, args.steps)
     launches = int(L.ni_launch_count())
+    clk = clocks.stop() if rank == 0 else None
     e2e(); ms_e2e = timed(e2e, args.steps)
     agg, prof_ms = _profiled(step, args.steps)
     pk = peaks()
@@ -663,6 +664,7 @@ def run_c3(args, rank, world, local_rank):
     L.ni_reset_launch_count()
     ms = timed(step, args.steps)
     launches = int(L.ni_launch_count())
+    clk = clocks.stop() if rank == 0 else None
     e2e(); ms_e2e = timed(e2e, args.steps)
     agg, prof_ms = _profiled(step, args.steps)
     pk = peaks()

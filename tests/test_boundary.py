@@ -176,3 +176,29 @@ def test_header_is_plain_c():
         assert out.returncode == 0, out.stderr
     src = open(header).read()
     assert 'torch' not in src and 'at::Tensor' not in src and '#include <cuda' not in src
+
+
+def test_no_undefined_names_in_bench_and_package():
+    """Static check (symtable): a function of bench.py / the package that reads a name which is neither local, nor module-level, nor a
+    builtin fails only when its configuration runs — on the GPU box, where a NameError costs a bench line (it did once: `clk` in run_c2)."""
+    import builtins
+    import symtable
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')]
+    for base, _, files in os.walk(os.path.join(root, 'neural_imaging_b200')):
+        paths += [os.path.join(base, f) for f in files if f.endswith('.py')]
+    bad = []
+    for path in paths:
+        with open(path) as fh:
+            top = symtable.symtable(fh.read(), path, 'exec')
+        module_names = {s.get_name() for s in top.get_symbols()}
+
+        def walk(table):
+            for ch in table.get_children():
+                if ch.get_type() == 'function':
+                    for s in ch.get_symbols():
+                        if s.is_global() and not s.is_declared_global() and s.get_name() not in module_names and not hasattr(builtins, s.get_name()):
+                            bad.append((os.path.relpath(path, root), ch.get_name(), s.get_name()))
+                walk(ch)
+        walk(top)
+    assert not bad, bad
