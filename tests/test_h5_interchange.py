@@ -174,3 +174,39 @@ def test_keras_layout_converters_and_errors(tmp_path):
     m3 = _host_model(forensics.FAN, n_classes=5)
     m3.load_model(os.path.join(str(tmp_path), 'legacy'))
     assert all(np.array_equal(p.init + 2.0, q.init) for p, q in zip(m._store.params, m3._store.params))
+
+
+def test_loader_accepts_what_keras_writes_around_the_weights(tmp_path):
+    """Keras writes a group for EVERY layer (weightless ones carry an empty float64 `weight_names` attribute), `model.save()` nests the
+    same structure under /model_weights, and layer names differ from this stack's: the loader must skip the former, find the latter and
+    match purely by order."""
+    from neural_imaging_b200.models import forensics
+    m = _host_model(forensics.FAN, n_classes=5)
+    m.save_model(str(tmp_path))
+    f = h5lite.File(os.path.join(str(tmp_path), 'fan', 'fan.h5'))
+    tree, attrs, names = {}, {}, []
+    k = 0
+    for layer in f.attrs['layer_names']:
+        g = f[layer.decode()]
+        new = 'renamed_layer_%d' % k                                          # Keras' automatic names depend on the session
+        k += 1
+        wn = []
+        tree[new] = {new: {}}
+        for w in g.attrs['weight_names']:
+            leaf = w.decode().rsplit('/', 1)[1]
+            tree[new][new][leaf] = g[w.decode()].read()
+            wn.append('{}/{}'.format(new, leaf).encode())
+        names.append(new.encode())
+        attrs['model_weights/' + new] = {'weight_names': np.array(wn, dtype='S')}
+        pool = 'max_pooling2d_%d' % k                                          # a weightless layer after every weighted one
+        tree[pool] = {}
+        names.append(pool.encode())
+        attrs['model_weights/' + pool] = {'weight_names': np.array([])}
+    attrs['model_weights'] = {'layer_names': np.array(names, dtype='S'), 'backend': np.bytes_(b'tensorflow'), 'keras_version': np.bytes_(b'2.2.4-tf')}
+    attrs[''] = {'keras_version': np.bytes_(b'2.2.4-tf'), 'model_config': np.bytes_(b'{}')}
+    out = os.path.join(str(tmp_path), 'saved', 'fan')
+    os.makedirs(out)
+    h5lite.write(os.path.join(out, 'fan.h5'), {'model_weights': tree}, attrs)
+    m2 = _host_model(forensics.FAN, n_classes=5, seed=99)
+    m2.load_model(os.path.join(str(tmp_path), 'saved'))
+    assert all(np.array_equal(p.init, q.init) for p, q in zip(m._store.params, m2._store.params))
