@@ -274,12 +274,12 @@ __device__ __forceinline__ void load_plane(const float* plane, float (&v)[8][8])
 }
 
 // ---------------------------------------------------------------------------------------------------- forward, generation 4
-// Persistent CTAs with a TMA ring (BASELINE north_star: "TMA staging into shared memory"). The image tensor is described to the copy
-// engine as a 3-D tensor (24 floats = one 8-pixel block row | blocks per image row | N*H pixel rows); a tile of TBX x TBY = 32 blocks is
-// ONE cp.async.bulk.tensor box (24 x TBX x 8*TBY) that lands densely ([row][block][24]) in a stage and completes on an mbarrier. One
-// elected thread issues the box of the CTA's NEXT tile as soon as the current stage has been consumed, so the load runs under the
-// DCT / quantisation / IDCT / colour work of the current tile (generation 3 relies on 8 co-resident single-tile CTAs for that overlap
-// and spends ~3 of its 93 thread-instructions per pixel on issuing 16-byte cp.async copies).
+// Persistent CTAs fed by TMA boxes (BASELINE north_star: "TMA staging into shared memory"). The image tensor is described to the copy
+// engine as a 3-D tensor (24 K floats = the 8-pixel rows of K neighbouring blocks | W / 8 / K | N*H pixel rows; K = 8 or 4, see
+// ni_djpeg_fwd); a tile of TBX x TBY = 32 blocks is ONE cp.async.bulk.tensor box that lands densely ([pixel row][block][24]) in a stage
+// and completes on an mbarrier. One thread issues the box of the CTA's NEXT tile as soon as the current stage has been consumed, so the
+// load runs under the DCT / quantisation / IDCT / colour work of the current tile (generation 3 relies on 8 co-resident single-tile CTAs
+// for that overlap and spends instructions on issuing 16-byte cp.async copies).
 // The dense stage cannot be read block-per-lane without bank conflicts (block pitch 96 B: only even 16-byte slots), so a colour
 // pre-pass converts it to the planar level-shifted Y | Cb | Cr layout of generation 3 (block pitch 196 words): a quarter-warp takes
 // 4 blocks x 2 half-rows with the row staggered per lane (i0 below) so that BOTH its 48-byte dense reads (slots 3u mod 8) and its planar
