@@ -2,7 +2,9 @@
 // VALID 5x5 convolution 3 -> 3 channels, no bias — forward, input gradient (with the transpose of the mirrored pad folded in) and filter
 // gradient. 1280 images of 128x128x3 per step: 0.25 GB in, 0.25 GB out, 225 FMAs per pixel. The generic small-channel kernels ran these
 // three launches at 9-12 TFLOP/s (0.8 + 1.0 + 0.43 (pad fold) + 1.0 ms per step at B = 256); here every thread owns a 2x2 pixel quad x 3
-// channels, streams the shared 6x6 window through registers with 64-bit shared loads, and reads the 225 weights as broadcast 128-bit words.
+// channels, streams the shared 6x6 window through registers with 64-bit shared loads, and takes the 225 weights as CONSTANT-BANK operands of
+// its FMAs (staged into __constant__ memory by a stream-ordered device-to-device copy): with the weights as 128-bit shared-memory broadcasts the
+// kernels issued one LDS per 4.4 FMAs, which is the shared-memory pipe's limit, not the FMA pipe's.
 #include "ni_common.cuh"
 #include "tile3.cuh"
 
@@ -17,26 +19,42 @@ __device__ __forceinline__ int symm_i(int u, int n) {
     return u < 0 ? 0 : (u >= n ? n - 1 : u);
 }
 
-// weights (5, 5, ci, co) -> shared [tap][ci][4] (co padded to 4) or, TRANSPOSED, [tap][co][4] (ci padded): one 128-bit broadcast per FMA triple
-template <bool TRANSPOSED>
-__device__ __forceinline__ void load_weights(float* sw, const float* __restrict__ w) {
-    for (int t = threadIdx.x; t < 25 * 3 * 4; t += kThreads) {
-        const int e = t & 3, m = (t >> 2) % 3, tap = t / 12;
-        float v = 0.f;
-        if (e < 3) v = TRANSPOSED ? __ldg(w + (tap * 3 + e) * 3 + m) : __ldg(w + (tap * 3 + m) * 3 + e);
-        sw[t] = v;
-    }
+// weights (5, 5, ci, co) -> [tap][ci][4] (co padded to 4) for the forward kernel or, TRANSPOSED, [tap][co][4] (ci padded) for the input
+// gradient, in __constant__ memory: every weight index of the unrolled kernels is a compile-time constant, so the FMAs read c[bank][offset]
+// directly. The filter lives in device memory (it is renormalised on the device every step), hence prep kernel -> staging buffer ->
+// cudaMemcpyToSymbolAsync(device to device) on the caller's stream (stream-ordered, capturable). One filter per direction at a time per
+// process: launches that use different filters must be ordered on one stream (they are: the forensic network owns one such layer).
+__constant__ float c_wf[25 * 3 * 4];
+__constant__ float c_wb[25 * 3 * 4];
+__device__ float g_wstage[2][25 * 3 * 4];
+
+__global__ void cconv5_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ dst, int transposed) {
+    const int t = threadIdx.x;
+    if (t >= 25 * 3 * 4) return;
+    const int e = t & 3, m = (t >> 2) % 3, tap = t / 12;
+    float v = 0.f;
+    if (e < 3) v = transposed ? __ldg(w + (tap * 3 + e) * 3 + m) : __ldg(w + (tap * 3 + m) * 3 + e);
+    dst[t] = v;
+}
+
+int stage_weights(const float* w, int transposed, cudaStream_t st) {
+    static float* stage = nullptr;
+    if (!stage) NI_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&stage), g_wstage));
+    float* dst = stage + transposed * (25 * 3 * 4);
+    cconv5_prep_weights_kernel<<<1, 320, 0, st>>>(w, dst, transposed);
+    NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
+    if (transposed) NI_CUDA(cudaMemcpyToSymbolAsync(c_wb, dst, sizeof(float) * 25 * 3 * 4, 0, cudaMemcpyDeviceToDevice, st));
+    else NI_CUDA(cudaMemcpyToSymbolAsync(c_wf, dst, sizeof(float) * 25 * 3 * 4, 0, cudaMemcpyDeviceToDevice, st));
+    return NI_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------ forward
 constexpr int kFH = 2, kFX = 4, kFC = 40, kFRS = kFC * 3;
 
 __global__ void __launch_bounds__(kThreads, 3)
-cconv5_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, int W) {
+cconv5_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W) {
     __shared__ __align__(16) float tile[(kTS + 2 * kFH) * kFRS];
-    __shared__ __align__(16) float sw[25 * 3 * 4];
     const int n = blockIdx.z, y0 = blockIdx.y * kTS, x0 = blockIdx.x * kTS;
-    load_weights<false>(sw, w);
     load_tile3<kTS, kFH, kFX, kFC, TILE_SYMMETRIC, kThreads>(tile, x + (size_t)n * H * W * 3, H, W, y0, x0);
     __syncthreads();
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -61,13 +79,13 @@ cconv5_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, floa
             for (int b = 0; b < 5; ++b)
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
-                    const float4 wv = *reinterpret_cast<const float4*>(sw + ((a * 5 + b) * 3 + ci) * 4);
+                    const int wi = ((a * 5 + b) * 3 + ci) * 4;          // compile-time after unrolling: constant-bank operands
 #pragma unroll
                     for (int qb = 0; qb < 2; ++qb) {
                         const float xv = row[(qb + b) * 3 + ci];
-                        acc[qa][qb][0] = fmaf(wv.x, xv, acc[qa][qb][0]);
-                        acc[qa][qb][1] = fmaf(wv.y, xv, acc[qa][qb][1]);
-                        acc[qa][qb][2] = fmaf(wv.z, xv, acc[qa][qb][2]);
+                        acc[qa][qb][0] = fmaf(c_wf[wi], xv, acc[qa][qb][0]);
+                        acc[qa][qb][1] = fmaf(c_wf[wi + 1], xv, acc[qa][qb][1]);
+                        acc[qa][qb][2] = fmaf(c_wf[wi + 2], xv, acc[qa][qb][2]);
                     }
                 }
         }
@@ -100,12 +118,10 @@ __device__ __forceinline__ int symm_aliases(int p, int n, int (&u)[3]) {
 }
 
 __global__ void __launch_bounds__(kThreads, 3)
-cconv5_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int H, int W, int accumulate) {
+cconv5_bwd_data_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int accumulate) {
     __shared__ __align__(16) float tile[(kTS + 2 * kBH) * kBRS];      // dy, rows y0 - 4 .., columns x0 - 8 .., zero outside the image
-    __shared__ __align__(16) float sw[25 * 3 * 4];                    // [tap][co][ci pad 4]
     __shared__ float ring[kRN * kRN * 3];                             // dxp of the cells OUTSIDE the image (border tiles only)
     const int n = blockIdx.z, y0 = blockIdx.y * kTS, x0 = blockIdx.x * kTS;
-    load_weights<true>(sw, w);
     load_tile3<kTS, kBH, kBX, kBC, TILE_ZERO, kThreads>(tile, dy + (size_t)n * H * W * 3, H, W, y0, x0);
     __syncthreads();
     const bool border = (y0 < 2) || (x0 < 2) || (y0 + kTS + 2 > H) || (x0 + kTS + 2 > W);
@@ -122,8 +138,8 @@ cconv5_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
                     const float* g = tile + (i + 4 - a) * kBRS + (j + 8 - b) * 3;
 #pragma unroll
                     for (int co = 0; co < 3; ++co) {
-                        const float4 wv = *reinterpret_cast<const float4*>(sw + ((a * 5 + b) * 3 + co) * 4);
-                        a0 = fmaf(wv.x, g[co], a0); a1 = fmaf(wv.y, g[co], a1); a2 = fmaf(wv.z, g[co], a2);
+                        const float* wv = c_wb + ((a * 5 + b) * 3 + co) * 4;      // run-time index: constant-cache loads (border tiles only)
+                        a0 = fmaf(wv[0], g[co], a0); a1 = fmaf(wv[1], g[co], a1); a2 = fmaf(wv[2], g[co], a2);
                     }
                 }
             ring[t * 3] = a0; ring[t * 3 + 1] = a1; ring[t * 3 + 2] = a2;
@@ -150,13 +166,13 @@ cconv5_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
             for (int b = 0; b < 5; ++b)
 #pragma unroll
                 for (int co = 0; co < 3; ++co) {
-                    const float4 wv = *reinterpret_cast<const float4*>(sw + ((a * 5 + b) * 3 + co) * 4);
+                    const int wi = ((a * 5 + b) * 3 + co) * 4;          // compile-time after unrolling: constant-bank operands
 #pragma unroll
                     for (int qb = 0; qb < 2; ++qb) {
                         const float g = row[(4 + qb - b) * 3 + co];
-                        acc[qa][qb][0] = fmaf(wv.x, g, acc[qa][qb][0]);
-                        acc[qa][qb][1] = fmaf(wv.y, g, acc[qa][qb][1]);
-                        acc[qa][qb][2] = fmaf(wv.z, g, acc[qa][qb][2]);
+                        acc[qa][qb][0] = fmaf(c_wb[wi], g, acc[qa][qb][0]);
+                        acc[qa][qb][1] = fmaf(c_wb[wi + 1], g, acc[qa][qb][1]);
+                        acc[qa][qb][2] = fmaf(c_wb[wi + 2], g, acc[qa][qb][2]);
                     }
                 }
         }
@@ -195,21 +211,29 @@ cconv5_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
 }
 
 // ------------------------------------------------------------------------------------------------------------ filter gradient
-// dw[a, b, ci, co] = sum_{n, p} xpad[p + (a, b) - 2, ci] dy[p, co]. Thread role = (a, ci, co) with 5 accumulators (b); 5 row-splits per
-// role; planar tiles so that a 4-pixel step is two 128-bit loads of x and one of dy feeding 20 FMAs. Persistent over tiles; one
-// atomicAdd per output per CTA.
-constexpr int kWX = 40;                          // planar x tile: 36 rows x 36 columns (x0 - 2 ..), row stride 40
-constexpr int kRoles = 45, kSplits = 5;
+// dw[a, b, ci, co] = sum_{n, p} xpad[p + (a, b) - 2, ci] dy[p, co]. Thread role = (a, ci) with 15 accumulators (3 co x 5 b); 16 row-splits per
+// role (two tile rows each); planar tiles so that a 4-pixel step is two 128-bit loads of x and three of dy feeding 60 FMAs (the first
+// version's role = (a, ci, co) fed 20 FMAs from three loads and sat on the shared-memory pipe). Row pitch 36 and a plane pitch = 3 mod 8
+// 16-byte slots put the eight (a, ci) rows of a quarter-warp in eight different bank slots. Persistent over tiles; one atomicAdd per output
+// per CTA.
+constexpr int kWX = 36;                          // planar x tile: 36 rows x 36 columns (x0 - 2 ..)
+constexpr int kWP = (kTS + 4) * kWX + 28;        // x plane pitch: 331 slots of 16 bytes = 3 (mod 8)
+constexpr int kDX = 36;                          // planar dy tile: 32 rows x 32 columns, row pitch 36
+constexpr int kRoles = 15, kSplits = 16;
 
 __global__ void __launch_bounds__(kThreads)
 cconv5_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int N, int H, int W,
                          int tiles_x, int tiles_y) {
-    __shared__ __align__(16) float sx[3 * (kTS + 4) * kWX];
-    __shared__ __align__(16) float sd[3 * kTS * kTS];
-    const int role = threadIdx.x % kRoles, split = threadIdx.x / kRoles;      // threads 225 .. 255 only help loading
+    __shared__ __align__(16) float sx[3 * kWP];
+    __shared__ __align__(16) float sd[3 * kTS * kDX];
+    const int role = threadIdx.x % kRoles, split = threadIdx.x / kRoles;      // threads 240 .. 255 only help loading
     const bool active = threadIdx.x < kRoles * kSplits;
-    const int a = role / 9, ci = (role / 3) % 3, co = role % 3;
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const int a = role / 3, ci = role % 3;
+    float acc[3][5];
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+        for (int bb = 0; bb < 5; ++bb) acc[co][bb] = 0.f;
     const int total = tiles_x * tiles_y * N;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int n = tile / (tiles_x * tiles_y), tr = tile - n * tiles_x * tiles_y;
@@ -222,7 +246,7 @@ cconv5_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ 
             // x: columns x0 - 2 .. x0 + 33 start at an even, not 16-byte aligned float: element-wise through the index map
             for (int t = threadIdx.x; t < (kTS + 4) * 36 * 3; t += kThreads) {
                 const int ch = t % 3, col = (t / 3) % 36, r = t / 108;
-                sx[(ch * (kTS + 4) + r) * kWX + col] = __ldg(xi + ((size_t)symm_i(y0 - 2 + r, H) * W + symm_i(x0 - 2 + col, W)) * 3 + ch);
+                sx[ch * kWP + r * kWX + col] = __ldg(xi + ((size_t)symm_i(y0 - 2 + r, H) * W + symm_i(x0 - 2 + col, W)) * 3 + ch);
             }
             const bool vec = (W & 3) == 0 && x0 + kTS <= W;
             if (vec) {
@@ -236,50 +260,59 @@ cconv5_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int f = 4 * v + k, col = f / 3, ch = f - col * 3;
-                        sd[(ch * kTS + r) * kTS + col] = e[k];
+                        sd[(ch * kTS + r) * kDX + col] = e[k];
                     }
                 }
             } else {
                 for (int t = threadIdx.x; t < kTS * kTS * 3; t += kThreads) {
                     const int ch = t % 3, col = (t / 3) % kTS, r = t / (3 * kTS);
                     const int gy = y0 + r, gx = x0 + col;
-                    sd[(ch * kTS + r) * kTS + col] = (gy < H && gx < W) ? __ldg(di + ((size_t)gy * W + gx) * 3 + ch) : 0.f;
+                    sd[(ch * kTS + r) * kDX + col] = (gy < H && gx < W) ? __ldg(di + ((size_t)gy * W + gx) * 3 + ch) : 0.f;
                 }
             }
         }
         __syncthreads();
         if (!active) continue;
-        for (int yy = split; yy < kTS; yy += kSplits) {
-            const float* xr = sx + (ci * (kTS + 4) + yy + a) * kWX;
-            const float* dr = sd + (co * kTS + yy) * kTS;
+#pragma unroll
+        for (int rr = 0; rr < kTS / kSplits; ++rr) {
+            const int yy = split * (kTS / kSplits) + rr;
+            const float* xr = sx + ci * kWP + (yy + a) * kWX;
+            const float* dr = sd + yy * kDX;
 #pragma unroll
             for (int xq = 0; xq < kTS; xq += 4) {
                 const float4 x0v = *reinterpret_cast<const float4*>(xr + xq), x1v = *reinterpret_cast<const float4*>(xr + xq + 4);
-                const float4 dv = *reinterpret_cast<const float4*>(dr + xq);
                 const float xv[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
-                const float g[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                for (int co = 0; co < 3; ++co) {
+                    const float4 dv = *reinterpret_cast<const float4*>(dr + co * kTS * kDX + xq);
+                    const float g[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-                    for (int b = 0; b < 5; ++b) acc[b] = fmaf(xv[e + b], g[e], acc[b]);
+                    for (int e = 0; e < 4; ++e)
+#pragma unroll
+                        for (int bb = 0; bb < 5; ++bb) acc[co][bb] = fmaf(xv[e + bb], g[e], acc[co][bb]);
+                }
             }
         }
     }
     // reduce the row-splits through shared memory, then one atomicAdd per output per CTA
     __syncthreads();
-    float* red = sx;
+    float* red = sx;                                       // (kSplits - 1) * 15 roles * 15 accumulators = 3375 floats <= 3 * kWP
     if (active && split > 0) {
 #pragma unroll
-        for (int b = 0; b < 5; ++b) red[((split - 1) * kRoles + role) * 5 + b] = acc[b];
+        for (int co = 0; co < 3; ++co)
+#pragma unroll
+            for (int bb = 0; bb < 5; ++bb) red[((split - 1) * kRoles + role) * 15 + co * 5 + bb] = acc[co][bb];
     }
     __syncthreads();
     if (active && split == 0) {
 #pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            float v = acc[b];
-            for (int s = 0; s < kSplits - 1; ++s) v += red[(s * kRoles + role) * 5 + b];
-            atomicAdd(dw + ((a * 5 + b) * 3 + ci) * 3 + co, v);
-        }
+        for (int co = 0; co < 3; ++co)
+#pragma unroll
+            for (int bb = 0; bb < 5; ++bb) {
+                float v = acc[co][bb];
+                for (int sp = 0; sp < kSplits - 1; ++sp) v += red[(sp * kRoles + role) * 15 + co * 5 + bb];
+                atomicAdd(dw + ((a * 5 + bb) * 3 + ci) * 3 + co, v);
+            }
     }
 }
 
@@ -288,8 +321,10 @@ cconv5_bwd_filter_kernel(const float* __restrict__ x, const float* __restrict__ 
 extern "C" int ni_cconv5_fwd(const float* x, const float* w, float* y, int n, int h, int w_, cudaStream_t st) {
     NI_REQUIRE(x && w && y && n >= 0 && h >= 4 && w_ >= 4, "ni_cconv5_fwd: invalid arguments");
     if (n == 0) return NI_OK;
+    int rc = stage_weights(w, 0, st);
+    if (rc) return rc;
     dim3 grid(ni_cdiv(w_, kTS), ni_cdiv(h, kTS), n);
-    cconv5_fwd_kernel<<<grid, kThreads, 0, st>>>(x, w, y, h, w_);
+    cconv5_fwd_kernel<<<grid, kThreads, 0, st>>>(x, y, h, w_);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
@@ -297,8 +332,10 @@ extern "C" int ni_cconv5_fwd(const float* x, const float* w, float* y, int n, in
 extern "C" int ni_cconv5_bwd_data(const float* dy, const float* w, float* dx, int n, int h, int w_, int accumulate, cudaStream_t st) {
     NI_REQUIRE(dy && w && dx && n >= 0 && h >= 4 && w_ >= 4, "ni_cconv5_bwd_data: invalid arguments");
     if (n == 0) return NI_OK;
+    int rc = stage_weights(w, 1, st);
+    if (rc) return rc;
     dim3 grid(ni_cdiv(w_, kTS), ni_cdiv(h, kTS), n);
-    cconv5_bwd_data_kernel<<<grid, kThreads, 0, st>>>(dy, w, dx, h, w_, accumulate);
+    cconv5_bwd_data_kernel<<<grid, kThreads, 0, st>>>(dy, dx, h, w_, accumulate);
     NI_LAUNCH_CHECK(); NI_COUNT_LAUNCH(1);
     return NI_OK;
 }
