@@ -165,6 +165,10 @@ class FAN(TFModel):
 
     def backward(self, dlogits, need_dx=False):
         """Back-propagate through the saved forward. Parameter gradients -> flat gradient buffer. Returns dx or None."""
+        with nn.deferred_wgrad_join():          # every gradient / activation buffer below is a distinct workspace buffer
+            return self._backward_impl(dlogits, need_dx)
+
+    def _backward_impl(self, dlogits, need_dx=False):
         L, ws, s = _lib.lib(), self._ws, stream()
         acts, descs, (m, h, w, ch, cw) = self._saved
         cur_in = acts['d%d' % (len(self._dense) - 1)] if self._dense else acts['g']

@@ -222,6 +222,10 @@ class UNet(NIPModel):
 
     def _backward(self, dy):
         """dy: gradient w.r.t. the output (B,2h,2w,3); the STE clip passes it through. Parameter grads -> flat buffer."""
+        with nn.deferred_wgrad_join():          # every gradient / activation buffer below is a distinct workspace buffer
+            return self._backward_impl(dy)
+
+    def _backward_impl(self, dy):
         L, ws, s, S = _lib.lib(), self._ws, stream(), self._h.n_steps
         acts, descs, (B, h, w) = self._saved
         # final conv (input dc{S-1}2)

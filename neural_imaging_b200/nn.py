@@ -61,6 +61,28 @@ WGRAD_OVERLAP = os.environ.get('NI_WGRAD_OVERLAP', '1') != '0'
 _SIDE_STREAMS = {}
 
 
+# Deferred join (`with deferred_wgrad_join():`, used by the U-Net and FAN backward passes; NI_WGRAD_DEFER=0 turns it off): inside the block bprop does not join the side stream; the filter gradients queue
+# up on it and run beside EVERYTHING the main stream does until the block ends. Only for backward passes whose gradient and activation
+# buffers are all distinct (U-Net, FAN: one workspace buffer per layer), because a filter gradient still reads its dy and x then.
+WGRAD_DEFER = os.environ.get('NI_WGRAD_DEFER', '1') != '0'
+_DEFER = {'depth': 0, 'pending': None}
+
+
+class deferred_wgrad_join(object):
+    def __enter__(self):
+        if WGRAD_DEFER:
+            _DEFER['depth'] += 1
+        return self
+
+    def __exit__(self, *exc):
+        if WGRAD_DEFER:
+            _DEFER['depth'] -= 1
+            if _DEFER['depth'] == 0 and _DEFER['pending'] is not None:
+                torch.cuda.current_stream().wait_stream(_DEFER['pending'])
+                _DEFER['pending'] = None
+        return False
+
+
 def _side_stream():
     if not WGRAD_OVERLAP or _lib.PROFILER is not None:
         return None
@@ -261,13 +283,16 @@ class Conv2D:
             return self._bprop(x, y, dy, dx, d, **kw)
         finally:
             if self._forked is not None:
-                torch.cuda.current_stream().wait_stream(self._forked)
+                if _DEFER['depth'] > 0:
+                    _DEFER['pending'] = self._forked
+                else:
+                    torch.cuda.current_stream().wait_stream(self._forked)
                 self._forked = None
 
     def _wgrad(self, dd, x, dy, dw, overlap):
         """ni_conv2d_wgrad on the side stream (behind everything queued on the main stream so far) when `overlap`, else in order."""
         L = _lib.lib()
-        side = _side_stream() if overlap else None
+        side = _side_stream() if (overlap or _DEFER['depth'] > 0) else None
         if side is None:
             L.ni_conv2d_wgrad(ctypes.byref(dd), ptr(x), ptr(dy), ptr(dw), stream())
             return
